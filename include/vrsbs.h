@@ -1,0 +1,167 @@
+/*
+ * vrsbs.h — C ABI of the B200-native SBS (side-by-side stereo) warp hot path.
+ *
+ * The reference (Gia-Huynh/VR-Video-Generator) has no FFI/plugin interface for this path: the
+ * boundary is the Python class `SbsProcessor` (PredictAndGenerate.py:63-198) plus the depth tail
+ * of the producer (depth_anything_v2/dpt.py:196-199, PredictAndGenerate.py:27-34,55).  The entry
+ * points below are what a maintainer would bind (ctypes) to replace those
+ * call sites; each one cites the reference lines it replaces.
+ *
+ * Conventions
+ *   - plain C, no C++ types, no exceptions across the boundary; every call returns 0 on success or
+ *     a negative VRSBS_E_* code and records a message retrievable with vrsbs_last_error();
+ *   - "dev" pointers are CUDA device pointers on the context's device, "host" pointers are host
+ *     memory (pinned or pageable); the caller owns every buffer it passes in;
+ *   - calls taking a stream are asynchronous and stream-ordered (stream = a cudaStream_t cast to
+ *     void*, NULL = the legacy default stream); nothing synchronises the host unless stated;
+ *   - a context is NOT thread-safe; use one per (process, device, clip range);
+ *   - frames are uint8 RGB, [H,W,3] row-major (what `left_side_sbs` receives); depth is IEEE fp16
+ *     (the producer's autocast dtype); an SBS frame is [H,2W,3] = [warped view | input frame].
+ *   - there is no CPU fallback: without a CUDA device vrsbs_create fails.
+ */
+#ifndef VRSBS_H
+#define VRSBS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VRSBS_ABI_VERSION 1
+
+enum {
+    VRSBS_OK            = 0,
+    VRSBS_E_INVALID     = -1,  /* bad argument (NULL, size out of the context's limits, ...)        */
+    VRSBS_E_CUDA        = -2,  /* a CUDA runtime call failed; message has cudaGetErrorString        */
+    VRSBS_E_NOMEM       = -3,
+    VRSBS_E_FRAME       = -4,  /* a frame of the batch was rejected on the device: NaN depth (the    */
+                               /* reference raises in math.ceil) or more layers than max_layers    */
+    VRSBS_E_STATE       = -5   /* call order violated (e.g. warp before prepare)                    */
+};
+
+/* per-frame status bits written by the device (vrsbs_frame_info.status) */
+#define VRSBS_FRAME_NAN        1u   /* depth.max() is NaN                                   */
+#define VRSBS_FRAME_OVERFLOW   2u   /* layer count > max_layers                             */
+#define VRSBS_FRAME_GENERIC    4u   /* non-monotone bounds: brute-force membership was used */
+
+typedef struct vrsbs_ctx vrsbs_ctx;
+
+/* Parameters of one clip range.  Mirrors what SbsProcessor.__init__ copies out of `args_god`
+ * (PredictAndGenerate.py:63-100) and the constants it derives. */
+typedef struct vrsbs_params {
+    double offset_fg;          /* --offset_fg        (PredictAndGenerate.py:340, default 0.025)  */
+    double offset_bg;          /* --offset_bg        (PredictAndGenerate.py:342, default -0.01)  */
+    int    offset_step_size;   /* --offset_step_size (PredictAndGenerate.py:344, default 1)      */
+    int    blur;               /* 1 = full path; 0 = stop after hole fill (pre-blur view, strip  */
+                               /*     not restored) — parity tiers T3/T4 only                    */
+} vrsbs_params;
+
+/* What the device decided for one frame (the python lists `get_cutoff` returns, flattened). */
+typedef struct vrsbs_frame_info {
+    uint32_t status;           /* VRSBS_FRAME_* bits                                             */
+    int32_t  layers;           /* L = len(step_list)                                             */
+    int32_t  limit_step;       /* math.ceil(depth.max())                                         */
+    int32_t  fill_layer;       /* int(L*3/5)                                                     */
+    int32_t  strip;            /* columns [0,strip) restored from the input                      */
+    int32_t  reserved;
+    float    depth_max;        /* depth.max() of the smoothed frame                              */
+    float    reserved2;
+    double   offset_range[2];  /* the averaged [bg,fg] pixel range (self.last_offset_range)      */
+    uint64_t holes;            /* number of unpainted destination pixels (before fill)           */
+} vrsbs_frame_info;
+
+int  vrsbs_abi_version(void);
+
+/* Life cycle.  Replaces SbsProcessor.__init__ (PredictAndGenerate.py:63-100): allocates scratch
+ * for frames up to max_h x max_w, batches up to max_batch, tables up to max_layers. */
+int  vrsbs_create(vrsbs_ctx **out, int device, int max_h, int max_w, int max_batch, int max_layers);
+int  vrsbs_destroy(vrsbs_ctx *ctx);
+const char *vrsbs_last_error(const vrsbs_ctx *ctx);   /* ctx may be NULL: last create() failure */
+
+/* Sets offsets/step and forgets depth history + range EMA — what constructing a fresh
+ * SbsProcessor per clip range does (PredictAndGenerate.py:209). */
+int  vrsbs_reset(vrsbs_ctx *ctx, const vrsbs_params *params);
+
+/* The range-EMA half of the clip state (SbsProcessor.last_offset_range, PredictAndGenerate.py:105-108),
+ * readable and writable so a host-side get_cutoff() and the device tables share one state.
+ * has_last = 0 means `last_offset_range is None`.  Both synchronise the device. */
+int  vrsbs_get_range_state(vrsbs_ctx *ctx, int *has_last, double range[2]);
+int  vrsbs_set_range_state(vrsbs_ctx *ctx, int has_last, const double range[2]);
+
+/* Gaussian weights for the hole blur, [ky,kx] row-major fp32, exactly as the caller's torchvision
+ * computes them (torchvision _misc.py:86-98 via PredictAndGenerate.py:191-193).  kx = 2k+3 along W,
+ * ky = 2k+1 along H, k = round(0.0036*H) (PredictAndGenerate.py:165).  Host pointer; copied. */
+int  vrsbs_set_blur_weights(vrsbs_ctx *ctx, const float *weights_host, int kx, int ky);
+
+/* ---- stage 1: depth tail + temporal smoothing + per-frame max --------------------------------
+ * Replaces dpt.py:196 (bicubic, A=-0.75, align_corners=True, fp32 accumulate -> fp16),
+ * PredictAndGenerate.py:55 (`* scaler` in fp16) and SbsProcessor.get_depth's smoothing
+ * (PredictAndGenerate.py:134-144: 0.58*d_t + 0.30*d_{t-1} + 0.12*d_{t-2}, fp16 rounding after every
+ * op, history holds RAW depths), plus the `depth.max()` of get_cutoff (PredictAndGenerate.py:102).
+ * depth_lo_dev  [B,h,w] fp16 DPT output;  depth_out_dev [B,H,W] fp16 smoothed full-res depth.
+ * Frames are consecutive frames of the clip range; history carries over between calls. */
+int  vrsbs_depth_from_lowres(vrsbs_ctx *ctx, const void *depth_lo_dev, int B, int h, int w,
+                             float scaler, int H, int W, void *depth_out_dev, void *stream);
+
+/* Same, but the raw depth is already full resolution ([B,H,W] fp16) — the tensor the reference's
+ * result_queue delivers to get_depth (PredictAndGenerate.py:133). */
+int  vrsbs_depth_from_full(vrsbs_ctx *ctx, const void *depth_raw_dev, int B, int H, int W,
+                           void *depth_out_dev, void *stream);
+
+/* ---- stage 2: layer tables on the device --------------------------------------------------------
+ * Replaces SbsProcessor.get_cutoff (PredictAndGenerate.py:101-126) for the B frames whose maxima
+ * the previous depth call left on the device: ceil(max), EMA of the offset range across frames,
+ * thresholds, sorted, steps, re-rounded offsets, bounds narrowed to fp16, fill layer, strip width.
+ * IEEE double arithmetic in the reference's operation order; no host round trip. */
+int  vrsbs_build_tables(vrsbs_ctx *ctx, int B, int H, int W, void *stream);
+
+/* ---- stage 3: layered warp + hole fill + hole blur + strip + SBS pack -----------------------------
+ * Replaces gpu_roll_with_offset and the body of left_side_sbs (PredictAndGenerate.py:150-155,
+ * 161-197) for B frames.  frames_dev [B,H,W,3] u8, depth_dev [B,H,W] fp16 (output of stage 1),
+ * sbs_dev [B,H,2W,3] u8.  Uses the tables stage 2 left in the context. */
+int  vrsbs_warp_batch(vrsbs_ctx *ctx, const uint8_t *frames_dev, const void *depth_dev,
+                      int B, int H, int W, uint8_t *sbs_dev, void *stream);
+
+/* Stage 1(full-res)+2+3 in one call on device buffers (the "warp stage" bench.py times). */
+int  vrsbs_process_batch(vrsbs_ctx *ctx, const uint8_t *frames_dev, const void *depth_raw_dev,
+                         int B, int H, int W, void *depth_scratch_dev, uint8_t *sbs_dev, void *stream);
+
+/* ---- host-buffer entry: what left_side_sbs does end to end ----------------------------------------
+ * Replaces the H2D copies (PredictAndGenerate.py:133,158), the whole warp and the blocking D2H
+ * (`.cpu().numpy()`, PredictAndGenerate.py:197) for B frames with HOST buffers.  depth_host is
+ * either full-res raw depth [B,H,W] fp16 (lowres_h = lowres_w = 0) or DPT low-res [B,h,w] fp16.
+ * Internally double-buffered: pinned staging + two streams; frames are processed in chunks so
+ * copy-in, kernels and copy-out of neighbouring chunks overlap.  Returns after sbs_host is
+ * complete (like the reference's blocking D2H). */
+int  vrsbs_process_host(vrsbs_ctx *ctx, const uint8_t *frames_host, const void *depth_host,
+                        int B, int H, int W, int lowres_h, int lowres_w, float scaler,
+                        uint8_t *sbs_host);
+
+/* ---- introspection (parity tiers T1..T3, error reporting) ------------------------------------------
+ * All of these synchronise `stream` first. */
+int  vrsbs_get_frame_info(vrsbs_ctx *ctx, int B, vrsbs_frame_info *info_host, void *stream);
+/* Tables of batch frame `frame`: cutoffs [L+1] (double), offsets [L] (int32), bounds lo/hi [L] as
+ * fp16 bit patterns.  Any output pointer may be NULL.  cap = capacity in elements of each array. */
+int  vrsbs_get_tables(vrsbs_ctx *ctx, int frame, int cap, double *cutoffs, int32_t *offsets,
+                      uint16_t *lo_f16, uint16_t *hi_f16, void *stream);
+/* Hole bitmask of the last vrsbs_warp_batch: [B,H,ceil(W/32)] uint32, bit x%32 of word x/32. */
+int  vrsbs_get_hole_mask(vrsbs_ctx *ctx, int B, int H, int W, uint32_t *mask_host, void *stream);
+/* Number of kernels this library has launched on this context (bench.py's gpu_launches). */
+uint64_t vrsbs_launch_count(const vrsbs_ctx *ctx);
+
+/* Per-stage device time (CUDA events recorded on the launching stream around every kernel while the
+ * option "stage_timing" is 1).  Synchronises, then ADDS the elapsed milliseconds of all launches
+ * recorded since the previous call to ms[0..4] = {depth, tables, warp, blur, strip} and the number
+ * of launches to count[0..4]; the caller zeroes the arrays.  bench.py's roofline uses ms[2]. */
+#define VRSBS_NUM_STAGES 5
+int  vrsbs_get_stage_times(vrsbs_ctx *ctx, double ms[VRSBS_NUM_STAGES], uint64_t count[VRSBS_NUM_STAGES]);
+
+/* Tuning knobs (0 = default): scatter mode 1 = plain store + verify/atomicMax, 2 = atomicMax only. */
+int  vrsbs_set_option(vrsbs_ctx *ctx, const char *name, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VRSBS_H */

@@ -1,0 +1,122 @@
+// Shared device helpers for the SBS warp kernels (sm_100a only).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vrsbs.h"
+
+namespace vrsbs {
+
+// ---------------------------------------------------------------------------------------------
+// Per-frame record shared by the table builder (writer) and the warp / blur kernels (readers).
+// ---------------------------------------------------------------------------------------------
+struct FrameTab {
+    int32_t  layers;        // L
+    int32_t  fill_off;      // off[int(L*3/5)] mod W, in [0,W)
+    int32_t  strip;         // columns [0,strip) are restored from the input
+    uint32_t status;        // VRSBS_FRAME_* bits
+    float    guess_scale;   // layer guess = floor(d*scale + bias); exactness never depends on it
+    float    guess_bias;
+    int32_t  limit_step;
+    int32_t  fill_layer;
+    float    depth_max;
+    float    pad;
+    double   range[2];
+    unsigned long long holes;
+};
+
+// Range-EMA state that survives between batches (SbsProcessor.last_offset_range).
+struct RangeState {
+    double range[2];
+    int    has_last;
+    int    pad;
+};
+
+// ---------------------------------------------------------------------------------------------
+// fp16 arithmetic exactly as torch applies it: fp32 opmath, one rounding to fp16 per op.
+// Intrinsics with explicit rounding are never contracted into FMAs by nvcc.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float h2f(__half h) { return __half2float(h); }
+__device__ __forceinline__ __half f2h(float f) { return __float2half_rn(f); }
+
+__device__ __forceinline__ __half smooth3(__half cur, __half p1, __half p2, float w0, float w1, float w2) {
+    __half d = f2h(__fmul_rn(h2f(cur), w0));                // depth *= 0.58
+    __half t = f2h(__fmul_rn(h2f(p1), w1));                 // list[1] * 0.3
+    d = f2h(__fadd_rn(h2f(d), h2f(t)));                     // depth += ...
+    t = f2h(__fmul_rn(h2f(p2), w2));                        // list[0] * 0.12
+    return f2h(__fadd_rn(h2f(d), h2f(t)));
+}
+
+// order-preserving float -> uint32 (so integer atomicMax / redux.max implement a float max)
+__device__ __forceinline__ uint32_t f2ord(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ord2f(uint32_t u) {
+    uint32_t v = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(v);
+#else
+    float f; memcpy(&f, &v, 4); return f;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier + bulk-copy (TMA engine, non-tensor form) PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// shared -> global, tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+                 "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// make generic-proxy smem writes visible to the async proxy (before a bulk store reads them)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__host__ __device__ __forceinline__ int wrap_mod(int v, int n) {
+    v %= n;
+    return v < 0 ? v + n : v;
+}
+__host__ __device__ __forceinline__ int reflect_idx(int i, int n) {
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+    return i;
+}
+__host__ __device__ __forceinline__ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace vrsbs

@@ -1,0 +1,203 @@
+// Stage 1: depth tail (bicubic + scaler), temporal smoothing, per-frame max.
+//
+// Replaces dpt.py:196 (F.interpolate bicubic, align_corners=True), PredictAndGenerate.py:55
+// (`* scaler`), PredictAndGenerate.py:134-144 (smoothing over RAW history) and the depth.max() of
+// PredictAndGenerate.py:102.
+//
+// Layout trick: one thread owns a pixel (or 8 consecutive pixels) for ALL frames of the batch and
+// walks the batch in time order with the two previous raw depths in registers.  The history is
+// therefore read/written once per batch instead of twice per frame, and the only per-frame HBM
+// traffic is "read raw (or low-res taps), write smoothed".
+#pragma once
+#include "common.cuh"
+
+namespace vrsbs {
+
+struct SmoothWeights {
+    float w_now, w_prev1, w_prev2;   // 1-(0.3+0.12), 0.3, 0.3*0.4 as python doubles narrowed to fp32
+};
+
+struct DepthArgs {
+    const __half *raw;        // [B, n] full-res raw depth            (full variant)
+    const __half *lowres;     // [B, h, w] DPT output                 (lowres variant)
+    __half *out;              // [B, n] smoothed
+    __half *hist1;            // [n] raw depth of frame t-1 (state)
+    __half *hist2;            // [n] raw depth of frame t-2 (state)
+    uint32_t *frame_max;      // [B] order-encoded float max, pre-zeroed
+    uint32_t *frame_nan;      // [B] !=0 if the smoothed frame contains a NaN, pre-zeroed
+    SmoothWeights sw;
+    int B, H, W, h, w;
+    int first;                // 1: frame 0 of this call is the first frame of the clip range
+    float scaler;
+    float scale_y, scale_x;   // (h-1)/(H-1), (w-1)/(W-1) in fp32 (area_pixel_compute_scale)
+};
+
+__device__ __forceinline__ void frame_max_commit(uint32_t enc, bool nan, int t, uint32_t *s_max, uint32_t *s_nan) {
+    enc = __reduce_max_sync(0xffffffffu, enc);
+    unsigned any_nan = __ballot_sync(0xffffffffu, nan);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(&s_max[t], enc);
+        if (any_nan) s_nan[t] = 1;
+    }
+}
+
+// ---- full-resolution raw depth in, 8 pixels per thread -------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(256) k_depth_full(DepthArgs a) {
+    extern __shared__ uint32_t s_red[];          // [B] max | [B] nan
+    uint32_t *s_max = s_red, *s_nan = s_red + a.B;
+    for (int i = threadIdx.x; i < 2 * a.B; i += blockDim.x) s_red[i] = 0;
+    __syncthreads();
+
+    const size_t n = (size_t)a.H * a.W;
+    const size_t nvec = (n + VEC - 1) / VEC;
+    const size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = v < nvec;
+    const size_t base = v * VEC;
+
+    __half p1[VEC], p2[VEC], cur[VEC], res[VEC];
+    auto load = [&](const __half *src, __half *dst) {
+        if (VEC == 8 && base + 8 <= n) {
+            *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(src + base);
+        } else {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) dst[e] = (base + e < n) ? src[base + e] : __float2half(0.f);
+        }
+    };
+    auto store = [&](__half *dst, const __half *src) {
+        if (VEC == 8 && base + 8 <= n) {
+            *reinterpret_cast<uint4 *>(dst + base) = *reinterpret_cast<const uint4 *>(src);
+        } else {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e)
+                if (base + e < n) dst[base + e] = src[e];
+        }
+    };
+
+    if (active && !a.first) { load(a.hist1, p1); load(a.hist2, p2); }
+    for (int t = 0; t < a.B; ++t) {
+        uint32_t enc = 0;
+        bool nan = false;
+        if (active) {
+            load(a.raw + (size_t)t * n, cur);
+            if (a.first && t == 0) {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) p1[e] = p2[e] = cur[e];
+            }
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                res[e] = smooth3(cur[e], p1[e], p2[e], a.sw.w_now, a.sw.w_prev1, a.sw.w_prev2);
+                float f = h2f(res[e]);
+                if (base + e < n) {
+                    if (f != f) nan = true; else enc = max(enc, f2ord(f));
+                }
+                p2[e] = p1[e];
+                p1[e] = cur[e];
+            }
+            store(a.out + (size_t)t * n, res);
+        }
+        frame_max_commit(enc, nan, t, s_max, s_nan);
+    }
+    if (active) { store(a.hist1, p1); store(a.hist2, p2); }
+    __syncthreads();
+    for (int t = threadIdx.x; t < a.B; t += blockDim.x) {
+        if (s_max[t]) atomicMax(&a.frame_max[t], s_max[t]);
+        if (s_nan[t]) atomicOr(&a.frame_nan[t], 1u);
+    }
+}
+
+// ---- bicubic coefficients: ATen's cuda/UpSample.cuh arithmetic (A = -0.75) -----------------------
+// `x + 1.0` is evaluated in double and narrowed, as the double literal in the ATen template forces.
+// CONTRACT selects whether mul+add pairs are fused the way nvcc's default -fmad=true fuses them in
+// torch's own binary (1) or kept separate (0); see DESIGN.md "bicubic parity".
+template <bool CONTRACT>
+struct Cubic {
+    static __device__ __forceinline__ float mad(float a, float b, float c) {
+        return CONTRACT ? __fmaf_rn(a, b, c) : __fadd_rn(__fmul_rn(a, b), c);
+    }
+    static __device__ __forceinline__ float conv1(float x) {   // ((A+2)x - (A+3)) x x + 1
+        const float A = -0.75f;
+        float t = mad(A + 2.f, x, -(A + 3.f));
+        return mad(__fmul_rn(t, x), x, 1.f);
+    }
+    static __device__ __forceinline__ float conv2(float x) {   // ((A x - 5A) x + 8A) x - 4A
+        const float A = -0.75f;
+        float t = mad(A, x, -5.f * A);
+        t = mad(t, x, 8.f * A);
+        return mad(t, x, -4.f * A);
+    }
+    static __device__ __forceinline__ void coeffs(float t, float c[4]) {
+        float x2 = (float)(1.0 - (double)t);
+        c[0] = conv2((float)((double)t + 1.0));
+        c[1] = conv1(t);
+        c[2] = conv1(x2);
+        c[3] = conv2((float)((double)x2 + 1.0));
+    }
+    static __device__ __forceinline__ float dot4(float v0, float v1, float v2, float v3, const float c[4]) {
+        float r = __fmul_rn(v0, c[0]);
+        r = mad(v1, c[1], r);
+        r = mad(v2, c[2], r);
+        return mad(v3, c[3], r);
+    }
+};
+
+// ---- low-res DPT output in: bicubic + scaler + smoothing + max, one output pixel per thread ------
+template <bool CONTRACT>
+__global__ void __launch_bounds__(256) k_depth_lowres(DepthArgs a) {
+    extern __shared__ uint32_t s_red[];
+    uint32_t *s_max = s_red, *s_nan = s_red + a.B;
+    for (int i = threadIdx.x; i < 2 * a.B; i += blockDim.x) s_red[i] = 0;
+    __syncthreads();
+
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const bool active = x < a.W && y < a.H;
+    const size_t n = (size_t)a.H * a.W;
+    const size_t pix = (size_t)y * a.W + x;
+
+    float cx[4], cy[4];
+    int ix[4], iy[4];
+    {
+        float rx = __fmul_rn(a.scale_x, (float)x), ry = __fmul_rn(a.scale_y, (float)y);
+        int fx = (int)floorf(rx), fy = (int)floorf(ry);
+        Cubic<CONTRACT>::coeffs(rx - (float)fx, cx);
+        Cubic<CONTRACT>::coeffs(ry - (float)fy, cy);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            ix[k] = max(min(fx - 1 + k, a.w - 1), 0);
+            iy[k] = max(min(fy - 1 + k, a.h - 1), 0) * a.w;
+        }
+    }
+    __half p1 = __float2half(0.f), p2 = p1;
+    if (active && !a.first) { p1 = a.hist1[pix]; p2 = a.hist2[pix]; }
+    for (int t = 0; t < a.B; ++t) {
+        uint32_t enc = 0;
+        bool nan = false;
+        if (active) {
+            const __half *src = a.lowres + (size_t)t * a.h * a.w;
+            float rows[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                rows[k] = Cubic<CONTRACT>::dot4(h2f(__ldg(src + iy[k] + ix[0])), h2f(__ldg(src + iy[k] + ix[1])),
+                                                h2f(__ldg(src + iy[k] + ix[2])), h2f(__ldg(src + iy[k] + ix[3])), cx);
+            __half cur = f2h(Cubic<CONTRACT>::dot4(rows[0], rows[1], rows[2], rows[3], cy));
+            if (a.scaler != 1.0f) cur = f2h(__fmul_rn(h2f(cur), a.scaler));
+            if (a.first && t == 0) p1 = p2 = cur;
+            __half res = smooth3(cur, p1, p2, a.sw.w_now, a.sw.w_prev1, a.sw.w_prev2);
+            a.out[(size_t)t * n + pix] = res;
+            float f = h2f(res);
+            if (f != f) nan = true; else enc = f2ord(f);
+            p2 = p1;
+            p1 = cur;
+        }
+        frame_max_commit(enc, nan, t, s_max, s_nan);
+    }
+    if (active) { a.hist1[pix] = p1; a.hist2[pix] = p2; }
+    __syncthreads();
+    for (int t = threadIdx.x; t < a.B; t += blockDim.x) {
+        if (s_max[t]) atomicMax(&a.frame_max[t], s_max[t]);
+        if (s_nan[t]) atomicOr(&a.frame_nan[t], 1u);
+    }
+}
+
+}  // namespace vrsbs

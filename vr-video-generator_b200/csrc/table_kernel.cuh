@@ -1,0 +1,162 @@
+// Stage 2: SbsProcessor.get_cutoff on the device (PredictAndGenerate.py:101-126) plus the derived
+// per-frame constants of left_side_sbs (fill layer :190, strip width :196, fp16-narrowed bounds :173).
+//
+// One CTA per frame of the batch.  The only cross-frame dependency is the EMA of the offset range
+// (`self.last_offset_range`), a chain of two double adds per frame; every CTA re-walks that chain
+// from the persisted state up to its own frame (B <= a few hundred iterations of trivial work), so
+// no grid-wide ordering is needed.  All arithmetic is IEEE double with explicit-rounding
+// intrinsics (never FMA-contracted), in the reference's python operation order, so the tables are
+// bit-identical to the python lists (parity tier T1).
+#pragma once
+#include "common.cuh"
+
+namespace vrsbs {
+
+struct TableArgs {
+    const uint32_t *frame_max;   // [B] order-encoded max of the smoothed depth
+    const uint32_t *frame_nan;   // [B]
+    const RangeState *state_in;  // EMA state before this batch
+    RangeState *state_out;       // EMA state after this batch (written by the last frame's CTA)
+    FrameTab *tabs;              // [B]
+    float2 *bounds;              // [B][Lcap]   (lo, hi) as floats holding exact fp16 values
+    int *offm;                   // [B][Lcap+1] offsets mod W; slot 0 = fill layer's offset
+    double *cutoffs;             // [B][Lcap+1] cutoff_list (introspection / T1)
+    int *offsets;                // [B][Lcap]   offset_x_list (signed)
+    uint16_t *lo16, *hi16;       // [B][Lcap]   fp16 bit patterns of the bounds
+    double offset_fg, offset_bg;
+    int step, B, H, W, Lcap;
+};
+
+__device__ __forceinline__ double py_round(double v) { return rint(v); }   // round-half-even
+__device__ __forceinline__ int clamp_int(double v) {
+    return v > 2.0e9 ? 2000000000 : (v < -2.0e9 ? -2000000000 : (int)v);
+}
+
+__global__ void __launch_bounds__(256) k_build_tables(TableArgs a) {
+    extern __shared__ double s_val[];          // [Lcap+2] unsorted marks, then [Lcap+2] sorted
+    double *s_sorted = s_val + (a.Lcap + 2);
+    __shared__ double s_r0, s_r1, s_span, s_top;
+    __shared__ int s_limit, s_start, s_nneg, s_E, s_bad;
+    __shared__ float s_max;
+
+    const int b = blockIdx.x;
+    FrameTab *tab = a.tabs + b;
+
+    if (threadIdx.x == 0) {
+        double l0 = a.state_in->range[0], l1 = a.state_in->range[1];
+        int has = a.state_in->has_last;
+        double r0 = 0, r1 = 0;
+        int limit = 0;
+        float fmax = 0.f;
+        for (int t = 0; t <= b; ++t) {
+            fmax = ord2f(a.frame_max[t]);
+            double c = ceil((double)fmax);
+            limit = (a.frame_nan[t] || !(c == c)) ? 0 : clamp_int(c);
+            // bg * H * limit / 14, left to right
+            r0 = __ddiv_rn(__dmul_rn(__dmul_rn(a.offset_bg, (double)a.H), (double)limit), 14.0);
+            r1 = __ddiv_rn(__dmul_rn(__dmul_rn(a.offset_fg, (double)a.H), (double)limit), 14.0);
+            if (has) {
+                r0 = __ddiv_rn(__dadd_rn(l0, r0), 2.0);
+                r1 = __ddiv_rn(__dadd_rn(l1, r1), 2.0);
+            }
+            l0 = r0; l1 = r1; has = 1;
+        }
+        if (b == a.B - 1) {
+            a.state_out->range[0] = r0;
+            a.state_out->range[1] = r1;
+            a.state_out->has_last = 1;
+        }
+        s_r0 = r0; s_r1 = r1; s_limit = limit; s_max = fmax;
+        s_span = __dsub_rn(__dadd_rn(0.00001, r1), r0);       // 0.00001 + r1 - r0
+        s_top = __dadd_rn(0.00001, (double)limit);            // 0.00001 + limit_step
+        int start = clamp_int(py_round(r0)), stop = clamp_int(py_round(r1));
+        long long nneg = start < 0 ? ((long long)(-(long long)start) + a.step - 1) / a.step : 0;   // range(start,0,step)
+        long long npos = stop > 1 ? ((long long)stop - 1 + a.step - 1) / a.step : 0;              // range(1,stop,step)
+        long long E = nneg + 1 + npos + 1;
+        s_bad = (E - 1 > a.Lcap) ? 1 : 0;
+        s_start = start; s_nneg = (int)min(nneg, (long long)a.Lcap);
+        s_E = s_bad ? 2 : (int)E;
+    }
+    __syncthreads();
+    const double r0 = s_r0, span = s_span, top = s_top;
+    const int E = s_E, L = E - 1, nneg = s_bad ? 0 : s_nneg;
+
+    // marks before sorting, in the order the reference appends them
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+        double v;
+        if (e == E - 1) {
+            v = (double)s_limit;
+        } else {
+            int px = (e < nneg) ? s_start + e * a.step : (e == nneg ? 0 : 1 + (e - nneg - 1) * a.step);
+            v = __dmul_rn(__ddiv_rn(__dsub_rn((double)px, r0), span), top);
+        }
+        s_val[e] = v;
+    }
+    __syncthreads();
+    // sorted(): stable rank sort (ties keep append order, as timsort does)
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+        double v = s_val[e];
+        int rank = 0;
+        for (int j = 0; j < E; ++j) {
+            double u = s_val[j];
+            rank += (u < v) || (u == v && j < e);
+        }
+        s_sorted[rank] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_sorted[0] = 0.0;                  // cutoff_list[0] = 0
+    __syncthreads();
+
+    float2 *bounds = a.bounds + (size_t)b * a.Lcap;
+    int *offm = a.offm + (size_t)b * (a.Lcap + 1);
+    int *offs = a.offsets + (size_t)b * a.Lcap;
+    double *cuts = a.cutoffs + (size_t)b * (a.Lcap + 1);
+    for (int e = threadIdx.x; e < E; e += blockDim.x) cuts[e] = s_sorted[e];
+    for (int k = threadIdx.x; k < L; k += blockDim.x) {
+        double c = s_sorted[k], s = __dsub_rn(s_sorted[k + 1], c);
+        // round(c / top * span + r0)
+        int off = clamp_int(py_round(__dadd_rn(__dmul_rn(__ddiv_rn(c, top), span), r0)));
+        // python double -> float -> half (c10::Half has only a float constructor)
+        __half lo = __float2half_rn(__double2float_rn(__dsub_rn(c, __dmul_rn(0.05, s))));
+        __half hi = __float2half_rn(__double2float_rn(__dadd_rn(c, __dmul_rn(1.05, s))));
+        bounds[k] = make_float2(__half2float(lo), __half2float(hi));
+        a.lo16[(size_t)b * a.Lcap + k] = __half_as_ushort(lo);
+        a.hi16[(size_t)b * a.Lcap + k] = __half_as_ushort(hi);
+        offs[k] = off;
+        offm[k + 1] = wrap_mod(off, a.W);
+    }
+    __syncthreads();   // global writes by this CTA are visible to it after the barrier
+    int mono = 1;
+    for (int k = threadIdx.x; k + 1 < L; k += blockDim.x) {
+        float2 p = bounds[k], q = bounds[k + 1];
+        if (!(p.x <= q.x) || !(p.y <= q.y)) mono = 0;
+    }
+    mono = __syncthreads_and(mono);
+    if (threadIdx.x == 0) {
+        int fill = (int)((double)(L * 3) / 5.0);               // int(len(offset_img)*3/5)
+        offm[0] = offm[fill + 1];
+        double sn = py_round(__dmul_rn(__ddiv_rn((double)offs[L - 1], 3.0), 2.0));   // round(offset_x/3*2)
+        int n = clamp_int(sn);
+        int strip = n >= 0 ? min(n, a.W) : max(0, a.W + n);    // python slice 0:n
+        float scale = 0.f, bias = 0.f;
+        if (L >= 3) {
+            float lo1 = bounds[1].x, loN = bounds[L - 1].x;
+            if (loN > lo1) { scale = (float)(L - 2) / (loN - lo1); bias = 1.f - lo1 * scale; }
+        }
+        tab->layers = L;
+        tab->fill_off = offm[0];
+        tab->strip = strip;
+        tab->status = (a.frame_nan[b] ? VRSBS_FRAME_NAN : 0u) | (s_bad ? VRSBS_FRAME_OVERFLOW : 0u) |
+                      (mono ? 0u : VRSBS_FRAME_GENERIC);
+        tab->guess_scale = scale;
+        tab->guess_bias = bias;
+        tab->limit_step = s_limit;
+        tab->fill_layer = fill;
+        tab->depth_max = s_max;
+        tab->range[0] = s_r0;
+        tab->range[1] = s_r1;
+        tab->holes = 0ull;
+    }
+}
+
+}  // namespace vrsbs

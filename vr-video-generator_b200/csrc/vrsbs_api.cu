@@ -1,0 +1,638 @@
+// C ABI of the SBS warp hot path (see include/vrsbs.h for the contract and reference citations).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <thread>
+#include <vector>
+
+#include "blur_kernel.cuh"
+#include "common.cuh"
+#include "depth_kernels.cuh"
+#include "table_kernel.cuh"
+#include "warp_kernel.cuh"
+
+using namespace vrsbs;
+
+namespace {
+
+thread_local char g_create_error[256] = "";
+
+struct Scratch {                 // per-batch device scratch; one per pipeline slot
+    uint32_t *frame_max = nullptr, *frame_nan = nullptr;
+    FrameTab *tabs = nullptr;
+    float2 *bounds = nullptr;
+    int *offm = nullptr;
+    double *cutoffs = nullptr;
+    int *offsets = nullptr;
+    uint16_t *lo16 = nullptr, *hi16 = nullptr;
+    uint32_t *hole_mask = nullptr;
+};
+
+struct HostSlot {                // double-buffered host<->device staging for vrsbs_process_host
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr, state_ready = nullptr;
+    uint8_t *pin_frames = nullptr, *pin_depth = nullptr, *pin_sbs = nullptr;
+    uint8_t *dev_frames = nullptr, *dev_depth_in = nullptr, *dev_depth = nullptr, *dev_sbs = nullptr;
+    size_t cap_frames = 0, cap_depth_in = 0, cap_depth = 0, cap_sbs = 0;
+    bool pin_ok = false;
+};
+
+}  // namespace
+
+struct vrsbs_ctx {
+    int device = 0, max_h = 0, max_w = 0, max_batch = 0, max_layers = 0;
+    int sm_count = 0;
+    vrsbs_params params{0.025, -0.01, 1, 1};
+    SmoothWeights sw{};
+    // clip-range state
+    __half *hist1 = nullptr, *hist2 = nullptr;
+    RangeState *state = nullptr;         // [2], ping-pong
+    int state_idx = 0;
+    long long depth_frames = 0;          // frames pushed through stage 1 since reset
+    int state_h = 0, state_w = 0;
+    // scratch
+    Scratch scratch[2];
+    float *weights = nullptr;
+    int kx = 0, ky = 0;
+    // host pipeline
+    HostSlot slot[2];
+    int host_chunk = 8;
+    int copy_threads = 4;
+    // options / accounting
+    int scatter_mode = 1;
+    int bicubic_contract = 1;
+    int blocks_per_sm = 0;               // 0 = occupancy API
+    uint64_t launches = 0;
+    int stage_timing = 0;
+    struct Stamp { int stage; cudaEvent_t a, b; };
+    std::vector<Stamp> stamps;           // recorded, not yet resolved
+    std::vector<cudaEvent_t> event_pool;
+    char err[256] = "";
+};
+
+namespace {
+
+int fail(vrsbs_ctx *ctx, int code, const char *fmt, ...) {
+    char *dst = ctx ? ctx->err : g_create_error;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 256, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU_TRY(ctx, call)                                                                              \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(ctx, VRSBS_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+template <typename T>
+cudaError_t dmalloc(T **p, size_t count) { return cudaMalloc(reinterpret_cast<void **>(p), count * sizeof(T)); }
+
+void free_scratch(Scratch &s) {
+    cudaFree(s.frame_max); cudaFree(s.frame_nan); cudaFree(s.tabs); cudaFree(s.bounds); cudaFree(s.offm);
+    cudaFree(s.cutoffs); cudaFree(s.offsets); cudaFree(s.lo16); cudaFree(s.hi16); cudaFree(s.hole_mask);
+    s = Scratch{};
+}
+
+int alloc_scratch(vrsbs_ctx *c, Scratch &s) {
+    const size_t B = c->max_batch, L = c->max_layers;
+    const size_t mask_words = B * c->max_h * ((c->max_w + 31) / 32);
+    CU_TRY(c, dmalloc(&s.frame_max, B));
+    CU_TRY(c, dmalloc(&s.frame_nan, B));
+    CU_TRY(c, dmalloc(&s.tabs, B));
+    CU_TRY(c, dmalloc(&s.bounds, B * L));
+    CU_TRY(c, dmalloc(&s.offm, B * (L + 1)));
+    CU_TRY(c, dmalloc(&s.cutoffs, B * (L + 1)));
+    CU_TRY(c, dmalloc(&s.offsets, B * L));
+    CU_TRY(c, dmalloc(&s.lo16, B * L));
+    CU_TRY(c, dmalloc(&s.hi16, B * L));
+    CU_TRY(c, dmalloc(&s.hole_mask, mask_words));
+    return VRSBS_OK;
+}
+
+int check_dims(vrsbs_ctx *c, int B, int H, int W) {
+    if (!c) return VRSBS_E_INVALID;
+    if (B < 1 || B > c->max_batch) return fail(c, VRSBS_E_INVALID, "batch %d outside [1,%d]", B, c->max_batch);
+    if (H < 2 || H > c->max_h || W < 2 || W > c->max_w)
+        return fail(c, VRSBS_E_INVALID, "frame %dx%d outside the context limit %dx%d", H, W, c->max_h, c->max_w);
+    return VRSBS_OK;
+}
+
+// Records an event pair around one kernel launch when stage timing is on.
+struct StageTimer {
+    vrsbs_ctx *c; cudaStream_t st; int stage; cudaEvent_t a = nullptr, b = nullptr;
+    static cudaEvent_t get(vrsbs_ctx *c) {
+        if (!c->event_pool.empty()) { cudaEvent_t e = c->event_pool.back(); c->event_pool.pop_back(); return e; }
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        return e;
+    }
+    StageTimer(vrsbs_ctx *c_, cudaStream_t st_, int stage_) : c(c_), st(st_), stage(stage_) {
+        if (!c->stage_timing) return;
+        a = get(c); b = get(c);
+        if (a) cudaEventRecord(a, st);
+    }
+    ~StageTimer() {
+        if (!a || !b) return;
+        cudaEventRecord(b, st);
+        c->stamps.push_back({stage, a, b});
+    }
+};
+
+// ---- stage launchers (stream-ordered, no host sync) ---------------------------------------------------
+int launch_depth(vrsbs_ctx *c, Scratch &s, const __half *raw, const __half *lowres, int B, int H, int W, int h, int w,
+                 float scaler, __half *out, cudaStream_t st) {
+    if (c->depth_frames > 0 && (c->state_h != H || c->state_w != W))
+        return fail(c, VRSBS_E_STATE, "frame size changed from %dx%d to %dx%d without vrsbs_reset", c->state_h,
+                    c->state_w, H, W);
+    CU_TRY(c, cudaMemsetAsync(s.frame_max, 0, sizeof(uint32_t) * B, st));
+    CU_TRY(c, cudaMemsetAsync(s.frame_nan, 0, sizeof(uint32_t) * B, st));
+    DepthArgs a{};
+    a.raw = raw; a.lowres = lowres; a.out = out; a.hist1 = c->hist1; a.hist2 = c->hist2;
+    a.frame_max = s.frame_max; a.frame_nan = s.frame_nan; a.sw = c->sw;
+    a.B = B; a.H = H; a.W = W; a.h = h; a.w = w; a.first = c->depth_frames == 0; a.scaler = scaler;
+    a.scale_y = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f;
+    a.scale_x = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
+    const size_t smem = sizeof(uint32_t) * 2 * B;
+    const size_t n = (size_t)H * W;
+    StageTimer timer(c, st, 0);
+    if (raw) {
+        const bool vec = (n % 8 == 0) && ((uintptr_t)raw % 16 == 0) && ((uintptr_t)out % 16 == 0);
+        if (vec) {
+            k_depth_full<8><<<(unsigned)((n / 8 + 255) / 256), 256, smem, st>>>(a);
+        } else {
+            k_depth_full<1><<<(unsigned)((n + 255) / 256), 256, smem, st>>>(a);
+        }
+    } else {
+        dim3 grid((W + 31) / 32, (H + 7) / 8);
+        if (c->bicubic_contract) k_depth_lowres<true><<<grid, 256, smem, st>>>(a);
+        else k_depth_lowres<false><<<grid, 256, smem, st>>>(a);
+    }
+    CU_TRY(c, cudaGetLastError());
+    c->launches++;
+    c->depth_frames += B;
+    c->state_h = H; c->state_w = W;
+    return VRSBS_OK;
+}
+
+int launch_tables(vrsbs_ctx *c, Scratch &s, int B, int H, int W, cudaStream_t st) {
+    TableArgs a{};
+    a.frame_max = s.frame_max; a.frame_nan = s.frame_nan;
+    a.state_in = c->state + c->state_idx; a.state_out = c->state + (c->state_idx ^ 1);
+    a.tabs = s.tabs; a.bounds = s.bounds; a.offm = s.offm; a.cutoffs = s.cutoffs; a.offsets = s.offsets;
+    a.lo16 = s.lo16; a.hi16 = s.hi16;
+    a.offset_fg = c->params.offset_fg; a.offset_bg = c->params.offset_bg; a.step = c->params.offset_step_size;
+    a.B = B; a.H = H; a.W = W; a.Lcap = c->max_layers;
+    const size_t smem = sizeof(double) * 2 * (c->max_layers + 2);
+    StageTimer timer(c, st, 1);
+    k_build_tables<<<B, 256, smem, st>>>(a);
+    CU_TRY(c, cudaGetLastError());
+    c->launches++;
+    c->state_idx ^= 1;
+    return VRSBS_OK;
+}
+
+template <int MODE, bool TMA, int NT>
+int launch_warp_inst(vrsbs_ctx *c, const WarpArgs &a, cudaStream_t st) {
+    auto kern = k_warp_rows<MODE, TMA, NT>;
+    const size_t smem = warp_smem_layout(a.W, a.Lcap).total;
+    CU_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = c->blocks_per_sm;
+    if (occ <= 0) CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
+    if (occ < 1) return fail(c, VRSBS_E_INVALID, "warp kernel does not fit: %zu B shared memory", smem);
+    long long rows = (long long)a.B * a.H;
+    long long grid = (long long)c->sm_count * occ;
+    if (grid > rows) grid = rows;
+    StageTimer timer(c, st, 2);
+    kern<<<(unsigned)grid, NT, smem, st>>>(a);
+    CU_TRY(c, cudaGetLastError());
+    c->launches++;
+    return VRSBS_OK;
+}
+
+template <int MODE, bool TMA>
+int launch_warp_nt(vrsbs_ctx *c, const WarpArgs &a, cudaStream_t st) {
+    if (a.W <= 2048) return launch_warp_inst<MODE, TMA, 256>(c, a, st);
+    if (a.W <= 4096) return launch_warp_inst<MODE, TMA, 512>(c, a, st);
+    return launch_warp_inst<MODE, TMA, 1024>(c, a, st);
+}
+
+int launch_warp(vrsbs_ctx *c, Scratch &s, const uint8_t *frames, const __half *depth, int B, int H, int W, uint8_t *sbs,
+                cudaStream_t st) {
+    if (c->params.blur && (c->kx <= 0 || c->ky <= 0))
+        return fail(c, VRSBS_E_STATE, "vrsbs_set_blur_weights must be called before the warp");
+    if (c->params.blur && (c->kx / 2 >= W || c->ky / 2 >= H))
+        return fail(c, VRSBS_E_INVALID, "blur kernel %dx%d too large for a %dx%d frame (reflect padding)", c->kx, c->ky, W, H);
+    WarpArgs a{};
+    a.frames = frames; a.depth = depth; a.sbs = sbs; a.tabs = s.tabs; a.bounds = s.bounds; a.offm = s.offm;
+    a.hole_mask = s.hole_mask; a.B = B; a.H = H; a.W = W; a.Lcap = c->max_layers; a.Wwords = (W + 31) / 32;
+    const bool tma = (W % 16 == 0) && ((uintptr_t)frames % 16 == 0) && ((uintptr_t)depth % 16 == 0) &&
+                     ((uintptr_t)sbs % 16 == 0);
+    int rc;
+    if (c->scatter_mode == 2) rc = tma ? launch_warp_nt<2, true>(c, a, st) : launch_warp_nt<2, false>(c, a, st);
+    else rc = tma ? launch_warp_nt<1, true>(c, a, st) : launch_warp_nt<1, false>(c, a, st);
+    if (rc) return rc;
+    if (!c->params.blur) return VRSBS_OK;
+
+    BlurArgs b{};
+    b.frames = frames; b.sbs = sbs; b.tabs = s.tabs; b.hole_mask = s.hole_mask; b.weights = c->weights;
+    b.B = B; b.H = H; b.W = W; b.Wwords = a.Wwords; b.kx = c->kx; b.ky = c->ky;
+    const long long words = (long long)B * H * a.Wwords;
+    long long blocks = (words + 7) / 8;
+    const long long cap = (long long)c->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    {
+        StageTimer timer(c, st, 3);
+        k_blur_holes<<<(unsigned)blocks, 256, sizeof(double) * c->kx * c->ky, st>>>(b);
+    }
+    CU_TRY(c, cudaGetLastError());
+    c->launches++;
+    long long rblocks = ((long long)B * H + 7) / 8;
+    if (rblocks > cap) rblocks = cap;
+    {
+        StageTimer timer(c, st, 4);
+        k_strip_restore<<<(unsigned)rblocks, 256, 0, st>>>(b);
+    }
+    CU_TRY(c, cudaGetLastError());
+    c->launches++;
+    return VRSBS_OK;
+}
+
+void parallel_memcpy(void *dst, const void *src, size_t bytes, int nthreads) {
+    if (bytes < (8u << 20) || nthreads <= 1) { memcpy(dst, src, bytes); return; }
+    std::vector<std::thread> th;
+    const size_t part = align_up((bytes + nthreads - 1) / nthreads, 4096);
+    for (int i = 0; i < nthreads; ++i) {
+        const size_t off = (size_t)i * part;
+        if (off >= bytes) break;
+        const size_t len = bytes - off < part ? bytes - off : part;
+        th.emplace_back([=] { memcpy((char *)dst + off, (const char *)src + off, len); });
+    }
+    for (auto &t : th) t.join();
+}
+
+bool is_pinned(const void *p) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+int ensure_slot(vrsbs_ctx *c, HostSlot &s, size_t frames_b, size_t depth_in_b, size_t depth_b, size_t sbs_b) {
+    if (!s.stream) {
+        CU_TRY(c, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CU_TRY(c, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        CU_TRY(c, cudaEventCreateWithFlags(&s.state_ready, cudaEventDisableTiming));
+    }
+    auto grow = [&](uint8_t *&dev, uint8_t **pin, size_t &cap, size_t need) -> cudaError_t {
+        if (need <= cap) return cudaSuccess;
+        cudaFree(dev); dev = nullptr;
+        if (pin) { cudaFreeHost(*pin); *pin = nullptr; }
+        cap = 0;
+        cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&dev), need);
+        if (e != cudaSuccess) return e;
+        if (pin) { e = cudaHostAlloc(reinterpret_cast<void **>(pin), need, cudaHostAllocDefault); if (e != cudaSuccess) return e; }
+        cap = need;
+        return cudaSuccess;
+    };
+    CU_TRY(c, grow(s.dev_frames, &s.pin_frames, s.cap_frames, frames_b));
+    CU_TRY(c, grow(s.dev_depth_in, &s.pin_depth, s.cap_depth_in, depth_in_b));
+    CU_TRY(c, grow(s.dev_depth, nullptr, s.cap_depth, depth_b));
+    CU_TRY(c, grow(s.dev_sbs, &s.pin_sbs, s.cap_sbs, sbs_b));
+    return VRSBS_OK;
+}
+
+void free_slot(HostSlot &s) {
+    if (s.stream) cudaStreamDestroy(s.stream);
+    if (s.done) cudaEventDestroy(s.done);
+    if (s.state_ready) cudaEventDestroy(s.state_ready);
+    cudaFree(s.dev_frames); cudaFree(s.dev_depth_in); cudaFree(s.dev_depth); cudaFree(s.dev_sbs);
+    cudaFreeHost(s.pin_frames); cudaFreeHost(s.pin_depth); cudaFreeHost(s.pin_sbs);
+    s = HostSlot{};
+}
+
+int frame_status_error(vrsbs_ctx *c, const FrameTab *tabs, int B, int first_index) {
+    for (int i = 0; i < B; ++i) {
+        if (tabs[i].status & VRSBS_FRAME_NAN)
+            return fail(c, VRSBS_E_FRAME, "frame %d: depth.max() is NaN (the reference raises in math.ceil)", first_index + i);
+        if (tabs[i].status & VRSBS_FRAME_OVERFLOW)
+            return fail(c, VRSBS_E_FRAME, "frame %d: layer count exceeds max_layers=%d (limit_step=%d)", first_index + i,
+                        c->max_layers, tabs[i].limit_step);
+    }
+    return VRSBS_OK;
+}
+
+}  // namespace
+
+// =========================================================================================================
+extern "C" {
+
+int vrsbs_abi_version(void) { return VRSBS_ABI_VERSION; }
+
+const char *vrsbs_last_error(const vrsbs_ctx *ctx) { return ctx ? ctx->err : g_create_error; }
+
+int vrsbs_create(vrsbs_ctx **out, int device, int max_h, int max_w, int max_batch, int max_layers) {
+    if (!out) return fail(nullptr, VRSBS_E_INVALID, "out is NULL");
+    *out = nullptr;
+    if (max_h < 2 || max_w < 2 || max_w > 8192 || max_batch < 1 || max_layers < 1 || max_layers > 4096)
+        return fail(nullptr, VRSBS_E_INVALID, "limits out of range (max_w <= 8192, max_layers <= 4096)");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, VRSBS_E_CUDA, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, VRSBS_E_INVALID, "device %d of %d", device, ndev);
+    DeviceGuard g(device);
+    if (!g.ok) return fail(nullptr, VRSBS_E_CUDA, "cudaSetDevice(%d) failed", device);
+    cudaDeviceProp prop{};
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+        return fail(nullptr, VRSBS_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, VRSBS_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                    prop.minor);
+    vrsbs_ctx *c = new (std::nothrow) vrsbs_ctx();
+    if (!c) return fail(nullptr, VRSBS_E_NOMEM, "out of host memory");
+    c->device = device; c->max_h = max_h; c->max_w = max_w; c->max_batch = max_batch; c->max_layers = max_layers;
+    c->sm_count = prop.multiProcessorCount;
+    auto init = [&]() -> int {
+        const size_t n = (size_t)max_h * max_w;
+        CU_TRY(c, dmalloc(&c->hist1, n));
+        CU_TRY(c, dmalloc(&c->hist2, n));
+        CU_TRY(c, dmalloc(&c->state, 2));
+        int rc = alloc_scratch(c, c->scratch[0]);
+        if (rc) return rc;
+        vrsbs_params p = c->params;
+        return vrsbs_reset(c, &p);
+    };
+    int rc = init();
+    if (rc) {
+        snprintf(g_create_error, sizeof g_create_error, "%s", c->err);
+        vrsbs_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return VRSBS_OK;
+}
+
+int vrsbs_destroy(vrsbs_ctx *c) {
+    if (!c) return VRSBS_OK;
+    DeviceGuard g(c->device);
+    cudaDeviceSynchronize();
+    cudaFree(c->hist1); cudaFree(c->hist2); cudaFree(c->state); cudaFree(c->weights);
+    free_scratch(c->scratch[0]); free_scratch(c->scratch[1]);
+    free_slot(c->slot[0]); free_slot(c->slot[1]);
+    for (auto &s : c->stamps) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    for (auto e : c->event_pool) cudaEventDestroy(e);
+    delete c;
+    return VRSBS_OK;
+}
+
+int vrsbs_reset(vrsbs_ctx *c, const vrsbs_params *p) {
+    if (!c) return VRSBS_E_INVALID;
+    DeviceGuard g(c->device);
+    if (p) {
+        if (p->offset_step_size < 1) return fail(c, VRSBS_E_INVALID, "offset_step_size must be >= 1");
+        c->params = *p;
+    }
+    // SbsProcessor.__init__: t = 0.3; sum += t; t *= 0.4 (twice); weight of the current frame = 1 - sum
+    double t = 0.3, acc = 0.0, taps[2];
+    for (int i = 0; i < 2; ++i) { acc = acc + t; taps[i] = t; t = t * 0.4; }
+    c->sw.w_now = (float)(1 - acc);
+    c->sw.w_prev1 = (float)taps[0];
+    c->sw.w_prev2 = (float)taps[1];
+    CU_TRY(c, cudaDeviceSynchronize());
+    CU_TRY(c, cudaMemset(c->state, 0, sizeof(RangeState) * 2));
+    c->state_idx = 0;
+    c->depth_frames = 0;
+    c->state_h = c->state_w = 0;
+    return VRSBS_OK;
+}
+
+int vrsbs_get_range_state(vrsbs_ctx *c, int *has_last, double range[2]) {
+    if (!c || !has_last || !range) return fail(c, VRSBS_E_INVALID, "NULL argument");
+    DeviceGuard g(c->device);
+    CU_TRY(c, cudaDeviceSynchronize());
+    RangeState st;
+    CU_TRY(c, cudaMemcpy(&st, c->state + c->state_idx, sizeof st, cudaMemcpyDeviceToHost));
+    *has_last = st.has_last; range[0] = st.range[0]; range[1] = st.range[1];
+    return VRSBS_OK;
+}
+
+int vrsbs_set_range_state(vrsbs_ctx *c, int has_last, const double range[2]) {
+    if (!c || (has_last && !range)) return fail(c, VRSBS_E_INVALID, "NULL argument");
+    DeviceGuard g(c->device);
+    CU_TRY(c, cudaDeviceSynchronize());
+    RangeState st{};
+    st.has_last = has_last ? 1 : 0;
+    if (has_last) { st.range[0] = range[0]; st.range[1] = range[1]; }
+    CU_TRY(c, cudaMemcpy(c->state + c->state_idx, &st, sizeof st, cudaMemcpyHostToDevice));
+    return VRSBS_OK;
+}
+
+int vrsbs_set_blur_weights(vrsbs_ctx *c, const float *w, int kx, int ky) {
+    if (!c || !w || kx < 1 || ky < 1 || kx > 255 || ky > 255 || !(kx & 1) || !(ky & 1))
+        return fail(c, VRSBS_E_INVALID, "bad blur kernel %dx%d", kx, ky);
+    DeviceGuard g(c->device);
+    CU_TRY(c, cudaDeviceSynchronize());
+    cudaFree(c->weights); c->weights = nullptr;
+    CU_TRY(c, dmalloc(&c->weights, (size_t)kx * ky));
+    CU_TRY(c, cudaMemcpy(c->weights, w, sizeof(float) * kx * ky, cudaMemcpyHostToDevice));
+    c->kx = kx; c->ky = ky;
+    return VRSBS_OK;
+}
+
+int vrsbs_depth_from_lowres(vrsbs_ctx *c, const void *lo, int B, int h, int w, float scaler, int H, int W, void *out,
+                            void *stream) {
+    int rc = check_dims(c, B, H, W);
+    if (rc) return rc;
+    if (!lo || !out || h < 1 || w < 1) return fail(c, VRSBS_E_INVALID, "bad low-res depth arguments");
+    DeviceGuard g(c->device);
+    return launch_depth(c, c->scratch[0], nullptr, (const __half *)lo, B, H, W, h, w, scaler, (__half *)out,
+                        (cudaStream_t)stream);
+}
+
+int vrsbs_depth_from_full(vrsbs_ctx *c, const void *raw, int B, int H, int W, void *out, void *stream) {
+    int rc = check_dims(c, B, H, W);
+    if (rc) return rc;
+    if (!raw || !out) return fail(c, VRSBS_E_INVALID, "NULL depth pointer");
+    DeviceGuard g(c->device);
+    return launch_depth(c, c->scratch[0], (const __half *)raw, nullptr, B, H, W, 0, 0, 1.f, (__half *)out,
+                        (cudaStream_t)stream);
+}
+
+int vrsbs_build_tables(vrsbs_ctx *c, int B, int H, int W, void *stream) {
+    int rc = check_dims(c, B, H, W);
+    if (rc) return rc;
+    DeviceGuard g(c->device);
+    return launch_tables(c, c->scratch[0], B, H, W, (cudaStream_t)stream);
+}
+
+int vrsbs_warp_batch(vrsbs_ctx *c, const uint8_t *frames, const void *depth, int B, int H, int W, uint8_t *sbs, void *stream) {
+    int rc = check_dims(c, B, H, W);
+    if (rc) return rc;
+    if (!frames || !depth || !sbs) return fail(c, VRSBS_E_INVALID, "NULL buffer");
+    DeviceGuard g(c->device);
+    return launch_warp(c, c->scratch[0], frames, (const __half *)depth, B, H, W, sbs, (cudaStream_t)stream);
+}
+
+int vrsbs_process_batch(vrsbs_ctx *c, const uint8_t *frames, const void *raw, int B, int H, int W, void *depth_scratch,
+                        uint8_t *sbs, void *stream) {
+    int rc = check_dims(c, B, H, W);
+    if (rc) return rc;
+    if (!frames || !raw || !depth_scratch || !sbs) return fail(c, VRSBS_E_INVALID, "NULL buffer");
+    DeviceGuard g(c->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    Scratch &s = c->scratch[0];
+    if ((rc = launch_depth(c, s, (const __half *)raw, nullptr, B, H, W, 0, 0, 1.f, (__half *)depth_scratch, st))) return rc;
+    if ((rc = launch_tables(c, s, B, H, W, st))) return rc;
+    return launch_warp(c, s, frames, (const __half *)depth_scratch, B, H, W, sbs, st);
+}
+
+int vrsbs_process_host(vrsbs_ctx *c, const uint8_t *frames, const void *depth, int B, int H, int W, int lh, int lw,
+                       float scaler, uint8_t *sbs) {
+    if (!c) return VRSBS_E_INVALID;
+    if (B < 1) return fail(c, VRSBS_E_INVALID, "batch %d", B);
+    int rc = check_dims(c, 1, H, W);
+    if (rc) return rc;
+    if (!frames || !depth || !sbs) return fail(c, VRSBS_E_INVALID, "NULL buffer");
+    const bool lowres = lh > 0 && lw > 0;
+    DeviceGuard g(c->device);
+    int chunk = c->host_chunk < c->max_batch ? c->host_chunk : c->max_batch;
+    if (chunk < 1) chunk = 1;
+    const size_t fb = (size_t)H * W * 3, sb = fb * 2, db = (size_t)H * W * 2;
+    const size_t dib = lowres ? (size_t)lh * lw * 2 : db;
+    if (!c->scratch[1].tabs && (rc = alloc_scratch(c, c->scratch[1]))) return rc;
+    for (int i = 0; i < 2; ++i)
+        if ((rc = ensure_slot(c, c->slot[i], fb * chunk, dib * chunk, db * chunk, sb * chunk))) return rc;
+    const bool pin_f = is_pinned(frames), pin_d = is_pinned(depth), pin_s = is_pinned(sbs);
+
+    std::vector<FrameTab> tabs(chunk);
+    int nchunks = (B + chunk - 1) / chunk;
+    int pending_n[2] = {0, 0}, pending_first[2] = {0, 0};
+    auto drain = [&](int si) -> int {     // wait for slot si's chunk, deliver its output, check status
+        HostSlot &s = c->slot[si];
+        if (!pending_n[si]) return VRSBS_OK;
+        CU_TRY(c, cudaEventSynchronize(s.done));
+        const int n = pending_n[si], first = pending_first[si];
+        if (!pin_s) parallel_memcpy(sbs + (size_t)first * sb, s.pin_sbs, sb * n, c->copy_threads);
+        CU_TRY(c, cudaMemcpy(tabs.data(), c->scratch[si].tabs, sizeof(FrameTab) * n, cudaMemcpyDeviceToHost));
+        pending_n[si] = 0;
+        return frame_status_error(c, tabs.data(), n, first);
+    };
+    for (int ci = 0; ci < nchunks; ++ci) {
+        const int si = ci & 1, first = ci * chunk, n = (B - first < chunk) ? B - first : chunk;
+        HostSlot &s = c->slot[si];
+        if ((rc = drain(si))) return rc;
+        const uint8_t *hf = frames + (size_t)first * fb;
+        const uint8_t *hd = (const uint8_t *)depth + (size_t)first * dib;
+        if (!pin_f) { parallel_memcpy(s.pin_frames, hf, fb * n, c->copy_threads); hf = s.pin_frames; }
+        if (!pin_d) { parallel_memcpy(s.pin_depth, hd, dib * n, c->copy_threads); hd = s.pin_depth; }
+        CU_TRY(c, cudaMemcpyAsync(s.dev_frames, hf, fb * n, cudaMemcpyHostToDevice, s.stream));
+        CU_TRY(c, cudaMemcpyAsync(s.dev_depth_in, hd, dib * n, cudaMemcpyHostToDevice, s.stream));
+        // stage 1/2 carry clip-range state from the previous chunk, which ran on the other stream
+        if (ci > 0) CU_TRY(c, cudaStreamWaitEvent(s.stream, c->slot[si ^ 1].state_ready, 0));
+        Scratch &sc = c->scratch[si];
+        if (lowres) rc = launch_depth(c, sc, nullptr, (const __half *)s.dev_depth_in, n, H, W, lh, lw, scaler, (__half *)s.dev_depth, s.stream);
+        else rc = launch_depth(c, sc, (const __half *)s.dev_depth_in, nullptr, n, H, W, 0, 0, 1.f, (__half *)s.dev_depth, s.stream);
+        if (rc) return rc;
+        if ((rc = launch_tables(c, sc, n, H, W, s.stream))) return rc;
+        CU_TRY(c, cudaEventRecord(s.state_ready, s.stream));
+        if ((rc = launch_warp(c, sc, s.dev_frames, (const __half *)s.dev_depth, n, H, W, s.dev_sbs, s.stream))) return rc;
+        uint8_t *ho = pin_s ? sbs + (size_t)first * sb : s.pin_sbs;
+        CU_TRY(c, cudaMemcpyAsync(ho, s.dev_sbs, sb * n, cudaMemcpyDeviceToHost, s.stream));
+        CU_TRY(c, cudaEventRecord(s.done, s.stream));
+        pending_n[si] = n; pending_first[si] = first;
+    }
+    // drain in submission order
+    const int last = (nchunks - 1) & 1;
+    if (nchunks > 1 && (rc = drain(last ^ 1))) return rc;
+    return drain(last);
+}
+
+int vrsbs_get_frame_info(vrsbs_ctx *c, int B, vrsbs_frame_info *info, void *stream) {
+    if (!c || !info || B < 1 || B > c->max_batch) return fail(c, VRSBS_E_INVALID, "bad arguments");
+    DeviceGuard g(c->device);
+    CU_TRY(c, cudaStreamSynchronize((cudaStream_t)stream));
+    std::vector<FrameTab> tabs(B);
+    CU_TRY(c, cudaMemcpy(tabs.data(), c->scratch[0].tabs, sizeof(FrameTab) * B, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < B; ++i) {
+        vrsbs_frame_info &o = info[i];
+        memset(&o, 0, sizeof o);
+        o.status = tabs[i].status; o.layers = tabs[i].layers; o.limit_step = tabs[i].limit_step;
+        o.fill_layer = tabs[i].fill_layer; o.strip = tabs[i].strip; o.depth_max = tabs[i].depth_max;
+        o.offset_range[0] = tabs[i].range[0]; o.offset_range[1] = tabs[i].range[1]; o.holes = tabs[i].holes;
+    }
+    return frame_status_error(c, tabs.data(), B, 0);
+}
+
+int vrsbs_get_tables(vrsbs_ctx *c, int frame, int cap, double *cutoffs, int32_t *offsets, uint16_t *lo, uint16_t *hi,
+                     void *stream) {
+    if (!c || frame < 0 || frame >= c->max_batch) return fail(c, VRSBS_E_INVALID, "bad frame index");
+    DeviceGuard g(c->device);
+    CU_TRY(c, cudaStreamSynchronize((cudaStream_t)stream));
+    FrameTab t;
+    Scratch &s = c->scratch[0];
+    CU_TRY(c, cudaMemcpy(&t, s.tabs + frame, sizeof t, cudaMemcpyDeviceToHost));
+    const int L = t.layers, Lc = c->max_layers;
+    if (cap < L + 1) return fail(c, VRSBS_E_INVALID, "capacity %d < L+1 = %d", cap, L + 1);
+    if (cutoffs) CU_TRY(c, cudaMemcpy(cutoffs, s.cutoffs + (size_t)frame * (Lc + 1), sizeof(double) * (L + 1), cudaMemcpyDeviceToHost));
+    if (offsets) CU_TRY(c, cudaMemcpy(offsets, s.offsets + (size_t)frame * Lc, sizeof(int32_t) * L, cudaMemcpyDeviceToHost));
+    if (lo) CU_TRY(c, cudaMemcpy(lo, s.lo16 + (size_t)frame * Lc, sizeof(uint16_t) * L, cudaMemcpyDeviceToHost));
+    if (hi) CU_TRY(c, cudaMemcpy(hi, s.hi16 + (size_t)frame * Lc, sizeof(uint16_t) * L, cudaMemcpyDeviceToHost));
+    return L;
+}
+
+int vrsbs_get_hole_mask(vrsbs_ctx *c, int B, int H, int W, uint32_t *mask, void *stream) {
+    int rc = check_dims(c, B, H, W);
+    if (rc) return rc;
+    if (!mask) return fail(c, VRSBS_E_INVALID, "NULL mask");
+    DeviceGuard g(c->device);
+    CU_TRY(c, cudaStreamSynchronize((cudaStream_t)stream));
+    CU_TRY(c, cudaMemcpy(mask, c->scratch[0].hole_mask, sizeof(uint32_t) * B * H * ((W + 31) / 32), cudaMemcpyDeviceToHost));
+    return VRSBS_OK;
+}
+
+int vrsbs_get_stage_times(vrsbs_ctx *c, double ms[VRSBS_NUM_STAGES], uint64_t count[VRSBS_NUM_STAGES]) {
+    if (!c || !ms || !count) return fail(c, VRSBS_E_INVALID, "NULL argument");
+    DeviceGuard g(c->device);
+    CU_TRY(c, cudaDeviceSynchronize());
+    for (auto &s : c->stamps) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, s.a, s.b) == cudaSuccess && s.stage >= 0 && s.stage < VRSBS_NUM_STAGES) {
+            ms[s.stage] += t;
+            count[s.stage] += 1;
+        }
+        c->event_pool.push_back(s.a);
+        c->event_pool.push_back(s.b);
+    }
+    c->stamps.clear();
+    return VRSBS_OK;
+}
+
+uint64_t vrsbs_launch_count(const vrsbs_ctx *c) { return c ? c->launches : 0; }
+
+int vrsbs_set_option(vrsbs_ctx *c, const char *name, int value) {
+    if (!c || !name) return VRSBS_E_INVALID;
+    if (!strcmp(name, "scatter_mode")) { if (value != 1 && value != 2) return fail(c, VRSBS_E_INVALID, "scatter_mode 1|2"); c->scatter_mode = value; }
+    else if (!strcmp(name, "bicubic_contract")) c->bicubic_contract = value != 0;
+    else if (!strcmp(name, "blocks_per_sm")) c->blocks_per_sm = value < 0 ? 0 : value;
+    else if (!strcmp(name, "host_chunk")) { if (value < 1) return fail(c, VRSBS_E_INVALID, "host_chunk >= 1"); c->host_chunk = value; }
+    else if (!strcmp(name, "stage_timing")) c->stage_timing = value != 0;
+    else if (!strcmp(name, "copy_threads")) c->copy_threads = value < 1 ? 1 : value;
+    else return fail(c, VRSBS_E_INVALID, "unknown option %s", name);
+    return VRSBS_OK;
+}
+
+}  // extern "C"

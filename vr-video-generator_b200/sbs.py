@@ -1,0 +1,175 @@
+"""Drop-in `SbsProcessor` backed by the sm_100a CUDA library (no CPU fallback).
+
+Mirrors the reference class (PredictAndGenerate.py:63-198): same constructor, `add_frame`,
+`get_depth`, `get_cutoff`, `left_side_sbs`, same parameters read from `args_god`
+(`offset_fg`, `offset_bg`, `offset_step_size`), same per-instance clip-range state (two raw
+depth frames of history + the previous offset range).  Batched / device-resident entry points are
+additions (`left_side_sbs_batch`, `warp_batch_device`).
+
+PyTorch is used for device memory and streams only.
+"""
+import numpy as np
+import torch
+
+from . import _native, tables
+
+DEFAULT_MAX_LAYERS = 512
+
+
+class SbsProcessor:
+    def __init__(self, gpu_notify_queue, gpu_notify_worker_idx, args_god, debug_config=[None],
+                 device=None, max_batch=64, max_layers=DEFAULT_MAX_LAYERS):
+        self.debug_filePrefix = debug_config[0]
+        self.gpu_notify_queue = gpu_notify_queue
+        self.gpu_notify_worker_idx = gpu_notify_worker_idx
+        self.args_god = args_god
+        self.offset_step_size = args_god.offset_step_size
+        self.offset_bg = args_god.offset_bg
+        self.offset_fg = args_god.offset_fg
+        self.sigmaboi = 3
+        self.depth_dampening_count = 2
+        self.depth_dampening_ratio = 0.4
+        self.depth_dampening_initial_value = 0.3
+        self.depth_dampening_original_ratio, _ = tables.smoothing_weights(
+            self.depth_dampening_count, self.depth_dampening_initial_value, self.depth_dampening_ratio)
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("vr-video-generator_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.max_batch, self.max_layers = max_batch, max_layers
+        self._ctx = None
+        self._shape = None          # (H, W) the context was created for
+        self._blur = True
+
+    # ------------------------------------------------------------------------------------------
+    def _context(self, H, W):
+        if self._ctx is None or self._shape != (H, W):
+            if self._ctx is not None:
+                self._ctx.close()
+            self._ctx = _native.Context(self.device.index, H, W, self.max_batch, self.max_layers)
+            self._ctx.reset(self.offset_fg, self.offset_bg, self.offset_step_size, self._blur)
+            kx, ky = tables.blur_kernel_shape(H)
+            self._ctx.set_blur_weights(tables.gaussian_weights(kx, ky, float(self.sigmaboi)))
+            self._shape = (H, W)
+        return self._ctx
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def close(self):
+        if self._ctx is not None:
+            self._ctx.close()
+            self._ctx = None
+
+    def reset_state(self):
+        """Forget depth history and range EMA (what a new reference SbsProcessor starts with)."""
+        if self._ctx is not None:
+            self._ctx.reset(self.offset_fg, self.offset_bg, self.offset_step_size, self._blur)
+
+    @property
+    def last_offset_range(self):
+        return None if self._ctx is None else self._ctx.get_range_state()
+
+    @last_offset_range.setter
+    def last_offset_range(self, value):
+        if self._ctx is None:
+            raise RuntimeError("no frame size known yet; process a frame or call _context(H, W) first")
+        self._ctx.set_range_state(value)
+
+    # ---- the reference's entry points -------------------------------------------------------
+    def add_frame(self, raw_img, job_queue, result_queue):
+        """Ask the depth producer for this frame (PredictAndGenerate.py:127-129)."""
+        self.gpu_notify_queue.put((self.gpu_notify_worker_idx,))
+        job_queue.put((raw_img,))
+
+    def get_depth(self, raw_img, job_queue, result_queue):
+        """Pop the producer's raw depth and return the temporally smoothed depth as a CUDA fp16
+        tensor [H,W] (PredictAndGenerate.py:131-145).  Advances the depth history."""
+        raw = result_queue.get()
+        return self._smooth(self._raw_to_device(raw))[0]
+
+    def get_cutoff(self, depth):
+        """Python lists exactly like the reference's get_cutoff (PredictAndGenerate.py:101-126);
+        updates the shared range state."""
+        ctx = self._context(depth.shape[0], depth.shape[1])
+        out = tables.layer_tables(float(depth.max()), depth.shape[0], self.offset_fg, self.offset_bg,
+                                  self.offset_step_size, ctx.get_range_state())
+        ctx.set_range_state(out[1])
+        return out
+
+    def left_side_sbs(self, raw_img, job_queue, result_queue):
+        """numpy [H,W,3] uint8 RGB -> numpy [H,2W,3] uint8 SBS frame (PredictAndGenerate.py:157-198)."""
+        H, W, _ = raw_img.shape
+        ctx = self._context(H, W)
+        with torch.cuda.device(self.device):
+            img = torch.from_numpy(np.ascontiguousarray(raw_img)).to(self.device, non_blocking=True)
+            raw = result_queue.get()
+            depth = self._smooth(self._raw_to_device(raw))
+            st = self._stream()
+            ctx.build_tables(1, H, W, st)
+            sbs = torch.empty((1, H, 2 * W, 3), dtype=torch.uint8, device=self.device)
+            ctx.warp_batch(img.data_ptr(), depth.data_ptr(), 1, H, W, sbs.data_ptr(), st)
+            out = sbs[0].cpu().numpy()           # blocking D2H, like the reference
+            ctx.frame_info(1, st)                # raises if the device rejected the frame
+        return out
+
+    # ---- batched additions ---------------------------------------------------------------------
+    def left_side_sbs_batch(self, frames, depths, scaler=1.0, out=None):
+        """Host-buffer batch: frames [B,H,W,3] uint8 and depths [B,H,W] fp16 (raw, full-res) or
+        [B,h,w] fp16 (DPT low-res; bicubic + `scaler` applied on the device).  numpy arrays or CPU
+        tensors, pinned or pageable.  Returns numpy [B,H,2W,3].  Pipelined (pinned double buffering)."""
+        f = _as_numpy(frames)
+        d = _as_numpy(depths)
+        if d.dtype != np.float16:
+            raise TypeError(f"depth must be float16 (the producer's autocast dtype), got {d.dtype}")
+        B, H, W, _ = f.shape
+        lowres = d.shape[1:] != (H, W)
+        ctx = self._context(H, W)
+        if out is None:
+            out = np.empty((B, H, 2 * W, 3), dtype=np.uint8)
+        ctx.process_host(f.ctypes.data, d.ctypes.data, B, H, W, d.shape[1] if lowres else 0,
+                         d.shape[2] if lowres else 0, float(scaler), out.ctypes.data)
+        return out
+
+    def warp_batch_device(self, frames, raw_depth, out=None, depth_scratch=None):
+        """Device-resident batch on the current stream, asynchronous: frames [B,H,W,3] uint8 CUDA,
+        raw_depth [B,H,W] fp16 CUDA (raw, full-res) -> sbs [B,H,2W,3] uint8 CUDA."""
+        B, H, W, _ = frames.shape
+        ctx = self._context(H, W)
+        if out is None:
+            out = torch.empty((B, H, 2 * W, 3), dtype=torch.uint8, device=self.device)
+        if depth_scratch is None:
+            depth_scratch = torch.empty((B, H, W), dtype=torch.float16, device=self.device)
+        _check_cuda(frames, torch.uint8), _check_cuda(raw_depth, torch.float16)
+        ctx.process_batch(frames.data_ptr(), raw_depth.data_ptr(), B, H, W, depth_scratch.data_ptr(),
+                          out.data_ptr(), self._stream())
+        return out
+
+    # ---- helpers ---------------------------------------------------------------------------------
+    def _raw_to_device(self, raw):
+        if isinstance(raw, np.ndarray):
+            raw = torch.from_numpy(raw)
+        if raw.dtype != torch.float16:
+            raise TypeError(f"depth must be float16 (the producer's autocast dtype), got {raw.dtype}")
+        return raw.to(self.device, non_blocking=True).contiguous()
+
+    def _smooth(self, raw_dev):
+        """raw_dev [H,W] or [B,H,W] fp16 CUDA -> smoothed [B,H,W]; leaves the frame maxima on the device."""
+        if raw_dev.dim() == 2:
+            raw_dev = raw_dev[None]
+        B, H, W = raw_dev.shape
+        ctx = self._context(H, W)
+        out = torch.empty_like(raw_dev)
+        ctx.depth_from_full(raw_dev.data_ptr(), B, H, W, out.data_ptr(), self._stream())
+        return out
+
+
+def _as_numpy(x):
+    if isinstance(x, torch.Tensor):
+        x = x.numpy()
+    return np.ascontiguousarray(x)
+
+
+def _check_cuda(t, dtype):
+    if not (t.is_cuda and t.is_contiguous() and t.dtype == dtype):
+        raise TypeError(f"expected a contiguous CUDA {dtype} tensor")

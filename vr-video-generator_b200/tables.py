@@ -1,0 +1,93 @@
+"""Host-side mirror of the scalar logic of the reference's SbsProcessor (no tensors, no CUDA).
+
+Used by the drop-in `SbsProcessor.get_cutoff` (which, like the reference, returns python lists)
+and by the tests that pin the device-side table builder (csrc/table_kernel.cuh) — parity tier T1.
+Every expression keeps the reference's operation order, because the results are compared as
+exact doubles.  Reference: PredictAndGenerate.py:63-126,165,190-196.
+"""
+import math
+
+
+def smoothing_weights(count=2, initial=0.3, ratio=0.4):
+    """(weight of the current frame, [weight of t-1, weight of t-2, ...]) — PredictAndGenerate.py:70-80."""
+    t, total, taps = initial, 0, []
+    for _ in range(count):
+        total = total + t
+        taps.append(t)
+        t = t * ratio
+    return 1 - total, taps
+
+
+def fix_offset_signs(offset_fg, offset_bg):
+    """The CLI's same-sign fix-up (PredictAndGenerate.py:387-393)."""
+    if offset_bg * offset_fg > 0:
+        if offset_bg >= 0:
+            offset_bg = offset_bg * (-1)
+        else:
+            offset_fg = offset_fg * (-1)
+    return offset_fg, offset_bg
+
+
+def layer_tables(depth_max, height, offset_fg, offset_bg, step, last_range):
+    """get_cutoff's arithmetic (PredictAndGenerate.py:101-126).
+
+    Returns (cutoff_list, offset_range, step_list, limit_step, offset_x_list); the caller stores
+    offset_range as the next `last_range`."""
+    limit_step = math.ceil(depth_max)
+    offset_range = [offset_bg * height * limit_step / 14, offset_fg * height * limit_step / 14]
+    if last_range is not None:
+        offset_range = [(last_range[0] + offset_range[0]) / 2, (last_range[1] + offset_range[1]) / 2]
+    near, far = offset_range[0], offset_range[1]
+    width = 0.00001 + far - near
+    ceiling = 0.00001 + limit_step
+    pixels = list(range(round(near), 0, step)) + [0] + list(range(1, round(far), step))
+    cutoff_list = [(px - near) / width * ceiling for px in pixels]
+    cutoff_list.append(limit_step)
+    cutoff_list = sorted(cutoff_list)
+    cutoff_list[0] = 0
+    step_list = [cutoff_list[i + 1] - cutoff_list[i] for i in range(len(cutoff_list) - 1)]
+    offset_x_list = [round(cutoff_list[i] / ceiling * width + near) for i in range(len(step_list))]
+    return cutoff_list, offset_range, step_list, limit_step, offset_x_list
+
+
+def layer_bounds(cutoff_list, step_list):
+    """Python-double [lo, hi) of every layer before narrowing to the depth dtype (:173)."""
+    return ([c - 0.05 * s for c, s in zip(cutoff_list, step_list)],
+            [c + 1.05 * s for c, s in zip(cutoff_list, step_list)])
+
+
+def fill_layer(num_layers):
+    return int(num_layers * 3 / 5)                                 # PredictAndGenerate.py:190
+
+
+def strip_columns(last_offset, width):
+    n = round(last_offset / 3 * 2)                                 # PredictAndGenerate.py:196
+    return max(0, min(width, n if n >= 0 else width + n))          # python slice 0:n
+
+
+def blur_kernel_shape(height):
+    """(kx, ky) handed to gaussian_blur: (2k+3, 2k+1), k = round(0.0036*H) (:165,:192)."""
+    k = round(0.0036 * height)
+    return k * 2 + 3, k * 2 + 1
+
+
+def gaussian_weights(kx, ky, sigma=3.0):
+    """fp32 [ky,kx] kernel exactly as torchvision 0.26 `_get_gaussian_kernel2d` builds it on the
+    CPU (same torch ops, same order): softmax(-(linspace(-lim,lim,k)/sigma)^2), outer product."""
+    import torch
+
+    def one(n):
+        lim = (n - 1) / (2.0 * math.sqrt(2.0))
+        x = torch.linspace(-lim, lim, steps=n, dtype=torch.float32)
+        return torch.softmax(x.div(sigma).pow(2).neg(), dim=0)
+
+    return (one(ky).unsqueeze(-1) * one(kx)).contiguous().numpy()
+
+
+def clip_ranges(start_frame, end_frame, video_length, num_workers):
+    """main_func's shard split (PredictAndGenerate.py:274-275,303): list of (begin, end)."""
+    stop = min(end_frame, video_length)
+    if stop <= start_frame or num_workers < 1:
+        return []
+    step = math.ceil((stop - start_frame) / num_workers)
+    return [(b, min(end_frame, b + step)) for b in range(start_frame, stop, step)]
