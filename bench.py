@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py — SBS frames/sec of the warp stage on B200 (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A "step" is one pass of the hot path over one batch of synthetic frames + depth maps:
+temporal depth smoothing + per-frame max, layer tables, layered warp, hole fill + blur, strip, SBS
+pack.  `value` = frames/s with inputs resident in HBM (the device-pointer C ABI), `e2e` = the same
+metric through `SbsProcessor.left_side_sbs_batch` with pinned HOST buffers (H2D + D2H in the timed
+region).  `--impl reference` times the CPU port of the reference's algorithm (oracle/sbs_layered.py,
+all host cores) on a bounded sample of the same workload.  For N > 1 launch under torchrun; every rank
+owns its own clip range (independent shards, no collective in the data path).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: 1080p, 64-frame batch, code-default offsets, step 1 (the metric's config)
+    "1080p_b64": dict(H=1080, W=1920, B=64, fg=0.025, bg=-0.01, step=1, depth="scene"),
+    # configs[0]: the reference's own CPU-runnable case
+    "1080p_b16_cfg1": dict(H=1080, W=1920, B=16, fg=0.025, bg=-0.015, step=1, depth="scene"),
+    # configs[2]: 4K, wide disparity
+    "4k_wide_b16": dict(H=2160, W=3840, B=16, fg=0.05, bg=-0.03, step=1, depth="scene"),
+    # configs[3]: step 2 banded sweep
+    "1080p_step2_b64": dict(H=1080, W=1920, B=64, fg=0.025, bg=-0.01, step=2, depth="scene"),
+    # scatter / blur stress (19 % holes)
+    "1080p_stress_b64": dict(H=1080, W=1920, B=64, fg=0.025, bg=-0.015, step=1, depth="stress"),
+}
+METRIC = "sbs_frames_per_sec_warp_stage"
+UNIT = "frames/s"
+
+
+def algorithmic_bytes(H, W):
+    """SURVEY.md section 8d, A_warp: fp16 full-res depth + RGB frame read once, SBS frame written once."""
+    return H * W * 2 + H * W * 3 + H * 2 * W * 3
+
+
+def measured_hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_inputs(wl, seed):
+    """Seeded synthetic batch: noise frames [B,H,W,3] u8 and D-scene/D-stress low-res depth [B,518,924]."""
+    from vr_video_generator_b200 import synth
+    frames = synth.frames_noise(wl["B"], wl["H"], wl["W"], seed)
+    lowres = synth.depth_lowres(wl["depth"], wl["B"], synth.DPT_H, synth.DPT_W, seed)
+    return frames, lowres
+
+
+def dist_setup():
+    """(rank, world, barrier, reduce_max) via vr_video_generator_b200.shard.Ranks (NCCL under torchrun)."""
+    import torch
+
+    from vr_video_generator_b200 import shard
+    rank, world, local = shard.world_from_env()
+    cuda = torch.cuda.is_available()
+    if cuda:
+        torch.cuda.set_device(local)
+    r = shard.Ranks(backend="nccl" if cuda else "gloo", device=f"cuda:{local}" if cuda else "cpu")
+    return r.rank, r.world, r.barrier, r.max
+
+
+# ---------------------------------------------------------------------------------------------------------
+def run_ours(args, wl, name):
+    import torch
+
+    import vr_video_generator_b200 as pkg
+    from vr_video_generator_b200 import _native, tables
+
+    rank, world, barrier, reduce_max = dist_setup()
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback in the product path)"
+    dev = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(dev)
+    H, W, B = wl["H"], wl["W"], wl["B"]
+    frames_h, lowres_h = make_inputs(wl, seed=100 + rank)        # every rank = its own clip range
+
+    ctx = _native.Context(dev, H, W, B, 512)
+    ctx.reset(wl["fg"], wl["bg"], wl["step"], True)
+    ctx.set_blur_weights(tables.gaussian_weights(*tables.blur_kernel_shape(H)))
+    if args.scatter_mode:
+        ctx.set_option("scatter_mode", args.scatter_mode)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # device-resident inputs: frames + RAW full-res fp16 depth (what SbsProcessor.get_depth receives),
+    # produced once, untimed, by the library's own depth tail from the low-res synthetic DPT maps
+    frames_d = torch.from_numpy(frames_h).cuda()
+    lowres_d = torch.from_numpy(lowres_h).cuda()
+    raw_d = torch.empty((B, H, W), dtype=torch.float16, device="cuda")
+    prep = _native.Context(dev, H, W, 1, 64)
+    for t in range(B):                                            # B=1 with a fresh clip each: raw depth, not smoothed
+        prep.reset(wl["fg"], wl["bg"], wl["step"], False)
+        prep.depth_from_lowres(lowres_d[t].data_ptr(), 1, lowres_h.shape[1], lowres_h.shape[2], 1.0, H, W,
+                               raw_d[t].data_ptr(), stream)
+        # first frame of a clip: smoothed = 0.58d + 0.3d + 0.12d != d in fp16; good enough as "raw" input
+    torch.cuda.synchronize()
+    prep.close()
+    raw_h = raw_d.cpu().numpy()
+    scratch_d = torch.empty_like(raw_d)
+    sbs_d = torch.empty((B, H, 2 * W, 3), dtype=torch.uint8, device="cuda")
+
+    def step():
+        ctx.process_batch(frames_d.data_ptr(), raw_d.data_ptr(), B, H, W, scratch_d.data_ptr(), sbs_d.data_ptr(), stream)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    infos = ctx.frame_info(B, stream)
+    ctx.stage_times()
+    ctx.set_option("stage_timing", 1)
+    launches0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(dev)
+    clocks.__enter__()                       # sampled over the device-timed region AND the e2e region
+    time.sleep(0.25)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    ms_total = reduce_max(e0.elapsed_time(e1))
+    stage = ctx.stage_times()
+    ctx.set_option("stage_timing", 0)
+    launches = ctx.launch_count() - launches0
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    # roofline of the dominant kernel (k_warp_rows): algorithmic bytes per launch / mean launch duration
+    warp_ms, warp_n = stage["warp"]
+    peak, peak_src = measured_hbm_peak()
+    abytes = algorithmic_bytes(H, W) * B
+    achieved = abytes / (warp_ms / max(warp_n, 1) * 1e-3) / 1e9 if warp_n else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(name)
+
+    # end to end: the public batch API with pinned host buffers (H2D + D2H inside the timed region)
+    ns = argparse.Namespace(offset_fg=wl["fg"], offset_bg=wl["bg"], offset_step_size=wl["step"])
+    proc = pkg.SbsProcessor(None, 0, ns, device=dev, max_batch=16)
+    f_pin = torch.from_numpy(frames_h).pin_memory()
+    d_pin = torch.from_numpy(raw_h).pin_memory()
+    o_pin = torch.empty((B, H, 2 * W, 3), dtype=torch.uint8).pin_memory()
+    o_np = o_pin.numpy()
+    for _ in range(max(1, min(args.warmup, 3))):
+        proc.left_side_sbs_batch(f_pin, d_pin, out=o_np)
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    for _ in range(e2e_steps):
+        proc.left_side_sbs_batch(f_pin, d_pin, out=o_np)
+    torch.cuda.synchronize()
+    e2e_s = reduce_max(time.perf_counter() - t0)
+    barrier()
+    clocks.__exit__()
+    e2e = {"value": world * B * e2e_steps / e2e_s, "unit": UNIT,
+           "h2d_bytes_per_step": int(frames_h.nbytes + raw_h.nbytes), "d2h_bytes_per_step": int(o_np.nbytes),
+           "steps": e2e_steps, "api": "SbsProcessor.left_side_sbs_batch (vrsbs_process_host), pinned buffers"}
+    same = bool(np.array_equal(o_np[0], sbs_d[0].cpu().numpy())) if e2e_steps else None
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_port_fps(wl, frames_h, raw_h, budget_s=args.cpu_budget)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8 pixels / fp16 depth compares / f64 table+blur accumulate", "data": "synthetic",
+            "config": {"workload": f"{name}: {W}x{H}, {B}-frame batch per GPU, fg={wl['fg']} bg={wl['bg']} step={wl['step']}, "
+                                   f"D-{wl['depth']} depth (limit_step {infos[0].limit_step}, {infos[0].layers} layers, "
+                                   f"{100.0 * infos[0].holes / (H * W):.2f}% holes)",
+                       "timed_region": "depth smoothing+max, device tables, warp, hole blur, strip, SBS pack; inputs/outputs in HBM",
+                       "l2": f"inputs per step {int((frames_h.nbytes + raw_h.nbytes) / 2**20)} MiB + outputs "
+                             f"{int(o_np.nbytes / 2**20)} MiB per GPU > 126 MB L2 (no flush needed)",
+                       "sharding": "independent clip range per GPU, no collective", "scatter_mode": args.scatter_mode or 1},
+            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_warp_rows", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": abytes, "launch_ms": warp_ms / max(warp_n, 1)},
+            "stage_ms_per_step": {k: v[0] / args.steps for k, v in stage.items()},
+            "e2e_equals_device_output": same,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    ctx.close()
+    proc.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+def _cpu_worker(job):
+    from oracle import sbs_layered as O
+    img, depth, marks, steps, offsets, weights = job
+    return O.warp_frame(img, depth, marks, steps, offsets, weights)[0, 0, 0]
+
+
+def cpu_port_fps(wl, frames, raw, budget_s=20.0, procs=None):
+    """The reference's algorithm on the host cores: oracle/sbs_layered.py (numpy layer loop, a port —
+    the Python reference itself cannot travel to the GPU box).  Smoothing + tables run serially (they
+    carry state), the per-frame warp — >99 % of the time — runs one frame per process."""
+    import multiprocessing as mp
+
+    from oracle import sbs_layered as O
+    cores = os.cpu_count() or 1
+    procs = procs or cores
+    st = O.WarpState(wl["fg"], wl["bg"], wl["step"])
+    weights = O.gaussian_weights(*O.blur_kernel_shape(wl["H"]))
+    # calibrate on one frame, then size the sample to the budget
+    d = O.smooth_depth(st, raw[0])
+    tabs = O.layer_tables(st, d.max(), d.shape[0])
+    t0 = time.perf_counter()
+    O.warp_frame(frames[0], d, tabs[0], tabs[1], tabs[2], weights)
+    one = time.perf_counter() - t0
+    n = int(max(procs, min(len(frames) - 1, procs * max(1, int(budget_s / max(one, 1e-3))))))
+    n = min(n, len(frames) - 1)
+    jobs = []
+    t0 = time.perf_counter()
+    for t in range(1, 1 + n):
+        d = O.smooth_depth(st, raw[t])
+        tabs = O.layer_tables(st, d.max(), d.shape[0])
+        jobs.append((frames[t], d, tabs[0], tabs[1], tabs[2], weights))
+    with mp.get_context("fork").Pool(min(procs, n)) as pool:
+        pool.map(_cpu_worker, jobs, chunksize=1)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": min(procs, n), "kind": "port",
+            "sample": f"{n} frames of the same workload ({wl['W']}x{wl['H']}), oracle/sbs_layered.py numpy layer loop, "
+                      f"one frame per process on {min(procs, n)} of {cores} host cores; single-frame latency {one:.2f} s"}
+
+
+def run_reference(args, wl, name):
+    """--impl reference: the CPU port of the reference's warp on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = min(wl["B"], 1 + (os.cpu_count() or 1) * 4)
+    sub = dict(wl, B=B)
+    frames, lowres = make_inputs(sub, seed=100)
+    from oracle import sbs_layered as O
+    raw = np.stack([O.bicubic_resize(lowres[t], wl["H"], wl["W"], 1.0) for t in range(B)])
+    vals = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_port_fps(sub, frames, raw, budget_s=args.cpu_budget / max(1, args.steps))
+        if i >= args.warmup:
+            vals.append(r)
+    v = float(np.mean([r["value"] for r in vals]))
+    n_frames = sum(int(r["sample"].split()[0]) for r in vals)
+    cpu = dict(vals[-1], value=v)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_frames / max(v, 1e-9) / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 pixels / fp16 depth", "data": "synthetic",
+        "config": {"workload": f"{name}: {wl['W']}x{wl['H']}, fg={wl['fg']} bg={wl['bg']} step={wl['step']}, D-{wl['depth']} depth; "
+                               f"each step = a bounded sample of the batch on the host CPU"},
+        "cpu_baseline": cpu, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="1080p_b64", choices=sorted(WORKLOADS))
+    ap.add_argument("--scatter-mode", type=int, default=0)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl, args.workload)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_ours(args, wl, args.workload)
+
+
+if __name__ == "__main__":
+    main()

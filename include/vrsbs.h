@@ -158,7 +158,9 @@ uint64_t vrsbs_launch_count(const vrsbs_ctx *ctx);
 #define VRSBS_NUM_STAGES 5
 int  vrsbs_get_stage_times(vrsbs_ctx *ctx, double ms[VRSBS_NUM_STAGES], uint64_t count[VRSBS_NUM_STAGES]);
 
-/* Tuning knobs (0 = default): scatter mode 1 = plain store + verify/atomicMax, 2 = atomicMax only. */
+/* Tuning knobs: "scatter_mode" 2 (default) = shared-memory atomicMax for every key, 1 = plain store +
+ * verify + atomicMax on conflicts; "bicubic_contract", "blocks_per_sm", "host_chunk", "copy_threads",
+ * "stage_timing". */
 int  vrsbs_set_option(vrsbs_ctx *ctx, const char *name, int value);
 
 #ifdef __cplusplus

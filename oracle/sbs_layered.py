@@ -283,7 +283,7 @@ def bicubic_resize(lowres, H, W, scaler=1.0):
     out = rows[0] * cy[0][:, None]
     for a in range(1, 4):
         out = out + rows[a] * cy[a][:, None]
-    out16 = out.astype(F16)
+    out16 = np.ascontiguousarray(out, dtype=F16)
     if scaler != 1.0:
-        out16 = _mul_scalar_f16(out16, scaler)
+        out16 = np.ascontiguousarray(_mul_scalar_f16(out16, scaler))
     return out16

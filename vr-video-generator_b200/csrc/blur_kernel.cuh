@@ -2,12 +2,15 @@
 //
 // The reference blurs the whole filled frame with a (2k+1)x(2k+3) fp32 gaussian (torchvision
 // gaussian_blur: reflect padding, one depthwise conv, round_) and keeps the result only at hole
-// pixels.  Here only hole pixels are evaluated.  The pre-blur image is reconstructed on the fly:
+// pixels.  Here only hole pixels are evaluated, tile by tile, and only tiles that contain holes are
+// visited: the warp kernel appends every 16x64 tile in which it found a hole to a work list.
+//
+// The pre-blur image is reconstructed while a tile (+ halo) is staged in shared memory:
 //     hole neighbour     -> img[y, (x - fill_off) mod W]   (what the hole fill wrote, :190)
 //     painted neighbour  -> the view the warp kernel already stored in the SBS frame
-// so blurred pixels can be written in place (a hole's stored value is never read).  The strip
-// columns [0,strip) keep their pre-blur values until k_strip_restore runs, because holes right of
-// the strip need them as neighbours.
+// so blurred pixels can be written in place (a hole's stored value is never read by anyone).  The
+// strip columns [0,strip) keep their pre-blur values until k_strip_restore runs, because holes right
+// of the strip need them as neighbours.
 //
 // Accumulation is fp64 FMA over the fp32 weights: exact for u8 pixels (no summation-order
 // dependence), then round-half-even like round_().  See DESIGN.md "blur parity".
@@ -16,57 +19,93 @@
 
 namespace vrsbs {
 
+constexpr int kTileH = 16, kTileW = 64;       // blur work unit; kTileW is a multiple of 32 (mask words)
+
 struct BlurArgs {
     const uint8_t *frames;       // [B,H,W,3]
     uint8_t *sbs;                // [B,H,2W,3]
     const FrameTab *tabs;        // [B]
     const uint32_t *hole_mask;   // [B][H][Wwords]
     const float *weights;        // [ky][kx]
-    int B, H, W, Wwords, kx, ky;
+    const uint32_t *tile_list;   // tiles that contain at least one hole (linear tile ids)
+    const uint32_t *tile_count;  // number of entries in tile_list
+    int B, H, W, Wwords, kx, ky, tiles_x, tiles_y;
 };
 
-__global__ void __launch_bounds__(256) k_blur_holes(BlurArgs a) {
-    extern __shared__ double s_w[];                          // [ky*kx]
-    for (int i = threadIdx.x; i < a.kx * a.ky; i += blockDim.x) s_w[i] = (double)a.weights[i];
-    __syncthreads();
+__host__ __device__ inline size_t blur_smem_bytes(int kx, int ky) {
+    const size_t sw = kTileW + kx - 1, sh = kTileH + ky - 1;
+    return sizeof(double) * kx * ky + sizeof(float) * 3 * sw * sh + sizeof(uint16_t) * kTileH * kTileW + 16;
+}
 
-    const int lane = threadIdx.x & 31;
-    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-    const long long total = (long long)a.B * a.H * a.Wwords;
-    const int W = a.W, H = a.H;
-    for (long long g = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < total; g += nwarps) {
-        const uint32_t m = a.hole_mask[g];
-        if (m == 0) continue;
-        const int wx = (int)(g % a.Wwords);
-        const long long by = g / a.Wwords;
-        const int y = (int)(by % H), b = (int)(by / H);
-        const int x = wx * 32 + lane;
+__global__ void __launch_bounds__(256) k_blur_tiles(BlurArgs a) {
+    extern __shared__ __align__(16) uint8_t blur_smem[];
+    const int kx = a.kx, ky = a.ky, W = a.W, H = a.H;
+    const int sw = kTileW + kx - 1, sh = kTileH + ky - 1, plane = sw * sh;
+    double *s_w = reinterpret_cast<double *>(blur_smem);
+    float *s_px = reinterpret_cast<float *>(s_w + kx * ky);              // [3][sh][sw]
+    uint16_t *s_list = reinterpret_cast<uint16_t *>(s_px + 3 * plane);   // (ly << 8) | lx
+    __shared__ int s_n;
+
+    for (int i = threadIdx.x; i < kx * ky; i += blockDim.x) s_w[i] = (double)a.weights[i];
+    const uint32_t ntiles = *a.tile_count;
+
+    for (uint32_t ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
+        const uint32_t tile = a.tile_list[ti];
+        const int tx = tile % a.tiles_x, ty = (tile / a.tiles_x) % a.tiles_y, b = tile / (a.tiles_x * a.tiles_y);
+        const int x0 = tx * kTileW, y0 = ty * kTileH;
         const FrameTab *t = a.tabs + b;
-        if (!((m >> lane) & 1u) || x < t->strip || x >= W) continue;
-        const int fill = t->fill_off;
-        double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
-        for (int i = 0; i < a.ky; ++i) {
-            const int yy = reflect_idx(y + i - a.ky / 2, H);
-            const size_t rb = (size_t)b * H + yy;
-            const uint32_t *mrow = a.hole_mask + rb * a.Wwords;
-            const uint8_t *view = a.sbs + rb * (size_t)W * 6;
-            const uint8_t *src = a.frames + rb * (size_t)W * 3;
-            for (int j = 0; j < a.kx; ++j) {
-                const int xx = reflect_idx(x + j - a.kx / 2, W);
-                const bool hole = (mrow[xx >> 5] >> (xx & 31)) & 1u;
-                int xs = xx - fill;
-                xs += (xs < 0) ? W : 0;
-                const uint8_t *p = hole ? src + 3 * xs : view + 3 * xx;
-                const double w = s_w[i * a.kx + j];
-                acc0 = fma(w, (double)p[0], acc0);
-                acc1 = fma(w, (double)p[1], acc1);
-                acc2 = fma(w, (double)p[2], acc2);
+        const int fill = t->fill_off, strip = t->strip;
+        const size_t frame_row0 = (size_t)b * H;
+        __syncthreads();                       // previous tile fully consumed (also orders s_w on the first pass)
+        if (threadIdx.x == 0) s_n = 0;
+        // ---- stage the pre-blur tile + halo as floats, channel-planar ----
+        for (int p = threadIdx.x; p < plane; p += blockDim.x) {
+            const int ly = p / sw, lx = p - ly * sw;
+            const int yy = reflect_idx(y0 + ly - ky / 2, H), xx = reflect_idx(x0 + lx - kx / 2, W);
+            const size_t rb = frame_row0 + yy;
+            const bool hole = (a.hole_mask[rb * a.Wwords + (xx >> 5)] >> (xx & 31)) & 1u;
+            int xs = xx - fill;
+            xs += (xs < 0) ? W : 0;
+            const uint8_t *src = hole ? a.frames + (rb * W + xs) * 3 : a.sbs + (rb * 2 * W + xx) * 3;
+            s_px[p] = (float)src[0];
+            s_px[plane + p] = (float)src[1];
+            s_px[2 * plane + p] = (float)src[2];
+        }
+        __syncthreads();
+        // ---- list the hole pixels of this tile (right of the strip, inside the frame) ----
+        for (int q = threadIdx.x; q < kTileH * (kTileW / 8); q += blockDim.x) {
+            const int ly = q / (kTileW / 8), cx = (q % (kTileW / 8)) * 8;
+            const int y = y0 + ly, x = x0 + cx;
+            if (y >= H || x >= W) continue;
+            uint32_t bits = (a.hole_mask[(frame_row0 + y) * a.Wwords + (x >> 5)] >> (x & 31)) & 0xffu;
+            while (bits) {
+                const int k = __ffs(bits) - 1;
+                bits &= bits - 1;
+                if (x + k >= strip && x + k < W) s_list[atomicAdd(&s_n, 1)] = (uint16_t)((ly << 8) | (cx + k));
             }
         }
-        uint8_t *o = a.sbs + ((size_t)b * H + y) * (size_t)W * 6 + 3 * x;
-        o[0] = (uint8_t)__double2int_rn(acc0);
-        o[1] = (uint8_t)__double2int_rn(acc1);
-        o[2] = (uint8_t)__double2int_rn(acc2);
+        __syncthreads();
+        const int n = s_n;
+        // ---- one thread per hole pixel: ky*kx taps x 3 channels, exact fp64 accumulation ----
+        for (int h = threadIdx.x; h < n; h += blockDim.x) {
+            const int ly = s_list[h] >> 8, lx = s_list[h] & 0xff;
+            const float *p0 = s_px + ly * sw + lx;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+            for (int i = 0; i < ky; ++i) {
+                const float *row = p0 + i * sw;
+                const double *wrow = s_w + i * kx;
+                for (int j = 0; j < kx; ++j) {
+                    const double w = wrow[j];
+                    a0 = fma(w, (double)row[j], a0);
+                    a1 = fma(w, (double)row[plane + j], a1);
+                    a2 = fma(w, (double)row[2 * plane + j], a2);
+                }
+            }
+            uint8_t *o = a.sbs + ((frame_row0 + y0 + ly) * 2 * W + x0 + lx) * 3;
+            o[0] = (uint8_t)__double2int_rn(a0);
+            o[1] = (uint8_t)__double2int_rn(a1);
+            o[2] = (uint8_t)__double2int_rn(a2);
+        }
     }
 }
 

@@ -27,6 +27,9 @@ struct Scratch {                 // per-batch device scratch; one per pipeline s
     int *offsets = nullptr;
     uint16_t *lo16 = nullptr, *hi16 = nullptr;
     uint32_t *hole_mask = nullptr;
+    uint32_t *tile_flag = nullptr;   // [tiles + 1]: flags, then the list counter in the last word
+    uint32_t *tile_list = nullptr;
+    size_t tiles_cap = 0;
 };
 
 struct HostSlot {                // double-buffered host<->device staging for vrsbs_process_host
@@ -60,7 +63,7 @@ struct vrsbs_ctx {
     int host_chunk = 8;
     int copy_threads = 4;
     // options / accounting
-    int scatter_mode = 1;
+    int scatter_mode = 2;
     int bicubic_contract = 1;
     int blocks_per_sm = 0;               // 0 = occupancy API
     uint64_t launches = 0;
@@ -105,6 +108,7 @@ cudaError_t dmalloc(T **p, size_t count) { return cudaMalloc(reinterpret_cast<vo
 void free_scratch(Scratch &s) {
     cudaFree(s.frame_max); cudaFree(s.frame_nan); cudaFree(s.tabs); cudaFree(s.bounds); cudaFree(s.offm);
     cudaFree(s.cutoffs); cudaFree(s.offsets); cudaFree(s.lo16); cudaFree(s.hi16); cudaFree(s.hole_mask);
+    cudaFree(s.tile_flag); cudaFree(s.tile_list);
     s = Scratch{};
 }
 
@@ -121,6 +125,9 @@ int alloc_scratch(vrsbs_ctx *c, Scratch &s) {
     CU_TRY(c, dmalloc(&s.lo16, B * L));
     CU_TRY(c, dmalloc(&s.hi16, B * L));
     CU_TRY(c, dmalloc(&s.hole_mask, mask_words));
+    s.tiles_cap = B * ((c->max_h + kTileH - 1) / kTileH) * ((c->max_w + kTileW - 1) / kTileW);
+    CU_TRY(c, dmalloc(&s.tile_flag, s.tiles_cap + 1));
+    CU_TRY(c, dmalloc(&s.tile_list, s.tiles_cap));
     return VRSBS_OK;
 }
 
@@ -240,6 +247,13 @@ int launch_warp(vrsbs_ctx *c, Scratch &s, const uint8_t *frames, const __half *d
     WarpArgs a{};
     a.frames = frames; a.depth = depth; a.sbs = sbs; a.tabs = s.tabs; a.bounds = s.bounds; a.offm = s.offm;
     a.hole_mask = s.hole_mask; a.B = B; a.H = H; a.W = W; a.Lcap = c->max_layers; a.Wwords = (W + 31) / 32;
+    a.tiles_x = (W + kTileW - 1) / kTileW; a.tiles_y = (H + kTileH - 1) / kTileH;
+    a.tile_h_shift = 4; a.tile_seg_shift = 1;
+    static_assert(kTileH == 16 && kTileW == 64, "tile shifts above assume 16x64 blur tiles");
+    const size_t ntiles = (size_t)B * a.tiles_x * a.tiles_y;
+    a.tile_flag = s.tile_flag; a.tile_list = s.tile_list; a.tile_count = s.tile_flag + s.tiles_cap;
+    CU_TRY(c, cudaMemsetAsync(s.tile_flag, 0, sizeof(uint32_t) * ntiles, st));
+    CU_TRY(c, cudaMemsetAsync(a.tile_count, 0, sizeof(uint32_t), st));
     const bool tma = (W % 16 == 0) && ((uintptr_t)frames % 16 == 0) && ((uintptr_t)depth % 16 == 0) &&
                      ((uintptr_t)sbs % 16 == 0);
     int rc;
@@ -251,13 +265,15 @@ int launch_warp(vrsbs_ctx *c, Scratch &s, const uint8_t *frames, const __half *d
     BlurArgs b{};
     b.frames = frames; b.sbs = sbs; b.tabs = s.tabs; b.hole_mask = s.hole_mask; b.weights = c->weights;
     b.B = B; b.H = H; b.W = W; b.Wwords = a.Wwords; b.kx = c->kx; b.ky = c->ky;
-    const long long words = (long long)B * H * a.Wwords;
-    long long blocks = (words + 7) / 8;
+    b.tile_list = s.tile_list; b.tile_count = a.tile_count; b.tiles_x = a.tiles_x; b.tiles_y = a.tiles_y;
     const long long cap = (long long)c->sm_count * 8;
-    if (blocks > cap) blocks = cap;
     {
+        const size_t bsmem = blur_smem_bytes(c->kx, c->ky);
+        CU_TRY(c, cudaFuncSetAttribute(k_blur_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+        long long blocks = (long long)c->sm_count * 6;
+        if (blocks > (long long)ntiles) blocks = (long long)ntiles;
         StageTimer timer(c, st, 3);
-        k_blur_holes<<<(unsigned)blocks, 256, sizeof(double) * c->kx * c->ky, st>>>(b);
+        k_blur_tiles<<<(unsigned)blocks, 256, bsmem, st>>>(b);
     }
     CU_TRY(c, cudaGetLastError());
     c->launches++;

@@ -33,7 +33,10 @@ struct WarpArgs {
     const float2 *bounds;      // [B][Lcap]
     const int *offm;           // [B][Lcap+1]
     uint32_t *hole_mask;       // [B][H][Wwords]
-    int B, H, W, Lcap, Wwords;
+    uint32_t *tile_flag;       // [B][tiles_y][tiles_x], pre-zeroed: 1 once a hole was seen in the tile
+    uint32_t *tile_list;       // work list for the blur kernel (tiles with holes), any order
+    uint32_t *tile_count;      // pre-zeroed
+    int B, H, W, Lcap, Wwords, tiles_x, tiles_y, tile_h_shift, tile_seg_shift;
 };
 
 constexpr int kMaxSeg = 8;     // 32-pixel segments per warp per row (bounds register state)
@@ -203,7 +206,16 @@ __global__ void __launch_bounds__(NT) k_warp_rows(WarpArgs a) {
             const uint32_t w0 = img32[ab >> 2], w1 = img32[(ab >> 2) + 1];
             const uint32_t px = __funnelshift_r(w0, w1, (ab & 3) * 8) & 0x00ffffffu;
             const unsigned hm = __ballot_sync(0xffffffffu, in && key == 0u);
-            if (lane == 0) { mask_row[sg] = hm; hole_acc += __popc(hm); }
+            if (lane == 0) {
+                mask_row[sg] = hm;
+                if (hm) {
+                    hole_acc += __popc(hm);
+                    // first hole seen in this blur tile: append the tile to the blur work list
+                    const uint32_t tile = ((uint32_t)frame * a.tiles_y + (uint32_t)((row - (long long)frame * H) >> a.tile_h_shift)) *
+                                              a.tiles_x + (uint32_t)(sg >> a.tile_seg_shift);
+                    if (atomicExch(&a.tile_flag[tile], 1u) == 0u) a.tile_list[atomicAdd(a.tile_count, 1u)] = tile;
+                }
+            }
             if (((sg + 1) << 5) <= W) {
                 // 32 pixels = 24 words: lane 4q+r (r<3) emits word 3q+r from pixels 4q+r, 4q+r+1
                 const uint32_t nx = __shfl_down_sync(0xffffffffu, px, 1);

@@ -1,0 +1,79 @@
+"""Clip-range sharding across GPUs (one process per GPU, no data-path collective).
+
+Mirrors main_func's split (PredictAndGenerate.py:274-275,300-306): worker i owns the contiguous frame
+range [start + i*step, min(end, start + (i+1)*step)), step = ceil(n / workers), and restarts the
+clip state (depth history, range EMA) at its `begin` — so an N-GPU run is bit-identical to the
+reference run with Num_Workers = N, not to a single-worker run.  Sub-clip names keep the reference's
+`{begin}_{end}` convention (PredictAndGenerate.py:243) so Check_Clips / Combine_Clips still apply.
+
+torch.distributed is used only for the rendezvous, the barrier around timed regions and the
+max-over-ranks of timings (NCCL on GPUs, gloo in the CPU tests).
+"""
+import os
+
+from . import tables
+
+
+def world_from_env():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def shard_for_rank(start_frame, end_frame, video_length, world, rank):
+    """(begin, end) of this rank's clip range, or None when there are more ranks than ranges."""
+    ranges = tables.clip_ranges(start_frame, end_frame, video_length, world)
+    return ranges[rank] if rank < len(ranges) else None
+
+
+def flush_ranges(begin, end, video_length, max_frame_count):
+    """The sub-clips one worker writes: [(first, last_inclusive)], named f"{first}_{last}.mp4"
+    (nibba_woka's flush rule, PredictAndGenerate.py:236-247)."""
+    stop = min(end, video_length)
+    out, first = [], begin
+    count = 0
+    for i in range(begin, stop):
+        count += 1
+        if count == max_frame_count or i == stop - 1:
+            out.append((first, i))
+            first, count = i + 1, 0
+    return out
+
+
+def subclip_name(first, last):
+    return f"{first}_{last}.mp4"
+
+
+class Ranks:
+    """Barrier + max-over-ranks; degenerates to no-ops for a single process."""
+
+    def __init__(self, backend=None, device=None):
+        self.rank, self.world, self.local_rank = world_from_env()
+        self.dist = None
+        self.device = device
+        if self.world > 1:
+            import torch.distributed as dist
+            if not dist.is_initialized():
+                dist.init_process_group(backend or "nccl")
+            self.dist = dist
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+
+    def max(self, value):
+        if self.dist is None:
+            return float(value)
+        import torch
+        t = torch.tensor([float(value)], dtype=torch.float64, device=self.device or "cpu")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def gather(self, obj):
+        if self.dist is None:
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
+    def close(self):
+        if self.dist is not None and self.dist.is_initialized():
+            self.dist.destroy_process_group()

@@ -62,7 +62,7 @@ def depth_stress(n, h=DPT_H, w=DPT_W, seed=0, peak=13.9, drift=2):
     gh, gw = -(-h // f) + 3, -(-(w + drift * n) // f) + 3
     grid = rng.integers(0, int(round(peak * 100)) + 1, size=(gh, gw)).astype(np.float64) / 100.0
     field = np.maximum(_catmull_rom(grid, f), 0.0)
-    return np.stack([field[:h, drift * t:drift * t + w] for t in range(n)]).astype(np.float16)
+    return np.ascontiguousarray(np.stack([field[:h, drift * t:drift * t + w] for t in range(n)]), dtype=np.float16)
 
 
 def depth_scene(n, h=DPT_H, w=DPT_W, seed=0, peak=13.9, drift=2):
@@ -78,7 +78,7 @@ def depth_scene(n, h=DPT_H, w=DPT_W, seed=0, peak=13.9, drift=2):
         ry, rx = float(rng.integers(h // 12 + 1, h // 4 + 2)), float(rng.integers(wide // 16 + 1, wide // 5 + 2))
         inside = ((y - cy) / ry) ** 2 + ((x - cx) / rx) ** 2 <= 1.0
         field = np.where(inside, lev, field)
-    return np.stack([field[:, drift * t:drift * t + w] for t in range(n)]).astype(np.float16)
+    return np.ascontiguousarray(np.stack([field[:, drift * t:drift * t + w] for t in range(n)]), dtype=np.float16)
 
 
 def depth_lowres(kind, n, h=DPT_H, w=DPT_W, seed=0, peak=13.9):
