@@ -130,7 +130,8 @@ def run_ours(args, wl, name):
     ctx = _native.Context(dev, H, W, B, 512)
     ctx.reset(wl["fg"], wl["bg"], wl["step"], True)
     ctx.set_blur_weights(tables.gaussian_weights(*tables.blur_kernel_shape(H)))
-    if args.scatter_mode:
+    if args.scatter_mode:                      # 1/2: the general row kernel instead of the fused route (A/B runs)
+        ctx.set_option("fused", 0)
         ctx.set_option("scatter_mode", args.scatter_mode)
     stream = torch.cuda.current_stream().cuda_stream
 
@@ -226,12 +227,13 @@ def run_ours(args, wl, name):
             "config": {"workload": f"{name}: {W}x{H}, {B}-frame batch per GPU, fg={wl['fg']} bg={wl['bg']} step={wl['step']}, "
                                    f"D-{wl['depth']} depth (limit_step {infos[0].limit_step}, {infos[0].layers} layers, "
                                    f"{100.0 * infos[0].holes / (H * W):.2f}% holes)",
-                       "timed_region": "depth smoothing+max, device tables, warp, hole blur, strip, SBS pack; inputs/outputs in HBM",
+                       "timed_region": "depth max pass, device tables, fused smoothing+warp+fill+pack, hole blur, strip; inputs/outputs in HBM",
                        "l2": f"inputs per step {int((frames_h.nbytes + raw_h.nbytes) / 2**20)} MiB + outputs "
                              f"{int(o_np.nbytes / 2**20)} MiB per GPU > 126 MB L2 (no flush needed)",
-                       "sharding": "independent clip range per GPU, no collective", "scatter_mode": args.scatter_mode or 1},
+                       "sharding": "independent clip range per GPU, no collective",
+                       "route": f"rows(scatter_mode={args.scatter_mode})" if args.scatter_mode else "fused"},
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_warp_rows", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_warp_rows" if args.scatter_mode else "k_warp_fused", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": abytes, "launch_ms": warp_ms / max(warp_n, 1)},
             "stage_ms_per_step": {k: v[0] / args.steps for k, v in stage.items()},

@@ -84,6 +84,7 @@ def warp_frame(img, depth, marks, steps, offsets, weights=None, stages=None):
     if weights is None:
         weights = L.gaussian_weights(kx, ky)
     weights = np.ascontiguousarray(weights, dtype=np.float32)
+    ky, kx = weights.shape                      # caller-supplied kernels keep their own shape
     img = np.ascontiguousarray(img)
     depth = np.ascontiguousarray(depth)
     sbs = np.empty((H, 2 * W, 3), dtype=np.uint8)

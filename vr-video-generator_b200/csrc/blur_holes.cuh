@@ -1,0 +1,161 @@
+// Stage 3b: hole blur, commit and strip restore (PredictAndGenerate.py:191-196).
+//
+// The reference blurs the whole filled frame with a (2k+1)x(2k+3) fp32 gaussian (torchvision
+// gaussian_blur: reflect padding, one depthwise conv, round_) and keeps the result only at hole
+// pixels.  Here only hole pixels are evaluated.  The warp kernel leaves (a) the FILLED pre-blur view in
+// the SBS frame, (b) a hole bitmask and (c) a list of the mask words that contain holes.
+//
+//   k_blur_holes  : one warp per listed mask word (32 pixels of one row).  The warp stages the word's
+//                   footprint (ky rows x (32 + kx - 1) pixels, reflect padded) once, as per-byte-column
+//                   vertical pair sums T_i = row(y-i) + row(y+i), then each lane evaluates one
+//                   (hole, channel): horizontal pair sums x unique weights.  Results go to a scratch
+//                   plane, NOT to the SBS frame, because neighbouring holes still need the pre-blur values.
+//   k_blur_commit : copies the scratch values of the listed holes into the SBS frame.
+//   k_strip_restore: result_img[:, 0:strip] = img[:, 0:strip] (PredictAndGenerate.py:196).
+//
+// Arithmetic.  The oracle defines the blurred value as the EXACT sum of fp32-weight x u8-pixel products,
+// rounded half-to-even (DESIGN.md "blur parity").  Integer path (PARTS = 2 or 3): when the weights are 4-fold
+// symmetric and every w * 2^S is an integer (true for every torchvision gaussian; checked on the host in
+// vrsbs_set_blur_weights), the sum is evaluated in integers: pixel quads are added first (<= 1020), the
+// integer weight is split into PARTS chunks of 15 (PARTS=2) or 13 (PARTS=3) bits so that 32-bit
+// accumulators never overflow, and the final value is rounded half-to-even from the 64-bit total.
+// Generic path (PARTS = 0): all ky*kx taps in fp64 FMA (exact for the same reason the oracle's float64
+// accumulation is).
+#pragma once
+#include "common.cuh"
+
+namespace vrsbs {
+
+struct BlurArgs {
+    const uint8_t *frames;       // [B,H,W,3]
+    uint8_t *sbs;                // [B,H,2W,3]
+    const FrameTab *tabs;        // [B]
+    const uint32_t *hole_mask;   // [B][H][Wwords]
+    const uint32_t *hole_list;   // global mask-word indices
+    const uint32_t *hole_count;
+    uint8_t *plane;              // [B,H,W,3] scratch: blurred values of hole pixels
+    const uint32_t *wq;          // integer path: [PARTS][(cy+1)][(cx+1)] parts of w * 2^S, low part first (i = |dy|, j = |dx|)
+    const float *weights;        // generic: [ky][kx]
+    int B, H, W, Wwords, kx, ky, wshift;   // wshift = S
+};
+
+// per-warp shared memory: T[(rows)][cols] u16, cols = 3*(32 + kx - 1) rounded up to a multiple of 32
+__host__ __device__ inline int blur_cols(int kx) { return (3 * (32 + kx - 1) + 31) / 32 * 32; }
+__host__ __device__ inline size_t blur_warp_smem(int kx, int ky, bool sym) {
+    return (size_t)(sym ? ky / 2 + 1 : ky) * blur_cols(kx) * sizeof(uint16_t);
+}
+
+template <int PARTS>
+__global__ void __launch_bounds__(256) k_blur_holes(BlurArgs a) {
+    extern __shared__ __align__(16) uint8_t blur_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int kx = a.kx, ky = a.ky, cx = kx / 2, cy = ky / 2, W = a.W, H = a.H;
+    const int cols = blur_cols(kx), ncol = 3 * (32 + kx - 1);
+    constexpr bool SYM = PARTS > 0;
+    constexpr int PBITS = PARTS == 2 ? 15 : 13;
+    const int trows = SYM ? cy + 1 : ky;
+    uint16_t *T = reinterpret_cast<uint16_t *>(blur_smem) + (size_t)warp * trows * cols;
+    const uint32_t count = *a.hole_count;
+
+    for (uint32_t ei = blockIdx.x * nwarps + warp; ei < count; ei += gridDim.x * nwarps) {
+        const uint32_t gw = a.hole_list[ei];
+        const uint32_t row = gw / a.Wwords, w = gw - row * a.Wwords;
+        const int b = row / H, y = row - b * H;
+        const int strip = a.tabs[b].strip;
+        uint32_t m = a.hole_mask[gw];
+        const int xw = (int)w * 32;
+        if (strip > xw) m = (strip - xw >= 32) ? 0u : (m & ~((1u << (strip - xw)) - 1u));
+        if (m == 0u) continue;
+        __syncwarp();
+        // ---- stage: byte column c <-> pixel X = xw - cx + c/3, channel c%3 (reflect padded) ----
+        const uint8_t *left = a.sbs + (size_t)b * H * W * 6;
+        for (int c = lane; c < ncol; c += 32) {
+            const int px = c / 3, ch = c - px * 3;
+            const int X = min(max(reflect_idx(xw - cx + px, W), 0), W - 1);
+            const uint8_t *colp = left + (size_t)X * 3 + ch;
+            if (SYM) {
+                T[c] = colp[(size_t)y * W * 6];
+                for (int i = 1; i <= cy; ++i) {
+                    const int ya = reflect_idx(y - i, H), yb = reflect_idx(y + i, H);
+                    T[i * cols + c] = (uint16_t)colp[(size_t)ya * W * 6] + (uint16_t)colp[(size_t)yb * W * 6];
+                }
+            } else {
+                for (int i = 0; i < ky; ++i) T[i * cols + c] = colp[(size_t)reflect_idx(y + i - cy, H) * W * 6];
+            }
+        }
+        __syncwarp();
+        // ---- evaluate: lane = 3*slot + channel, 10 holes per pass ----
+        const int nh = __popc(m);
+        const int slot = lane / 3, ch = lane - slot * 3;
+        for (int h0 = 0; h0 < nh; h0 += 10) {
+            const int hi = h0 + slot;
+            if (lane < 30 && hi < nh) {
+                const int xo = __fns(m, 0, hi + 1);                  // bit position of the hi-th hole
+                const int cc = 3 * (xo + cx) + ch;                   // its byte column in the footprint
+                uint32_t result;
+                if (SYM) {
+                    uint32_t acc[3] = {0u, 0u, 0u};
+                    const int nw = (cy + 1) * (cx + 1);
+                    for (int i = 0; i <= cy; ++i) {
+                        const uint16_t *Ti = T + i * cols + cc;
+                        const uint32_t *wr = a.wq + i * (cx + 1);
+                        for (int j = 0; j <= cx; ++j) {
+                            const uint32_t v = j ? (uint32_t)Ti[-3 * j] + (uint32_t)Ti[3 * j] : (uint32_t)Ti[0];
+#pragma unroll
+                            for (int p = 0; p < PARTS; ++p) acc[p] += v * __ldg(wr + p * nw + j);
+                        }
+                    }
+                    unsigned long long total = 0ull;
+#pragma unroll
+                    for (int p = PARTS - 1; p >= 0; --p) total = (total << PBITS) + acc[p];
+                    const int S = a.wshift;
+                    unsigned long long q = total >> S;
+                    const unsigned long long r = total & ((1ull << S) - 1ull), half = 1ull << (S - 1);
+                    q += (r > half || (r == half && (q & 1ull))) ? 1ull : 0ull;
+                    result = (uint32_t)q;
+                } else {
+                    double acc = 0.0;
+                    for (int i = 0; i < ky; ++i) {
+                        const uint16_t *Ti = T + i * cols + cc - 3 * cx;
+                        const float *wr = a.weights + i * kx;
+                        for (int j = 0; j < kx; ++j) acc = fma((double)__ldg(wr + j), (double)Ti[3 * j], acc);
+                    }
+                    result = (uint32_t)__double2int_rn(acc);
+                }
+                a.plane[((size_t)row * W + xw + xo) * 3 + ch] = (uint8_t)result;
+            }
+        }
+    }
+}
+
+// one warp per listed mask word: plane -> SBS frame for the hole pixels right of the strip
+__global__ void __launch_bounds__(256) k_blur_commit(BlurArgs a) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t count = *a.hole_count;
+    for (uint32_t ei = blockIdx.x * nwarps + warp; ei < count; ei += gridDim.x * nwarps) {
+        const uint32_t gw = a.hole_list[ei];
+        const uint32_t row = gw / a.Wwords, w = gw - row * a.Wwords;
+        const int b = row / a.H;
+        const int x = (int)w * 32 + lane;
+        if (((a.hole_mask[gw] >> lane) & 1u) && x >= a.tabs[b].strip && x < a.W) {
+            const uint8_t *src = a.plane + ((size_t)row * a.W + x) * 3;
+            uint8_t *dst = a.sbs + ((size_t)row * 2 * a.W + x) * 3;
+            dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+        }
+    }
+}
+
+// result_img[:, 0:strip] = img[:, 0:strip]  (PredictAndGenerate.py:196); one warp per image row.
+__global__ void __launch_bounds__(256) k_strip_restore(BlurArgs a) {
+    const int lane = threadIdx.x & 31;
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long rows = (long long)a.B * a.H;
+    for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += nwarps) {
+        const int nbytes = a.tabs[r / a.H].strip * 3;
+        const uint8_t *src = a.frames + r * (size_t)a.W * 3;
+        uint8_t *dst = a.sbs + r * (size_t)a.W * 6;
+        for (int c = lane; c < nbytes; c += 32) dst[c] = src[c];
+    }
+}
+
+}  // namespace vrsbs

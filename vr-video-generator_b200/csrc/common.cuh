@@ -24,7 +24,32 @@ struct FrameTab {
     float    pad;
     double   range[2];
     unsigned long long holes;
+    uint32_t fast;          // 1: the colour-key fast path tables (blob) are valid for this frame
+    uint32_t lut_shift;     // cell = fp16 bits >> lut_shift
+    uint32_t lut_cells;     // number of non-negative cells; index lut_cells = "negative" cell
+    uint32_t pad2;
 };
+
+// ---------------------------------------------------------------------------------------------
+// Per-frame "blob" consumed by k_warp_fused (one TMA bulk copy per image row):
+//   [BlobHdr 16 B][LayerEnt x (ent_cap+1)][cell LUT, lut_cap bytes]
+// LayerEnt e (e = 0..L) describes the two layers a depth value of a cell with LUT value e can
+// belong to: layer e-1 (painted iff d < hi) and layer e (painted iff !(d < lo_next)).
+// ---------------------------------------------------------------------------------------------
+struct BlobHdr {
+    int32_t  fill_off;      // fill layer's offset mod W
+    uint32_t shift;
+    uint32_t ncells;
+    uint32_t flags;         // bit 0: fast; bits 8..: L
+};
+struct LayerEnt {
+    uint32_t hi_lo;         // half2: .x (low 16) = hi of layer e-1 (-inf for e = 0), .y = lo of layer e (+inf for e = L)
+    uint32_t off4;          // low 16: 4*(offset of layer e-1 mod W); high 16: 4*(offset of layer e mod W)
+};
+__host__ __device__ inline uint32_t blob_ent_bytes(int ent_cap) { return (uint32_t)(((ent_cap + 1) * 8 + 15) / 16 * 16); }
+__host__ __device__ inline uint32_t blob_bytes(int ent_cap, int lut_cap) {
+    return 16u + blob_ent_bytes(ent_cap) + (uint32_t)((lut_cap + 15) / 16 * 16);
+}
 
 // Range-EMA state that survives between batches (SbsProcessor.last_offset_range).
 struct RangeState {

@@ -106,6 +106,82 @@ __global__ void __launch_bounds__(256) k_depth_full(DepthArgs a) {
     }
 }
 
+// ---- packed fp16 smoothing: two pixels per instruction where the reference's rounding allows it ------
+// rn16(float(x) * w) needs the fp32 product (w is not an fp16 value); the two adds are plain fp16 adds
+// (an fp32 add of two fp16 values rounded to fp16 equals the correctly rounded fp16 add: 24 >= 2*11+2).
+__device__ __forceinline__ __half2 mul_w(__half2 v, float w) {
+    const float2 f = __half22float2(v);
+    return __floats2half2_rn(__fmul_rn(f.x, w), __fmul_rn(f.y, w));
+}
+__device__ __forceinline__ __half2 smooth3x2(__half2 cur, __half2 p1, __half2 p2, const SmoothWeights &sw) {
+    __half2 d = __hadd2(mul_w(cur, sw.w_now), mul_w(p1, sw.w_prev1));
+    return __hadd2(d, mul_w(p2, sw.w_prev2));
+}
+
+// ---- pass 1 of the fused pipeline: per-frame max of the SMOOTHED depth, nothing else written -------------
+// Reads raw [B,n] once; the smoothed frames are recomputed inside k_warp_fused from the same raw rows,
+// so the smoothed depth never exists in HBM.  Also writes the next batch's history (raw B-1, raw B-2) into
+// the ping-pong history buffers hist1_out/hist2_out.
+struct DepthMaxArgs {
+    const __half *raw;                   // [B, n]
+    const __half *hist1, *hist2;         // [n] raw t-1, t-2 of the previous batch
+    __half *hist1_out, *hist2_out;       // [n]
+    uint32_t *frame_max, *frame_nan;     // [B], pre-zeroed
+    SmoothWeights sw;
+    int B, first;
+    size_t n;                            // H*W, multiple of 8
+};
+
+__global__ void __launch_bounds__(256) k_depth_max(DepthMaxArgs a) {
+    extern __shared__ uint32_t s_red[];          // [B] max | [B] nan
+    uint32_t *s_max = s_red, *s_nan = s_red + a.B;
+    for (int i = threadIdx.x; i < 2 * a.B; i += blockDim.x) s_red[i] = 0;
+    __syncthreads();
+    const size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = v * 8 < a.n;
+    const size_t base = active ? v * 8 : 0;
+    union V { uint4 u; __half2 h[4]; };
+    V p1, p2, cur;
+    p1.u = p2.u = make_uint4(0, 0, 0, 0);
+    if (active && !a.first) {
+        p1.u = __ldg(reinterpret_cast<const uint4 *>(a.hist1 + base));
+        p2.u = __ldg(reinterpret_cast<const uint4 *>(a.hist2 + base));
+    }
+    const int lane = threadIdx.x & 31;
+#pragma unroll 4
+    for (int t = 0; t < a.B; ++t) {
+        uint32_t enc = 0;
+        bool nan = false;
+        if (active) {
+            cur.u = __ldg(reinterpret_cast<const uint4 *>(a.raw + (size_t)t * a.n + base));
+            if (a.first && t == 0) { p1.u = cur.u; p2.u = cur.u; }
+            __half2 m = smooth3x2(cur.h[0], p1.h[0], p2.h[0], a.sw);
+#pragma unroll
+            for (int e = 1; e < 4; ++e) m = __hmax2_nan(m, smooth3x2(cur.h[e], p1.h[e], p2.h[e], a.sw));
+            const float2 f = __half22float2(m);
+            nan = (f.x != f.x) || (f.y != f.y);
+            enc = nan ? 0u : max(f2ord(f.x), f2ord(f.y));
+            p2.u = p1.u;
+            p1.u = cur.u;
+        }
+        enc = __reduce_max_sync(0xffffffffu, enc);
+        const unsigned any_nan = __ballot_sync(0xffffffffu, nan);
+        if (lane == 0) {
+            atomicMax(&s_max[t], enc);
+            if (any_nan) s_nan[t] = 1;
+        }
+    }
+    if (active) {
+        *reinterpret_cast<uint4 *>(a.hist1_out + base) = p1.u;
+        *reinterpret_cast<uint4 *>(a.hist2_out + base) = p2.u;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < a.B; t += blockDim.x) {
+        if (s_max[t]) atomicMax(&a.frame_max[t], s_max[t]);
+        if (s_nan[t]) atomicOr(&a.frame_nan[t], 1u);
+    }
+}
+
 // ---- bicubic coefficients: ATen's cuda/UpSample.cuh arithmetic (A = -0.75) -----------------------
 // `x + 1.0` is evaluated in double and narrowed, as the double literal in the ATen template forces.
 // CONTRACT selects whether mul+add pairs are fused the way nvcc's default -fmad=true fuses them in

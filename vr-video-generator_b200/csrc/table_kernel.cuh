@@ -23,9 +23,28 @@ struct TableArgs {
     double *cutoffs;             // [B][Lcap+1] cutoff_list (introspection / T1)
     int *offsets;                // [B][Lcap]   offset_x_list (signed)
     uint16_t *lo16, *hi16;       // [B][Lcap]   fp16 bit patterns of the bounds
+    uint8_t *blobs;              // [B][blob_stride] fast-path tables (see common.cuh), or nullptr
     double offset_fg, offset_bg;
     int step, B, H, W, Lcap;
+    int ent_cap, lut_cap;        // capacity of the blob's entry table (layers) and cell LUT (bytes)
 };
+
+// LUT value for the cell of depth values [vmin, vmax] (monotone bounds required): e such that every
+// value of the cell can only belong to layer e-1 (iff v < hi[e-1]) or layer e (iff v >= lo[e]);
+// -1 if the cell is too coarse for that to hold.
+__device__ __forceinline__ int cell_entry(const float2 *bounds, int L, float vmin, float vmax) {
+    int lo_i = 0, hi_i = L;                       // a = #{k : hi_k <= vmin}
+    while (lo_i < hi_i) {
+        int mid = (lo_i + hi_i) >> 1;
+        if (bounds[mid].y <= vmin) lo_i = mid + 1; else hi_i = mid;
+    }
+    const int a = lo_i;
+    if (a >= L) return L;                         // above every layer: nothing is painted
+    if (vmin >= bounds[a].x && (a + 2 > L - 1 || vmax < bounds[a + 2].x) && (a + 1 > L - 1 || vmax < bounds[a + 1].y))
+        return a + 1;
+    if (vmax < bounds[a].y && (a + 1 > L - 1 || vmax < bounds[a + 1].x)) return a;
+    return -1;
+}
 
 __device__ __forceinline__ double py_round(double v) { return rint(v); }   // round-half-even
 __device__ __forceinline__ int clamp_int(double v) {
@@ -156,6 +175,59 @@ __global__ void __launch_bounds__(256) k_build_tables(TableArgs a) {
         tab->range[0] = s_r0;
         tab->range[1] = s_r1;
         tab->holes = 0ull;
+    }
+
+    // ---- fast-path blob: entry table + cell LUT (validated exactly, cell by cell) ----------------------
+    if (!a.blobs) { if (threadIdx.x == 0) { tab->fast = 0; tab->lut_shift = 0; tab->lut_cells = 0; } return; }
+    const uint32_t ent_bytes = blob_ent_bytes(a.ent_cap);
+    uint8_t *blob = a.blobs + (size_t)b * blob_bytes(a.ent_cap, a.lut_cap);
+    BlobHdr *hdr = reinterpret_cast<BlobHdr *>(blob);
+    LayerEnt *ent = reinterpret_cast<LayerEnt *>(blob + 16);
+    uint8_t *lut = blob + 16 + ent_bytes;
+    const float fmax = s_max;
+    bool ok = mono && !s_bad && !a.frame_nan[b] && L <= a.ent_cap && L <= 255 && a.W * 4 <= 65535 && fmax < 60000.f;
+    const uint32_t maxbits = (fmax > 0.f) ? (uint32_t)__half_as_ushort(__float2half_rn(fmax)) : 0u;
+    int shift = -1;
+    uint32_t ncells = 0;
+    if (ok) {
+        for (int sh = 9; sh >= 0; --sh) {
+            const uint32_t nc = (maxbits >> sh) + 1;
+            if (nc + 1 > (uint32_t)a.lut_cap) break;
+            int valid = 1;
+            for (uint32_t q = threadIdx.x; q <= nc; q += blockDim.x) {
+                float vmin, vmax;
+                if (q < nc) {
+                    uint32_t b0 = q << sh, b1 = min(((q + 1) << sh) - 1, maxbits);
+                    vmin = __half2float(__ushort_as_half((unsigned short)b0));
+                    vmax = __half2float(__ushort_as_half((unsigned short)b1));
+                } else {                           // every negative value (and -0.0)
+                    vmin = -INFINITY; vmax = 0.f;
+                }
+                int e = cell_entry(bounds, L, vmin, vmax);
+                if (e < 0) valid = 0; else lut[q] = (uint8_t)e;
+            }
+            if (__syncthreads_and(valid)) { shift = sh; ncells = nc; break; }
+        }
+    }
+    ok = ok && shift >= 0;
+    for (int e = threadIdx.x; e <= L && e <= a.ent_cap; e += blockDim.x) {
+        LayerEnt le;
+        const uint32_t hi = e >= 1 ? a.hi16[(size_t)b * a.Lcap + e - 1] : 0xFC00u;        // -inf
+        const uint32_t lo = e <= L - 1 ? a.lo16[(size_t)b * a.Lcap + e] : 0x7C00u;        // +inf
+        const uint32_t o0 = e >= 1 ? (uint32_t)offm[e] * 4u : 0u;
+        const uint32_t o1 = e <= L - 1 ? (uint32_t)offm[e + 1] * 4u : 0u;
+        le.hi_lo = hi | (lo << 16);
+        le.off4 = (o0 & 0xffffu) | (o1 << 16);
+        ent[e] = le;
+    }
+    if (threadIdx.x == 0) {
+        hdr->fill_off = offm[0];
+        hdr->shift = ok ? (uint32_t)shift : 0u;
+        hdr->ncells = ok ? ncells : 0u;
+        hdr->flags = (ok ? 1u : 0u) | ((uint32_t)L << 8);
+        tab->fast = ok ? 1u : 0u;
+        tab->lut_shift = hdr->shift;
+        tab->lut_cells = hdr->ncells;
     }
 }
 

@@ -1,15 +1,17 @@
 // C ABI of the SBS warp hot path (see include/vrsbs.h for the contract and reference citations).
 #include <cstdarg>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <new>
 #include <thread>
 #include <vector>
 
-#include "blur_kernel.cuh"
+#include "blur_holes.cuh"
 #include "common.cuh"
 #include "depth_kernels.cuh"
 #include "table_kernel.cuh"
+#include "warp_fused.cuh"
 #include "warp_kernel.cuh"
 
 using namespace vrsbs;
@@ -19,7 +21,7 @@ namespace {
 thread_local char g_create_error[256] = "";
 
 struct Scratch {                 // per-batch device scratch; one per pipeline slot
-    uint32_t *frame_max = nullptr, *frame_nan = nullptr;
+    uint32_t *frame_max = nullptr, *frame_nan = nullptr;   // one allocation: [B] max | [B] nan | [1] hole_count
     FrameTab *tabs = nullptr;
     float2 *bounds = nullptr;
     int *offm = nullptr;
@@ -27,10 +29,13 @@ struct Scratch {                 // per-batch device scratch; one per pipeline s
     int *offsets = nullptr;
     uint16_t *lo16 = nullptr, *hi16 = nullptr;
     uint32_t *hole_mask = nullptr;
-    uint32_t *tile_flag = nullptr;   // [tiles + 1]: flags, then the list counter in the last word
-    uint32_t *tile_list = nullptr;
-    size_t tiles_cap = 0;
+    uint32_t *hole_list = nullptr;   // mask words that contain holes (blur work list)
+    uint32_t *hole_count = nullptr;  // points into frame_max's allocation: one memset clears all three
+    uint8_t *blobs = nullptr;        // [B][kBlobMax] fast-path tables
+    uint8_t *plane = nullptr;        // [B,H,W,3] blurred hole values (allocated on first blur)
 };
+
+constexpr int kEntCapMax = 255, kLutCapMax = 8192;
 
 struct HostSlot {                // double-buffered host<->device staging for vrsbs_process_host
     cudaStream_t stream = nullptr;
@@ -49,7 +54,8 @@ struct vrsbs_ctx {
     vrsbs_params params{0.025, -0.01, 1, 1};
     SmoothWeights sw{};
     // clip-range state
-    __half *hist1 = nullptr, *hist2 = nullptr;
+    __half *hist[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [set][0: raw t-1, 1: raw t-2]; set hist_idx is current
+    int hist_idx = 0;
     RangeState *state = nullptr;         // [2], ping-pong
     int state_idx = 0;
     long long depth_frames = 0;          // frames pushed through stage 1 since reset
@@ -57,7 +63,11 @@ struct vrsbs_ctx {
     // scratch
     Scratch scratch[2];
     float *weights = nullptr;
-    int kx = 0, ky = 0;
+    uint32_t *wq = nullptr;              // integer blur weights [parts][(ky/2+1)*(kx/2+1)]
+    int kx = 0, ky = 0, wparts = 0, wshift = 0;
+    int ent_cap = 0, lut_cap = 0;        // fast-path table capacities of the last vrsbs_build_tables
+    int fused = 1;                       // option: use the fused route in vrsbs_process_batch when possible
+    int fast_tables = 1;                 // option (tests): 0 forces the slow membership path of k_warp_fused
     // host pipeline
     HostSlot slot[2];
     int host_chunk = 8;
@@ -106,17 +116,18 @@ template <typename T>
 cudaError_t dmalloc(T **p, size_t count) { return cudaMalloc(reinterpret_cast<void **>(p), count * sizeof(T)); }
 
 void free_scratch(Scratch &s) {
-    cudaFree(s.frame_max); cudaFree(s.frame_nan); cudaFree(s.tabs); cudaFree(s.bounds); cudaFree(s.offm);
+    cudaFree(s.frame_max); cudaFree(s.tabs); cudaFree(s.bounds); cudaFree(s.offm);
     cudaFree(s.cutoffs); cudaFree(s.offsets); cudaFree(s.lo16); cudaFree(s.hi16); cudaFree(s.hole_mask);
-    cudaFree(s.tile_flag); cudaFree(s.tile_list);
+    cudaFree(s.hole_list); cudaFree(s.blobs); cudaFree(s.plane);
     s = Scratch{};
 }
 
 int alloc_scratch(vrsbs_ctx *c, Scratch &s) {
     const size_t B = c->max_batch, L = c->max_layers;
     const size_t mask_words = B * c->max_h * ((c->max_w + 31) / 32);
-    CU_TRY(c, dmalloc(&s.frame_max, B));
-    CU_TRY(c, dmalloc(&s.frame_nan, B));
+    CU_TRY(c, dmalloc(&s.frame_max, 2 * B + 1));
+    s.frame_nan = s.frame_max + B;
+    s.hole_count = s.frame_max + 2 * B;
     CU_TRY(c, dmalloc(&s.tabs, B));
     CU_TRY(c, dmalloc(&s.bounds, B * L));
     CU_TRY(c, dmalloc(&s.offm, B * (L + 1)));
@@ -125,9 +136,8 @@ int alloc_scratch(vrsbs_ctx *c, Scratch &s) {
     CU_TRY(c, dmalloc(&s.lo16, B * L));
     CU_TRY(c, dmalloc(&s.hi16, B * L));
     CU_TRY(c, dmalloc(&s.hole_mask, mask_words));
-    s.tiles_cap = B * ((c->max_h + kTileH - 1) / kTileH) * ((c->max_w + kTileW - 1) / kTileW);
-    CU_TRY(c, dmalloc(&s.tile_flag, s.tiles_cap + 1));
-    CU_TRY(c, dmalloc(&s.tile_list, s.tiles_cap));
+    CU_TRY(c, dmalloc(&s.hole_list, mask_words));
+    CU_TRY(c, dmalloc(&s.blobs, B * (size_t)blob_bytes(kEntCapMax, kLutCapMax)));
     return VRSBS_OK;
 }
 
@@ -161,15 +171,27 @@ struct StageTimer {
 };
 
 // ---- stage launchers (stream-ordered, no host sync) ---------------------------------------------------
-int launch_depth(vrsbs_ctx *c, Scratch &s, const __half *raw, const __half *lowres, int B, int H, int W, int h, int w,
-                 float scaler, __half *out, cudaStream_t st) {
+int clear_counters(vrsbs_ctx *c, Scratch &s, int B, cudaStream_t st) {
+    (void)B;
+    CU_TRY(c, cudaMemsetAsync(s.frame_max, 0, sizeof(uint32_t) * (2 * c->max_batch + 1), st));
+    return VRSBS_OK;
+}
+
+int check_state_dims(vrsbs_ctx *c, int H, int W) {
     if (c->depth_frames > 0 && (c->state_h != H || c->state_w != W))
         return fail(c, VRSBS_E_STATE, "frame size changed from %dx%d to %dx%d without vrsbs_reset", c->state_h,
                     c->state_w, H, W);
-    CU_TRY(c, cudaMemsetAsync(s.frame_max, 0, sizeof(uint32_t) * B, st));
-    CU_TRY(c, cudaMemsetAsync(s.frame_nan, 0, sizeof(uint32_t) * B, st));
+    return VRSBS_OK;
+}
+
+// staged route: smoothed depth is materialised (vrsbs_depth_from_full / vrsbs_depth_from_lowres)
+int launch_depth(vrsbs_ctx *c, Scratch &s, const __half *raw, const __half *lowres, int B, int H, int W, int h, int w,
+                 float scaler, __half *out, cudaStream_t st) {
+    int rc = check_state_dims(c, H, W);
+    if (rc) return rc;
+    if ((rc = clear_counters(c, s, B, st))) return rc;
     DepthArgs a{};
-    a.raw = raw; a.lowres = lowres; a.out = out; a.hist1 = c->hist1; a.hist2 = c->hist2;
+    a.raw = raw; a.lowres = lowres; a.out = out; a.hist1 = c->hist[c->hist_idx][0]; a.hist2 = c->hist[c->hist_idx][1];
     a.frame_max = s.frame_max; a.frame_nan = s.frame_nan; a.sw = c->sw;
     a.B = B; a.H = H; a.W = W; a.h = h; a.w = w; a.first = c->depth_frames == 0; a.scaler = scaler;
     a.scale_y = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f;
@@ -196,6 +218,49 @@ int launch_depth(vrsbs_ctx *c, Scratch &s, const __half *raw, const __half *lowr
     return VRSBS_OK;
 }
 
+// fused route, pass 1: per-frame max of the smoothed depth only; history goes to the other ping-pong set
+int launch_depth_max(vrsbs_ctx *c, Scratch &s, const __half *raw, int B, int H, int W, cudaStream_t st) {
+    int rc = check_state_dims(c, H, W);
+    if (rc) return rc;
+    if ((rc = clear_counters(c, s, B, st))) return rc;
+    DepthMaxArgs a{};
+    a.raw = raw; a.hist1 = c->hist[c->hist_idx][0]; a.hist2 = c->hist[c->hist_idx][1];
+    a.hist1_out = c->hist[c->hist_idx ^ 1][0]; a.hist2_out = c->hist[c->hist_idx ^ 1][1];
+    a.frame_max = s.frame_max; a.frame_nan = s.frame_nan; a.sw = c->sw;
+    a.B = B; a.first = c->depth_frames == 0; a.n = (size_t)H * W;
+    StageTimer timer(c, st, 0);
+    k_depth_max<<<(unsigned)((a.n / 8 + 255) / 256), 256, sizeof(uint32_t) * 2 * B, st>>>(a);
+    CU_TRY(c, cudaGetLastError());
+    c->launches++;
+    return VRSBS_OK;
+}
+
+// Capacities of the fast-path tables, from the parameters alone (no device round trip): enough layers and
+// LUT cells for limit_step <= 32; frames that need more take the slow path inside k_warp_fused.
+void fast_caps(const vrsbs_ctx *c, int H, int *ent_cap, int *lut_cap) {
+    const double span_per_limit = fabs(c->params.offset_fg - c->params.offset_bg) * H / 14.0;   // pixels of offset per unit of limit
+    const int step = c->params.offset_step_size;
+    double layers = span_per_limit * 32.0 / step + 6.0;
+    int ec = layers > kEntCapMax ? kEntCapMax : (int)layers;
+    if (ec < 8) ec = 8;
+    // layer width in depth units ~ step / span_per_limit; a LUT cell must be narrower than ~0.9 of it
+    const double width = span_per_limit > 0 ? 0.85 * 0.9 * step / span_per_limit : 1e9;
+    int cells = 64;
+    for (int e = -14; e <= 4; ++e) {                       // binade [2^e, 2^(e+1)) of the frame maximum, up to 32
+        const double ulp = ldexp(1.0, e - 10);
+        int sh = 0;
+        while (sh < 9 && ulp * (2 << sh) <= width) ++sh;
+        const int top_bits = (e + 15 + 1) << 10;           // fp16 bits of 2^(e+1)
+        const int n = (top_bits >> sh) + 2;
+        if (n > cells) cells = n;
+    }
+    if (cells > kLutCapMax) cells = kLutCapMax;
+    if (cells > 5120 && ec > 128) cells = 5120;            // keep two 4K CTAs per SM
+    if (!c->fast_tables) { ec = 0; cells = 16; }
+    *ent_cap = ec;
+    *lut_cap = (cells + 15) / 16 * 16;
+}
+
 int launch_tables(vrsbs_ctx *c, Scratch &s, int B, int H, int W, cudaStream_t st) {
     TableArgs a{};
     a.frame_max = s.frame_max; a.frame_nan = s.frame_nan;
@@ -204,6 +269,8 @@ int launch_tables(vrsbs_ctx *c, Scratch &s, int B, int H, int W, cudaStream_t st
     a.lo16 = s.lo16; a.hi16 = s.hi16;
     a.offset_fg = c->params.offset_fg; a.offset_bg = c->params.offset_bg; a.step = c->params.offset_step_size;
     a.B = B; a.H = H; a.W = W; a.Lcap = c->max_layers;
+    fast_caps(c, H, &c->ent_cap, &c->lut_cap);
+    a.blobs = s.blobs; a.ent_cap = c->ent_cap; a.lut_cap = c->lut_cap;
     const size_t smem = sizeof(double) * 2 * (c->max_layers + 2);
     StageTimer timer(c, st, 1);
     k_build_tables<<<B, 256, smem, st>>>(a);
@@ -238,46 +305,57 @@ int launch_warp_nt(vrsbs_ctx *c, const WarpArgs &a, cudaStream_t st) {
     return launch_warp_inst<MODE, TMA, 1024>(c, a, st);
 }
 
-int launch_warp(vrsbs_ctx *c, Scratch &s, const uint8_t *frames, const __half *depth, int B, int H, int W, uint8_t *sbs,
-                cudaStream_t st) {
-    if (c->params.blur && (c->kx <= 0 || c->ky <= 0))
-        return fail(c, VRSBS_E_STATE, "vrsbs_set_blur_weights must be called before the warp");
-    if (c->params.blur && (c->kx / 2 >= W || c->ky / 2 >= H))
-        return fail(c, VRSBS_E_INVALID, "blur kernel %dx%d too large for a %dx%d frame (reflect padding)", c->kx, c->ky, W, H);
-    WarpArgs a{};
-    a.frames = frames; a.depth = depth; a.sbs = sbs; a.tabs = s.tabs; a.bounds = s.bounds; a.offm = s.offm;
-    a.hole_mask = s.hole_mask; a.B = B; a.H = H; a.W = W; a.Lcap = c->max_layers; a.Wwords = (W + 31) / 32;
-    a.tiles_x = (W + kTileW - 1) / kTileW; a.tiles_y = (H + kTileH - 1) / kTileH;
-    a.tile_h_shift = 4; a.tile_seg_shift = 1;
-    static_assert(kTileH == 16 && kTileW == 64, "tile shifts above assume 16x64 blur tiles");
-    const size_t ntiles = (size_t)B * a.tiles_x * a.tiles_y;
-    a.tile_flag = s.tile_flag; a.tile_list = s.tile_list; a.tile_count = s.tile_flag + s.tiles_cap;
-    CU_TRY(c, cudaMemsetAsync(s.tile_flag, 0, sizeof(uint32_t) * ntiles, st));
-    CU_TRY(c, cudaMemsetAsync(a.tile_count, 0, sizeof(uint32_t), st));
-    const bool tma = (W % 16 == 0) && ((uintptr_t)frames % 16 == 0) && ((uintptr_t)depth % 16 == 0) &&
-                     ((uintptr_t)sbs % 16 == 0);
-    int rc;
-    if (c->scatter_mode == 2) rc = tma ? launch_warp_nt<2, true>(c, a, st) : launch_warp_nt<2, false>(c, a, st);
-    else rc = tma ? launch_warp_nt<1, true>(c, a, st) : launch_warp_nt<1, false>(c, a, st);
-    if (rc) return rc;
-    if (!c->params.blur) return VRSBS_OK;
-
-    BlurArgs b{};
-    b.frames = frames; b.sbs = sbs; b.tabs = s.tabs; b.hole_mask = s.hole_mask; b.weights = c->weights;
-    b.B = B; b.H = H; b.W = W; b.Wwords = a.Wwords; b.kx = c->kx; b.ky = c->ky;
-    b.tile_list = s.tile_list; b.tile_count = a.tile_count; b.tiles_x = a.tiles_x; b.tiles_y = a.tiles_y;
-    const long long cap = (long long)c->sm_count * 8;
-    {
-        const size_t bsmem = blur_smem_bytes(c->kx, c->ky);
-        CU_TRY(c, cudaFuncSetAttribute(k_blur_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
-        long long blocks = (long long)c->sm_count * 6;
-        if (blocks > (long long)ntiles) blocks = (long long)ntiles;
-        StageTimer timer(c, st, 3);
-        k_blur_tiles<<<(unsigned)blocks, 256, bsmem, st>>>(b);
-    }
+template <bool SMOOTH, int NT>
+int launch_fused_inst(vrsbs_ctx *c, const FusedArgs &a, cudaStream_t st) {
+    auto kern = k_warp_fused<SMOOTH, NT>;
+    const size_t smem = fused_smem_layout(a.W, a.blob_bytes).total;
+    CU_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
+    if (c->blocks_per_sm > 0 && c->blocks_per_sm < occ) occ = c->blocks_per_sm;
+    if (occ < 1) return fail(c, VRSBS_E_INVALID, "fused warp kernel does not fit: %zu B shared memory", smem);
+    long long iters = (long long)a.B * a.H;
+    long long grid = (long long)c->sm_count * occ;
+    if (grid > iters) grid = iters;
+    StageTimer timer(c, st, 2);
+    kern<<<(unsigned)grid, NT, smem, st>>>(a);
     CU_TRY(c, cudaGetLastError());
     c->launches++;
+    return VRSBS_OK;
+}
+
+bool fused_capable(const vrsbs_ctx *c, const void *frames, const void *depth, const void *sbs, int W) {
+    const size_t smem = fused_smem_layout(W, blob_bytes(c->ent_cap, c->lut_cap)).total;
+    return (W % 16 == 0) && W * 4 <= 65535 && ((uintptr_t)frames % 16 == 0) && ((uintptr_t)depth % 16 == 0) &&
+           ((uintptr_t)sbs % 16 == 0) && smem <= 200 * 1024;
+}
+
+int launch_blur(vrsbs_ctx *c, Scratch &s, const uint8_t *frames, int B, int H, int W, uint8_t *sbs, cudaStream_t st) {
+    if (!s.plane) CU_TRY(c, dmalloc(&s.plane, (size_t)c->max_batch * c->max_h * c->max_w * 3));
+    BlurArgs b{};
+    b.frames = frames; b.sbs = sbs; b.tabs = s.tabs; b.hole_mask = s.hole_mask; b.hole_list = s.hole_list;
+    b.hole_count = s.hole_count; b.plane = s.plane; b.wq = c->wq; b.weights = c->weights;
+    b.B = B; b.H = H; b.W = W; b.Wwords = (W + 31) / 32; b.kx = c->kx; b.ky = c->ky; b.wshift = c->wshift;
+    const size_t per_warp = blur_warp_smem(c->kx, c->ky, c->wparts > 0);
+    int warps = 8;
+    while (warps > 1 && per_warp * warps > 96 * 1024) warps >>= 1;
+    const size_t bsmem = per_warp * warps;
+    if (bsmem > 200 * 1024) return fail(c, VRSBS_E_INVALID, "blur kernel %dx%d needs %zu B shared memory per warp", c->kx, c->ky, per_warp);
+    auto kern = c->wparts == 2 ? k_blur_holes<2> : (c->wparts == 3 ? k_blur_holes<3> : k_blur_holes<0>);
+    CU_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+    int occ = 0;
+    CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, bsmem));
+    if (occ < 1) occ = 1;
+    {
+        StageTimer timer(c, st, 3);
+        kern<<<(unsigned)(c->sm_count * occ), warps * 32, bsmem, st>>>(b);
+        CU_TRY(c, cudaGetLastError());
+        k_blur_commit<<<(unsigned)(c->sm_count * 8), 256, 0, st>>>(b);
+        CU_TRY(c, cudaGetLastError());
+    }
+    c->launches += 2;
     long long rblocks = ((long long)B * H + 7) / 8;
+    const long long cap = (long long)c->sm_count * 8;
     if (rblocks > cap) rblocks = cap;
     {
         StageTimer timer(c, st, 4);
@@ -286,6 +364,68 @@ int launch_warp(vrsbs_ctx *c, Scratch &s, const uint8_t *frames, const __half *d
     CU_TRY(c, cudaGetLastError());
     c->launches++;
     return VRSBS_OK;
+}
+
+int check_blur_ready(vrsbs_ctx *c, int H, int W) {
+    if (c->params.blur && (c->kx <= 0 || c->ky <= 0))
+        return fail(c, VRSBS_E_STATE, "vrsbs_set_blur_weights must be called before the warp");
+    if (c->params.blur && (c->kx / 2 >= W || c->ky / 2 >= H))
+        return fail(c, VRSBS_E_INVALID, "blur kernel %dx%d too large for a %dx%d frame (reflect padding)", c->kx, c->ky, W, H);
+    return VRSBS_OK;
+}
+
+FusedArgs make_fused_args(vrsbs_ctx *c, Scratch &s, const uint8_t *frames, const __half *depth, int B, int H, int W, uint8_t *sbs) {
+    FusedArgs a{};
+    a.frames = frames; a.depth = depth; a.hist1 = c->hist[c->hist_idx][0]; a.hist2 = c->hist[c->hist_idx][1];
+    a.sbs = sbs; a.blobs = s.blobs; a.tabs = s.tabs; a.bounds = s.bounds; a.offm = s.offm;
+    a.hole_mask = s.hole_mask; a.hole_list = s.hole_list; a.hole_count = s.hole_count;
+    a.B = B; a.H = H; a.W = W; a.Lcap = c->max_layers; a.Wwords = (W + 31) / 32;
+    a.first = 0;
+    a.blob_bytes = blob_bytes(c->ent_cap, c->lut_cap); a.ent_bytes = blob_ent_bytes(c->ent_cap);
+    a.w0 = c->sw.w_now; a.w1 = c->sw.w_prev1; a.w2 = c->sw.w_prev2;
+    return a;
+}
+
+// staged route, stage 3: depth is the SMOOTHED depth left by launch_depth
+int launch_warp(vrsbs_ctx *c, Scratch &s, const uint8_t *frames, const __half *depth, int B, int H, int W, uint8_t *sbs,
+                cudaStream_t st) {
+    int rc = check_blur_ready(c, H, W);
+    if (rc) return rc;
+    if (c->fused && fused_capable(c, frames, depth, sbs, W)) {
+        FusedArgs a = make_fused_args(c, s, frames, depth, B, H, W, sbs);
+        rc = W <= 2048 ? launch_fused_inst<false, 256>(c, a, st) : launch_fused_inst<false, 512>(c, a, st);
+    } else {
+        WarpArgs a{};
+        a.frames = frames; a.depth = depth; a.sbs = sbs; a.tabs = s.tabs; a.bounds = s.bounds; a.offm = s.offm;
+        a.hole_mask = s.hole_mask; a.B = B; a.H = H; a.W = W; a.Lcap = c->max_layers; a.Wwords = (W + 31) / 32;
+        a.hole_list = s.hole_list; a.hole_count = s.hole_count;
+        const bool tma = (W % 16 == 0) && ((uintptr_t)frames % 16 == 0) && ((uintptr_t)depth % 16 == 0) &&
+                         ((uintptr_t)sbs % 16 == 0);
+        if (c->scatter_mode == 2) rc = tma ? launch_warp_nt<2, true>(c, a, st) : launch_warp_nt<2, false>(c, a, st);
+        else rc = tma ? launch_warp_nt<1, true>(c, a, st) : launch_warp_nt<1, false>(c, a, st);
+    }
+    if (rc) return rc;
+    if (!c->params.blur) return VRSBS_OK;
+    return launch_blur(c, s, frames, B, H, W, sbs, st);
+}
+
+// fused route: raw depth in, smoothing recomputed inside the warp kernel (no smoothed depth in HBM)
+int launch_process_fused(vrsbs_ctx *c, Scratch &s, const uint8_t *frames, const __half *raw, int B, int H, int W,
+                         uint8_t *sbs, cudaStream_t st) {
+    int rc = check_blur_ready(c, H, W);
+    if (rc) return rc;
+    const bool first = c->depth_frames == 0;
+    if ((rc = launch_depth_max(c, s, raw, B, H, W, st))) return rc;
+    if ((rc = launch_tables(c, s, B, H, W, st))) return rc;
+    FusedArgs a = make_fused_args(c, s, frames, raw, B, H, W, sbs);
+    a.first = first ? 1 : 0;
+    rc = W <= 2048 ? launch_fused_inst<true, 256>(c, a, st) : launch_fused_inst<true, 512>(c, a, st);
+    if (rc) return rc;
+    c->hist_idx ^= 1;                        // k_depth_max wrote the next batch's history into the other set
+    c->depth_frames += B;
+    c->state_h = H; c->state_w = W;
+    if (!c->params.blur) return VRSBS_OK;
+    return launch_blur(c, s, frames, B, H, W, sbs, st);
 }
 
 void parallel_memcpy(void *dst, const void *src, size_t bytes, int nthreads) {
@@ -384,8 +524,8 @@ int vrsbs_create(vrsbs_ctx **out, int device, int max_h, int max_w, int max_batc
     c->sm_count = prop.multiProcessorCount;
     auto init = [&]() -> int {
         const size_t n = (size_t)max_h * max_w;
-        CU_TRY(c, dmalloc(&c->hist1, n));
-        CU_TRY(c, dmalloc(&c->hist2, n));
+        for (int i = 0; i < 2; ++i)
+            for (int j = 0; j < 2; ++j) CU_TRY(c, dmalloc(&c->hist[i][j], n));
         CU_TRY(c, dmalloc(&c->state, 2));
         int rc = alloc_scratch(c, c->scratch[0]);
         if (rc) return rc;
@@ -406,7 +546,9 @@ int vrsbs_destroy(vrsbs_ctx *c) {
     if (!c) return VRSBS_OK;
     DeviceGuard g(c->device);
     cudaDeviceSynchronize();
-    cudaFree(c->hist1); cudaFree(c->hist2); cudaFree(c->state); cudaFree(c->weights);
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j) cudaFree(c->hist[i][j]);
+    cudaFree(c->state); cudaFree(c->weights); cudaFree(c->wq);
     free_scratch(c->scratch[0]); free_scratch(c->scratch[1]);
     free_slot(c->slot[0]); free_slot(c->slot[1]);
     for (auto &s : c->stamps) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
@@ -463,9 +605,47 @@ int vrsbs_set_blur_weights(vrsbs_ctx *c, const float *w, int kx, int ky) {
     DeviceGuard g(c->device);
     CU_TRY(c, cudaDeviceSynchronize());
     cudaFree(c->weights); c->weights = nullptr;
+    cudaFree(c->wq); c->wq = nullptr;
     CU_TRY(c, dmalloc(&c->weights, (size_t)kx * ky));
     CU_TRY(c, cudaMemcpy(c->weights, w, sizeof(float) * kx * ky, cudaMemcpyHostToDevice));
-    c->kx = kx; c->ky = ky;
+    c->kx = kx; c->ky = ky; c->wparts = 0; c->wshift = 0;
+    // Integer path (blur_holes.cuh): 4-fold symmetric, positive weights whose common scale 2^S makes them
+    // integers that split into 2 x 15 or 3 x 13 bits without overflowing 32-bit accumulators.
+    const int cx = kx / 2, cy = ky / 2, nu = (cx + 1) * (cy + 1);
+    bool sym = true;
+    for (int i = 0; i < ky && sym; ++i)
+        for (int j = 0; j < kx; ++j) {
+            const float v = w[i * kx + j];
+            if (!(v >= 0.f) || !std::isfinite(v) || v != w[(ky - 1 - i) * kx + j] || v != w[i * kx + (kx - 1 - j)]) { sym = false; break; }
+        }
+    if (sym) {
+        int S = -1;
+        for (int s = 1; s <= 62 && S < 0; ++s) {
+            bool all = true;
+            for (int i = 0; i < kx * ky && all; ++i) { const double v = ldexp((double)w[i], s); all = v == floor(v); }
+            if (all) S = s;
+        }
+        double wmax = 0;
+        for (int i = 0; i < kx * ky; ++i) wmax = w[i] > wmax ? w[i] : wmax;
+        int parts = 0;
+        if (S > 0) {
+            const double qmax = ldexp(wmax, S);
+            if (qmax < ldexp(1.0, 30) && nu <= 100) parts = 2;
+            else if (qmax < ldexp(1.0, 39) && nu <= 400) parts = 3;
+        }
+        if (parts) {
+            const int pbits = parts == 2 ? 15 : 13;
+            std::vector<uint32_t> q((size_t)parts * nu);
+            for (int i = 0; i <= cy; ++i)
+                for (int j = 0; j <= cx; ++j) {
+                    unsigned long long v = (unsigned long long)ldexp((double)w[(cy - i) * kx + (cx - j)], S);
+                    for (int p = 0; p < parts; ++p) { q[(size_t)p * nu + i * (cx + 1) + j] = (uint32_t)(v & ((1ull << pbits) - 1ull)); v >>= pbits; }
+                }
+            CU_TRY(c, dmalloc(&c->wq, q.size()));
+            CU_TRY(c, cudaMemcpy(c->wq, q.data(), sizeof(uint32_t) * q.size(), cudaMemcpyHostToDevice));
+            c->wparts = parts; c->wshift = S;
+        }
+    }
     return VRSBS_OK;
 }
 
@@ -507,10 +687,14 @@ int vrsbs_process_batch(vrsbs_ctx *c, const uint8_t *frames, const void *raw, in
                         uint8_t *sbs, void *stream) {
     int rc = check_dims(c, B, H, W);
     if (rc) return rc;
-    if (!frames || !raw || !depth_scratch || !sbs) return fail(c, VRSBS_E_INVALID, "NULL buffer");
+    if (!frames || !raw || !sbs) return fail(c, VRSBS_E_INVALID, "NULL buffer");
     DeviceGuard g(c->device);
     cudaStream_t st = (cudaStream_t)stream;
     Scratch &s = c->scratch[0];
+    fast_caps(c, H, &c->ent_cap, &c->lut_cap);
+    if (c->fused && ((size_t)H * W) % 8 == 0 && fused_capable(c, frames, raw, sbs, W))
+        return launch_process_fused(c, s, frames, (const __half *)raw, B, H, W, sbs, st);
+    if (!depth_scratch) return fail(c, VRSBS_E_INVALID, "depth_scratch_dev is required for this frame size / alignment");
     if ((rc = launch_depth(c, s, (const __half *)raw, nullptr, B, H, W, 0, 0, 1.f, (__half *)depth_scratch, st))) return rc;
     if ((rc = launch_tables(c, s, B, H, W, st))) return rc;
     return launch_warp(c, s, frames, (const __half *)depth_scratch, B, H, W, sbs, st);
@@ -533,6 +717,11 @@ int vrsbs_process_host(vrsbs_ctx *c, const uint8_t *frames, const void *depth, i
     for (int i = 0; i < 2; ++i)
         if ((rc = ensure_slot(c, c->slot[i], fb * chunk, dib * chunk, db * chunk, sb * chunk))) return rc;
     const bool pin_f = is_pinned(frames), pin_d = is_pinned(depth), pin_s = is_pinned(sbs);
+    fast_caps(c, H, &c->ent_cap, &c->lut_cap);
+    const int want_blur = c->params.blur;
+    if ((rc = check_blur_ready(c, H, W))) return rc;
+    const bool use_fused = !lowres && c->fused && ((size_t)H * W) % 8 == 0 &&
+                           fused_capable(c, c->slot[0].dev_frames, c->slot[0].dev_depth_in, c->slot[0].dev_sbs, W);
 
     std::vector<FrameTab> tabs(chunk);
     int nchunks = (B + chunk - 1) / chunk;
@@ -560,12 +749,22 @@ int vrsbs_process_host(vrsbs_ctx *c, const uint8_t *frames, const void *depth, i
         // stage 1/2 carry clip-range state from the previous chunk, which ran on the other stream
         if (ci > 0) CU_TRY(c, cudaStreamWaitEvent(s.stream, c->slot[si ^ 1].state_ready, 0));
         Scratch &sc = c->scratch[si];
-        if (lowres) rc = launch_depth(c, sc, nullptr, (const __half *)s.dev_depth_in, n, H, W, lh, lw, scaler, (__half *)s.dev_depth, s.stream);
-        else rc = launch_depth(c, sc, (const __half *)s.dev_depth_in, nullptr, n, H, W, 0, 0, 1.f, (__half *)s.dev_depth, s.stream);
-        if (rc) return rc;
-        if ((rc = launch_tables(c, sc, n, H, W, s.stream))) return rc;
-        CU_TRY(c, cudaEventRecord(s.state_ready, s.stream));
-        if ((rc = launch_warp(c, sc, s.dev_frames, (const __half *)s.dev_depth, n, H, W, s.dev_sbs, s.stream))) return rc;
+        if (use_fused) {
+            // the warp kernel itself reads the depth history, so the next chunk may only start after it
+            c->params.blur = 0;
+            rc = launch_process_fused(c, sc, s.dev_frames, (const __half *)s.dev_depth_in, n, H, W, s.dev_sbs, s.stream);
+            c->params.blur = want_blur;
+            if (rc) return rc;
+            CU_TRY(c, cudaEventRecord(s.state_ready, s.stream));
+            if (want_blur && (rc = launch_blur(c, sc, s.dev_frames, n, H, W, s.dev_sbs, s.stream))) return rc;
+        } else {
+            if (lowres) rc = launch_depth(c, sc, nullptr, (const __half *)s.dev_depth_in, n, H, W, lh, lw, scaler, (__half *)s.dev_depth, s.stream);
+            else rc = launch_depth(c, sc, (const __half *)s.dev_depth_in, nullptr, n, H, W, 0, 0, 1.f, (__half *)s.dev_depth, s.stream);
+            if (rc) return rc;
+            if ((rc = launch_tables(c, sc, n, H, W, s.stream))) return rc;
+            CU_TRY(c, cudaEventRecord(s.state_ready, s.stream));
+            if ((rc = launch_warp(c, sc, s.dev_frames, (const __half *)s.dev_depth, n, H, W, s.dev_sbs, s.stream))) return rc;
+        }
         uint8_t *ho = pin_s ? sbs + (size_t)first * sb : s.pin_sbs;
         CU_TRY(c, cudaMemcpyAsync(ho, s.dev_sbs, sb * n, cudaMemcpyDeviceToHost, s.stream));
         CU_TRY(c, cudaEventRecord(s.done, s.stream));
@@ -647,6 +846,8 @@ int vrsbs_set_option(vrsbs_ctx *c, const char *name, int value) {
     else if (!strcmp(name, "host_chunk")) { if (value < 1) return fail(c, VRSBS_E_INVALID, "host_chunk >= 1"); c->host_chunk = value; }
     else if (!strcmp(name, "stage_timing")) c->stage_timing = value != 0;
     else if (!strcmp(name, "copy_threads")) c->copy_threads = value < 1 ? 1 : value;
+    else if (!strcmp(name, "fused")) c->fused = value != 0;
+    else if (!strcmp(name, "fast_tables")) c->fast_tables = value != 0;
     else return fail(c, VRSBS_E_INVALID, "unknown option %s", name);
     return VRSBS_OK;
 }

@@ -1,0 +1,309 @@
+// Stage 3a (fast route): temporal smoothing + layered painter's-order warp + hole fill + SBS pack in ONE pass.
+//
+// Replaces get_depth's smoothing (PredictAndGenerate.py:134-144), gpu_roll_with_offset, the layer loop,
+// the hole fill and the SBS pack of left_side_sbs (PredictAndGenerate.py:150-155,169-190,197).
+// Restatement implemented (pinned bit-for-bit by the oracle tests):
+//     every source pixel (y,xs) of layer k lands at xd = (xs + off_k) mod W; the highest k wins;
+//     unhit destinations are holes and take img[y, (xd - off_f) mod W].
+//
+// Design (all of it chosen to cut instructions per pixel: the previous kernel was issue bound at 141
+// thread-instructions per pixel, see profiles/r01a_ncu_summary.md):
+//   * key = (k+1) << 24 | RGB.  One shared-memory atomicMax per (pixel, layer) moves the colour together
+//     with the priority, so the painter's order is resolved by the atomic itself and the destination pass
+//     is a plain read of the key row: no gather, no offset lookup.  (Two sources with the same k can never
+//     meet: same k = same offset.)  Needs L <= 255; larger tables take the slow path below.
+//   * layer membership = cell LUT + one packed fp16 compare.  cell = fp16 bits >> shift indexes a byte LUT
+//     built (and validated cell by cell) by k_build_tables; its value e names the only two layers the
+//     value can belong to, and LayerEnt[e] holds the two thresholds that decide (setp.lt.f16x2).
+//   * time-major order: a CTA owns an image row y and walks the batch in time (flattened index
+//     f = y*B + t, split evenly over the grid), so the two previous RAW depth rows needed by the
+//     smoothing are already in its shared-memory ring and the smoothed depth never touches HBM.
+//   * TMA bulk copies (mbarrier completion) stage rows two iterations ahead; the SBS row leaves through two
+//     bulk stores: [warped view | input row], the right half straight from the staged input.
+//   * scatter phase: lane <-> pixel interleaved (conflict-free atomics); destination phase: 4 pixels per
+//     thread (128-bit key reads, keys zeroed in the same pass, 3 packed 32-bit stores).
+#pragma once
+#include "common.cuh"
+
+namespace vrsbs {
+
+struct FusedArgs {
+    const uint8_t *frames;     // [B,H,W,3]
+    const __half *depth;       // [B,H,W] RAW depth (SMOOTH) or already smoothed depth (!SMOOTH)
+    const __half *hist1;       // [H,W] raw t-1 of the previous batch (SMOOTH)
+    const __half *hist2;       // [H,W] raw t-2
+    uint8_t *sbs;              // [B,H,2W,3]
+    const uint8_t *blobs;      // [B][blob_bytes]
+    FrameTab *tabs;            // [B]
+    const float2 *bounds;      // [B][Lcap]    (slow path)
+    const int *offm;           // [B][Lcap+1]  (slow path)
+    uint32_t *hole_mask;       // [B][H][Wwords]
+    uint32_t *hole_list;       // global index of every mask word that has a hole (any order)
+    uint32_t *hole_count;      // pre-zeroed
+    int B, H, W, Lcap, Wwords;
+    int first;                 // frame 0 of the batch is the first frame of the clip range
+    uint32_t blob_bytes, ent_bytes;
+    float w0, w1, w2;          // smoothing weights (fp32 narrowing of the python doubles)
+};
+
+struct FusedSmem {
+    size_t img, img_stride, dep, dep_stride, out, keys, blob, blob_stride, mask, bars, total;
+};
+constexpr int kImgSlots = 3, kDepSlots = 4, kBlobSlots = 2, kBars = 3;
+
+__host__ __device__ inline FusedSmem fused_smem_layout(int W, uint32_t blob_b) {
+    FusedSmem s;
+    size_t o = 0;
+    s.img = o;  s.img_stride = align_up((size_t)W * 3 + 16, 128);  o += kImgSlots * s.img_stride;
+    s.dep = o;  s.dep_stride = align_up((size_t)W * 2, 128);       o += kDepSlots * s.dep_stride;
+    s.out = o;  o += align_up((size_t)W * 3 + 16, 128);
+    s.keys = o; o += align_up((size_t)W * 4, 128);
+    s.blob = o; s.blob_stride = align_up((size_t)blob_b, 128);     o += kBlobSlots * s.blob_stride;
+    s.mask = o; o += align_up((size_t)((W + 31) / 32) * 4, 16);
+    s.bars = o; o += 8 * kBars;
+    s.total = align_up(o, 16);
+    return s;
+}
+
+// 3 bytes at byte offset 3*x of a 4-byte aligned row
+__device__ __forceinline__ uint32_t fetch_rgb(const uint8_t *row, int x) {
+    const int ab = 3 * x;
+    const uint32_t *p = reinterpret_cast<const uint32_t *>(row) + (ab >> 2);
+    return __funnelshift_r(p[0], p[1], (ab & 3) * 8) & 0x00ffffffu;
+}
+
+template <bool SMOOTH, int NT>
+__global__ void __launch_bounds__(NT) k_warp_fused(FusedArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const FusedSmem lay = fused_smem_layout(a.W, a.blob_bytes);
+    uint32_t *keys = reinterpret_cast<uint32_t *>(smem + lay.keys);
+    uint8_t *out_row = smem + lay.out;
+    uint32_t *s_mask = reinterpret_cast<uint32_t *>(smem + lay.mask);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + lay.bars);
+
+    constexpr int NW = NT / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int W = a.W, H = a.H, B = a.B;
+    const uint32_t img_bytes = (uint32_t)W * 3, dep_bytes = (uint32_t)W * 2, W4 = (uint32_t)W * 4;
+    const int nseg = (W + 31) >> 5, nquad = W >> 2, Wwords = a.Wwords;
+
+    const long long F = (long long)B * H;
+    const long long f_lo = F * blockIdx.x / gridDim.x, f_hi = F * (blockIdx.x + 1) / gridDim.x;
+    const int N = (int)(f_hi - f_lo);
+    if (N <= 0) return;
+
+    {   // zero the key row and the mask row once; later rows are re-zeroed by the destination pass
+        uint4 z = make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < nquad; i += NT) reinterpret_cast<uint4 *>(keys)[i] = z;
+        for (int i = tid; i < Wwords; i += NT) s_mask[i] = 0;
+    }
+    if (tid == 0) {
+        for (int i = 0; i < kBars; ++i) mbar_init(&bars[i], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    auto depth_row = [&](int y, int tt) -> const __half * {
+        if (tt >= 0) return a.depth + ((size_t)tt * H + y) * W;
+        if (a.first) return a.depth + (size_t)y * W;             // clip start: history = the first raw frame
+        return (tt == -1 ? a.hist1 : a.hist2) + (size_t)y * W;
+    };
+    // thread 0: stage image row + current depth row + table blob of iteration k
+    auto issue_main = [&](int k, int y, int t, int dslot, bool bnd) {
+        uint64_t *bar = &bars[k % kBars];
+        mbar_expect_tx(bar, img_bytes + dep_bytes + a.blob_bytes + ((SMOOTH && bnd) ? 2 * dep_bytes : 0u));
+        bulk_g2s(smem + lay.img + (k % kImgSlots) * lay.img_stride, a.frames + ((size_t)t * H + y) * img_bytes, img_bytes, bar);
+        bulk_g2s(smem + lay.dep + dslot * lay.dep_stride, depth_row(y, t), dep_bytes, bar);
+        bulk_g2s(smem + lay.blob + (k & 1) * lay.blob_stride, a.blobs + (size_t)t * a.blob_bytes, a.blob_bytes, bar);
+    };
+    auto issue_hist = [&](int k, int y, int t, int s_h1, int s_h2) {
+        uint64_t *bar = &bars[k % kBars];
+        bulk_g2s(smem + lay.dep + s_h2 * lay.dep_stride, depth_row(y, t - 2), dep_bytes, bar);
+        bulk_g2s(smem + lay.dep + s_h1 * lay.dep_stride, depth_row(y, t - 1), dep_bytes, bar);
+    };
+
+    // (y,t) of iterations n, n+1, n+2 and the depth-ring slots of n and n+1 (uniform state)
+    int y0 = (int)(f_lo / B), t0 = (int)(f_lo - (long long)y0 * B);
+    auto next_yt = [&](int &y, int &t) { if (++t == B) { t = 0; ++y; } };
+    int y1 = y0, t1 = t0; next_yt(y1, t1);
+    int y2 = y1, t2 = t1; next_yt(y2, t2);
+    int c0 = 0, h1_0 = 2, h2_0 = 1, c1 = 3;                      // slots: cur(0), hist(0), cur(1)
+    if (tid == 0) {
+        issue_main(0, y0, t0, c0, true);
+        if (SMOOTH) issue_hist(0, y0, t0, h1_0, h2_0);
+        if (N > 1) issue_main(1, y1, t1, c1, t1 == 0);
+    }
+
+    const int wofs = (3 * lane) >> 2, wsh = ((3 * lane) & 3) * 8;       // lane-constant part of the pixel fetch
+
+    for (int n = 0; n < N; ++n) {
+        // slots of iteration n+1's history and of cur(n+2)
+        const bool bnd1 = SMOOTH && (t1 == 0);
+        int h1_1, h2_1, c2;
+        if (bnd1) { h2_1 = (c1 + 1) & 3; h1_1 = (c1 + 2) & 3; c2 = (c1 + 3) & 3; }
+        else      { h1_1 = c0; h2_1 = h1_0; c2 = c1 ^ c0 ^ h1_0; }
+
+        const uint8_t *img_row = smem + lay.img + (n % kImgSlots) * lay.img_stride;
+        const uint8_t *blob = smem + lay.blob + (n & 1) * lay.blob_stride;
+        const uint16_t *dcur = reinterpret_cast<const uint16_t *>(smem + lay.dep + c0 * lay.dep_stride);
+        const uint16_t *dp1 = reinterpret_cast<const uint16_t *>(smem + lay.dep + h1_0 * lay.dep_stride);
+        const uint16_t *dp2 = reinterpret_cast<const uint16_t *>(smem + lay.dep + h2_0 * lay.dep_stride);
+
+        mbar_wait(&bars[n % kBars], (n / kBars) & 1);
+
+        const BlobHdr hdr = *reinterpret_cast<const BlobHdr *>(blob);
+        const bool fast = hdr.flags & 1u;
+        const int fill = hdr.fill_off;
+        const uint32_t *img32 = reinterpret_cast<const uint32_t *>(img_row);
+
+        auto smoothed = [&](int x) -> __half2 {                 // both halves = the smoothed depth of pixel x
+            if (SMOOTH) {
+                const float c = __half2float(__ushort_as_half(dcur[x]));
+                const float p1 = __half2float(__ushort_as_half(dp1[x]));
+                const float p2 = __half2float(__ushort_as_half(dp2[x]));
+                const float m0 = __fmul_rn(c, a.w0), m1 = __fmul_rn(p1, a.w1), m2 = __fmul_rn(p2, a.w2);
+                __half2 d = __hadd2(__floats2half2_rn(m0, m0), __floats2half2_rn(m1, m1));
+                return __hadd2(d, __floats2half2_rn(m2, m2));
+            } else {
+                const uint32_t v = dcur[x];
+                uint32_t r = v | (v << 16);
+                return *reinterpret_cast<__half2 *>(&r);
+            }
+        };
+
+        // ---- scatter ------------------------------------------------------------------------------------
+        if (fast) {
+            const LayerEnt *ent = reinterpret_cast<const LayerEnt *>(blob + 16);
+            const uint8_t *lut = blob + 16 + a.ent_bytes;
+            const uint32_t shift = hdr.shift, ncells = hdr.ncells;
+#pragma unroll 4
+            for (int seg = warp; seg < nseg; seg += NW) {
+                const int x = (seg << 5) + lane;
+                if (x < W) {
+                    const __half2 dd = smoothed(x);
+                    const uint32_t ddu = *reinterpret_cast<const uint32_t *>(&dd);
+                    const uint32_t idx = min((ddu & 0xffffu) >> shift, ncells);
+                    const uint32_t e = lut[idx];
+                    const uint2 en = *reinterpret_cast<const uint2 *>(ent + e);
+                    uint32_t in_lo, below_next;             // d < hi(e-1) ; d < lo(e)
+                    asm("{\n\t.reg .pred p, q;\n\t"
+                        "setp.lt.f16x2 p|q, %2, %3;\n\t"
+                        "selp.u32 %0, 1, 0, p;\n\t"
+                        "selp.u32 %1, 1, 0, q;\n\t}"
+                        : "=r"(in_lo), "=r"(below_next) : "r"(ddu), "r"(en.x));
+                    const uint32_t px = __funnelshift_r(img32[seg * 24 + wofs], img32[seg * 24 + wofs + 1], wsh) & 0x00ffffffu;
+                    const uint32_t key0 = px | (e << 24);
+                    const uint32_t x4 = (uint32_t)x * 4u;
+                    uint32_t a0 = x4 + (en.y & 0xffffu), a1 = x4 + (en.y >> 16);
+                    a0 = min(a0, a0 - W4);
+                    a1 = min(a1, a1 - W4);
+                    if (in_lo) atomicMax(reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(keys) + a0), key0);
+                    if (!below_next) atomicMax(reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(keys) + a1), key0 + 0x01000000u);
+                }
+            }
+        } else {
+            // slow path (L > 255, non-monotone bounds, LUT too coarse): brute-force membership, layer-only keys
+            const int L = (int)(hdr.flags >> 8);
+            const int frame = t0;
+            const float2 *gb = a.bounds + (size_t)frame * a.Lcap;
+            const int *go = a.offm + (size_t)frame * (a.Lcap + 1);
+            for (int seg = warp; seg < nseg; seg += NW) {
+                const int x = (seg << 5) + lane;
+                if (x < W) {
+                    const float d = __low2float(smoothed(x));
+                    for (int k = 0; k < L; ++k) {
+                        const float2 b = __ldg(gb + k);
+                        if (b.x <= d && d < b.y) {
+                            int xd = x + __ldg(go + k + 1);
+                            xd -= (xd >= W) ? W : 0;
+                            atomicMax(&keys[xd], (uint32_t)(k + 1));
+                        }
+                    }
+                }
+            }
+        }
+        if (tid == 0) bulk_wait_read0();        // the previous row's bulk stores have finished reading out_row / img slots
+        __syncthreads();
+
+        // ---- destination pass: 4 pixels per thread --------------------------------------------------------
+        {
+            uint4 *keys4 = reinterpret_cast<uint4 *>(keys);
+            uint32_t *out32 = reinterpret_cast<uint32_t *>(out_row);
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            const int *go = a.offm + (size_t)t0 * (a.Lcap + 1);
+            for (int j = tid; j < nquad; j += NT) {
+                uint4 k = keys4[j];
+                keys4[j] = z;
+                uint32_t kk[4] = {k.x, k.y, k.z, k.w};
+                if (fast) {
+                    const uint32_t mn = min(min(k.x, k.y), min(k.z, k.w));
+                    if (mn < 0x01000000u) {
+                        uint32_t hm = 0;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            if (kk[i] < 0x01000000u) {
+                                int xs = 4 * j + i - fill;
+                                xs += (xs < 0) ? W : 0;
+                                kk[i] = fetch_rgb(img_row, xs);
+                                hm |= 1u << i;
+                            }
+                        }
+                        atomicOr(&s_mask[j >> 3], hm << ((j & 7) * 4));
+                    }
+                } else {
+                    uint32_t hm = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        int xs = 4 * j + i - (kk[i] ? __ldg(go + kk[i]) : fill);
+                        xs += (xs < 0) ? W : 0;
+                        hm |= (kk[i] ? 0u : 1u) << i;
+                        kk[i] = fetch_rgb(img_row, xs);
+                    }
+                    if (hm) atomicOr(&s_mask[j >> 3], hm << ((j & 7) * 4));
+                }
+                out32[3 * j + 0] = __byte_perm(kk[0], kk[1], 0x4210);
+                out32[3 * j + 1] = __byte_perm(kk[1], kk[2], 0x5421);
+                out32[3 * j + 2] = __byte_perm(kk[2], kk[3], 0x6542);
+            }
+        }
+        fence_async_smem();
+        __syncthreads();
+
+        const long long row = (long long)t0 * H + y0;             // global row index of this iteration
+        if (tid == 0) {
+            uint8_t *go = a.sbs + (size_t)row * img_bytes * 2;
+            bulk_s2g(go, out_row, img_bytes);
+            bulk_s2g(go + img_bytes, img_row, img_bytes);
+            bulk_commit();
+            if (n + 2 < N) issue_main(n + 2, y2, t2, c2, t2 == 0);
+            if (SMOOTH && bnd1 && n + 1 < N) issue_hist(n + 1, y1, t1, h1_1, h2_1);
+        }
+        // ---- hole mask row -> global bitmask + work list for the blur -----------------------------------------
+        if (warp < ((Wwords + 31) >> 5)) {
+            const int w = tid;
+            uint32_t v = 0;
+            if (w < Wwords) {
+                v = s_mask[w];
+                s_mask[w] = 0;
+                a.hole_mask[(size_t)row * Wwords + w] = v;
+            }
+            const unsigned nz = __ballot_sync(0xffffffffu, v != 0u);
+            if (nz) {
+                const unsigned holes = __reduce_add_sync(0xffffffffu, (unsigned)__popc(v));
+                uint32_t base = 0;
+                if (lane == 0) {
+                    base = atomicAdd(a.hole_count, (uint32_t)__popc(nz));
+                    atomicAdd(&a.tabs[t0].holes, (unsigned long long)holes);
+                }
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (v) a.hole_list[base + __popc(nz & ((1u << lane) - 1u))] = (uint32_t)(row * Wwords + w);
+            }
+        }
+        // advance the uniform state
+        y0 = y1; t0 = t1; y1 = y2; t1 = t2; next_yt(y2, t2);
+        h2_0 = h2_1; h1_0 = h1_1; c0 = c1; c1 = c2;
+    }
+    if (tid == 0) bulk_wait0();
+}
+
+}  // namespace vrsbs

@@ -1,4 +1,5 @@
-// Stage 3a: the layered painter's-order warp as a per-row scatter/gather in shared memory.
+// Stage 3a (general route: any width / alignment / layer count; the fast route is warp_fused.cuh):
+// the layered painter's-order warp as a per-row scatter/gather in shared memory.
 //
 // Replaces gpu_roll_with_offset + the layer loop + hole fill + SBS pack of left_side_sbs
 // (PredictAndGenerate.py:150-155,169-190,197).  Restatement being implemented (SURVEY.md section 0,
@@ -33,10 +34,9 @@ struct WarpArgs {
     const float2 *bounds;      // [B][Lcap]
     const int *offm;           // [B][Lcap+1]
     uint32_t *hole_mask;       // [B][H][Wwords]
-    uint32_t *tile_flag;       // [B][tiles_y][tiles_x], pre-zeroed: 1 once a hole was seen in the tile
-    uint32_t *tile_list;       // work list for the blur kernel (tiles with holes), any order
-    uint32_t *tile_count;      // pre-zeroed
-    int B, H, W, Lcap, Wwords, tiles_x, tiles_y, tile_h_shift, tile_seg_shift;
+    uint32_t *hole_list;       // global index of every mask word that has a hole (blur work list, any order)
+    uint32_t *hole_count;      // pre-zeroed
+    int B, H, W, Lcap, Wwords;
 };
 
 constexpr int kMaxSeg = 8;     // 32-pixel segments per warp per row (bounds register state)
@@ -210,10 +210,7 @@ __global__ void __launch_bounds__(NT) k_warp_rows(WarpArgs a) {
                 mask_row[sg] = hm;
                 if (hm) {
                     hole_acc += __popc(hm);
-                    // first hole seen in this blur tile: append the tile to the blur work list
-                    const uint32_t tile = ((uint32_t)frame * a.tiles_y + (uint32_t)((row - (long long)frame * H) >> a.tile_h_shift)) *
-                                              a.tiles_x + (uint32_t)(sg >> a.tile_seg_shift);
-                    if (atomicExch(&a.tile_flag[tile], 1u) == 0u) a.tile_list[atomicAdd(a.tile_count, 1u)] = tile;
+                    a.hole_list[atomicAdd(a.hole_count, 1u)] = (uint32_t)(row * a.Wwords + sg);
                 }
             }
             if (((sg + 1) << 5) <= W) {
