@@ -10,8 +10,8 @@
 //                   vertical pair sums T_i = row(y-i) + row(y+i), then each lane evaluates one
 //                   (hole, channel): horizontal pair sums x unique weights.  Results go to a scratch
 //                   plane, NOT to the SBS frame, because neighbouring holes still need the pre-blur values.
-//   k_blur_commit : copies the scratch values of the listed holes into the SBS frame.
-//   k_strip_restore: result_img[:, 0:strip] = img[:, 0:strip] (PredictAndGenerate.py:196).
+//   k_blur_commit : copies the scratch values of the listed holes into the SBS frame, then restores the strip:
+//                   result_img[:, 0:strip] = img[:, 0:strip] (PredictAndGenerate.py:196).
 //
 // Arithmetic.  The oracle defines the blurred value as the EXACT sum of fp32-weight x u8-pixel products,
 // rounded half-to-even (DESIGN.md "blur parity").  Integer path (PARTS = 2 or 3): when the weights are 4-fold
@@ -31,12 +31,13 @@ struct BlurArgs {
     uint8_t *sbs;                // [B,H,2W,3]
     const FrameTab *tabs;        // [B]
     const uint32_t *hole_mask;   // [B][H][Wwords]
-    const uint32_t *hole_list;   // global mask-word indices
+    const uint32_t *hole_list;   // (global row << 8 | word index) of the mask words that contain holes
     const uint32_t *hole_count;
     uint8_t *plane;              // [B,H,W,3] scratch: blurred values of hole pixels
     const uint32_t *wq;          // integer path: [PARTS][(cy+1)][(cx+1)] parts of w * 2^S, low part first (i = |dy|, j = |dx|)
     const float *weights;        // generic: [ky][kx]
     int B, H, W, Wwords, kx, ky, wshift;   // wshift = S
+    unsigned long long magic_h;  // ceil(2^40 / H): frame = (row * magic_h) >> 40, exact for row < 2^24
 };
 
 // per-warp shared memory: T[(rows)][cols] u16, cols = 3*(32 + kx - 1) rounded up to a multiple of 32
@@ -58,11 +59,11 @@ __global__ void __launch_bounds__(256) k_blur_holes(BlurArgs a) {
     const uint32_t count = *a.hole_count;
 
     for (uint32_t ei = blockIdx.x * nwarps + warp; ei < count; ei += gridDim.x * nwarps) {
-        const uint32_t gw = a.hole_list[ei];
-        const uint32_t row = gw / a.Wwords, w = gw - row * a.Wwords;
-        const int b = row / H, y = row - b * H;
+        const uint32_t ent = a.hole_list[ei];
+        const uint32_t row = ent >> 8, w = ent & 0xffu;
+        const int b = (int)(((unsigned long long)row * a.magic_h) >> 40), y = (int)row - b * H;
         const int strip = a.tabs[b].strip;
-        uint32_t m = a.hole_mask[gw];
+        uint32_t m = a.hole_mask[(size_t)row * a.Wwords + w];
         const int xw = (int)w * 32;
         if (strip > xw) m = (strip - xw >= 32) ? 0u : (m & ~((1u << (strip - xw)) - 1u));
         if (m == 0u) continue;
@@ -128,30 +129,152 @@ __global__ void __launch_bounds__(256) k_blur_holes(BlurArgs a) {
     }
 }
 
-// one warp per listed mask word: plane -> SBS frame for the hole pixels right of the strip
-__global__ void __launch_bounds__(256) k_blur_commit(BlurArgs a) {
+// ---- specialised hole blur: kernel size known at compile time, integer weights in the kernel parameters ----
+// Same algorithm as k_blur_holes, three things tightened (the generic kernel was issue bound at ~980
+// warp-instructions per listed word, profiles/r01b):
+//   * weights live in the parameter constant bank and every (i,j) is unrolled, so a tap costs two LDS.U16, one
+//     add and PARTS IMADs with a constant operand - no weight loads, no loop counters;
+//   * interior words stage their footprint with aligned 32-bit loads (one or two per lane per row) and build the
+//     vertical pair sums on packed bytes (2 x 16-bit lanes per register);
+//   * hole positions come from a rank table instead of __fns.
+template <int PARTS, int CX, int CY>
+struct BlurWeights { uint32_t q[PARTS][(CY + 1) * (CX + 1)]; };
+
+template <int PARTS, int CX, int CY>
+__global__ void __launch_bounds__(256) k_blur_holes_fixed(BlurArgs a, const __grid_constant__ BlurWeights<PARTS, CX, CY> wts) {
+    constexpr int PBITS = PARTS == 2 ? 15 : 13;
+    constexpr int KX = 2 * CX + 1, NPX = 32 + KX - 1;
+    constexpr int PHASE = ((-3 * CX) % 4 + 4) % 4;                    // (96 w - 3 CX) mod 4: the same for every word
+    constexpr int NWORDS = (PHASE + 3 * NPX + 3) / 4;                 // aligned 32-bit words that cover the footprint
+    constexpr int COLS = (NWORDS * 4 + 7) / 8 * 8;                    // u16 columns per T row (16-byte multiple)
+    static_assert(NWORDS <= 64, "footprint wider than two words per lane");
+    extern __shared__ __align__(16) uint8_t blur_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int W = a.W, H = a.H;
+    uint16_t *T = reinterpret_cast<uint16_t *>(blur_smem) + (size_t)warp * ((CY + 1) * COLS + 32);
+    uint16_t *pos = T + (CY + 1) * COLS;                              // hole rank -> bit position
     const uint32_t count = *a.hole_count;
+    const size_t pitch = (size_t)W * 6;
+
     for (uint32_t ei = blockIdx.x * nwarps + warp; ei < count; ei += gridDim.x * nwarps) {
-        const uint32_t gw = a.hole_list[ei];
-        const uint32_t row = gw / a.Wwords, w = gw - row * a.Wwords;
-        const int b = row / a.H;
-        const int x = (int)w * 32 + lane;
-        if (((a.hole_mask[gw] >> lane) & 1u) && x >= a.tabs[b].strip && x < a.W) {
-            const uint8_t *src = a.plane + ((size_t)row * a.W + x) * 3;
-            uint8_t *dst = a.sbs + ((size_t)row * 2 * a.W + x) * 3;
-            dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+        const uint32_t ent = a.hole_list[ei];
+        const uint32_t row = ent >> 8, w = ent & 0xffu;
+        const int b = (int)(((unsigned long long)row * a.magic_h) >> 40), y = (int)row - b * H;
+        const int strip = a.tabs[b].strip;
+        uint32_t m = a.hole_mask[(size_t)row * a.Wwords + w];
+        const int xw = (int)w * 32;
+        if (strip > xw) m = (strip - xw >= 32) ? 0u : (m & ~((1u << (strip - xw)) - 1u));
+        if (m == 0u) continue;
+        __syncwarp();
+        if ((m >> lane) & 1u) pos[__popc(m & ((1u << lane) - 1u))] = (uint16_t)lane;
+        const uint8_t *left = a.sbs + (size_t)b * H * pitch;
+        const int s0 = 3 * (xw - CX);                                 // byte offset of the footprint in its row
+        int phase;                                                    // byte column of footprint byte 0 inside T
+        if (xw - CX >= 0 && xw + 31 + CX < W) {
+            // interior: aligned words, packed vertical pair sums
+            const int A = s0 - PHASE;
+            phase = PHASE;
+#pragma unroll
+            for (int half = 0; half < (NWORDS + 31) / 32; ++half) {
+                const int k = lane + 32 * half;
+                if (k < NWORDS) {
+                    const uint8_t *colp = left + A + 4 * k;
+                    uint32_t v[2 * CY + 1];
+#pragma unroll
+                    for (int i = 0; i <= 2 * CY; ++i)
+                        v[i] = __ldg(reinterpret_cast<const uint32_t *>(colp + (size_t)reflect_idx(y + i - CY, H) * pitch));
+#pragma unroll
+                    for (int i = 0; i <= CY; ++i) {
+                        const uint32_t p = v[CY - i], q = v[CY + i];
+                        uint32_t lo = p & 0x00ff00ffu, hi = (p >> 8) & 0x00ff00ffu;
+                        if (i) { lo += q & 0x00ff00ffu; hi += (q >> 8) & 0x00ff00ffu; }
+                        *reinterpret_cast<uint2 *>(T + i * COLS + 4 * k) = make_uint2(__byte_perm(lo, hi, 0x5410), __byte_perm(lo, hi, 0x7632));
+                    }
+                }
+            }
+        } else {
+            // border words: byte by byte with reflect padding
+            phase = 0;
+            for (int c = lane; c < 3 * NPX; c += 32) {
+                const int px = c / 3, ch = c - px * 3;
+                const int X = min(max(reflect_idx(xw - CX + px, W), 0), W - 1);
+                const uint8_t *colp = left + (size_t)X * 3 + ch;
+                T[c] = colp[(size_t)y * pitch];
+#pragma unroll
+                for (int i = 1; i <= CY; ++i)
+                    T[i * COLS + c] = (uint16_t)colp[(size_t)reflect_idx(y - i, H) * pitch] + (uint16_t)colp[(size_t)reflect_idx(y + i, H) * pitch];
+            }
+        }
+        __syncwarp();
+        const int nh = __popc(m);
+        const int slot = lane / 3, ch = lane - slot * 3;
+        for (int h0 = 0; h0 < nh; h0 += 10) {
+            const int hi_ = h0 + slot;
+            if (lane < 30 && hi_ < nh) {
+                const int xo = pos[hi_];
+                const uint16_t *Tc = T + phase + 3 * (xo + CX) + ch;
+                uint32_t acc[PARTS];
+#pragma unroll
+                for (int p = 0; p < PARTS; ++p) acc[p] = 0u;
+#pragma unroll
+                for (int i = 0; i <= CY; ++i) {
+#pragma unroll
+                    for (int j = 0; j <= CX; ++j) {
+                        const uint32_t v = j ? (uint32_t)Tc[i * COLS - 3 * j] + (uint32_t)Tc[i * COLS + 3 * j] : (uint32_t)Tc[i * COLS];
+#pragma unroll
+                        for (int p = 0; p < PARTS; ++p) acc[p] += v * wts.q[p][i * (CX + 1) + j];
+                    }
+                }
+                unsigned long long total = 0ull;
+#pragma unroll
+                for (int p = PARTS - 1; p >= 0; --p) total = (total << PBITS) + acc[p];
+                const int S = a.wshift;
+                unsigned long long q = total >> S;
+                const unsigned long long r = total & ((1ull << S) - 1ull), half = 1ull << (S - 1);
+                q += (r > half || (r == half && (q & 1ull))) ? 1ull : 0ull;
+                a.plane[((size_t)row * W + xw + xo) * 3 + ch] = (uint8_t)q;
+            }
         }
     }
 }
+template <int CX, int CY>
+__host__ __device__ constexpr size_t blur_fixed_warp_smem() {
+    constexpr int PHASE = ((-3 * CX) % 4 + 4) % 4;
+    constexpr int NWORDS = (PHASE + 3 * (32 + 2 * CX) + 3) / 4, COLS = (NWORDS * 4 + 7) / 8 * 8;
+    return ((size_t)(CY + 1) * COLS + 32) * sizeof(uint16_t);
+}
 
-// result_img[:, 0:strip] = img[:, 0:strip]  (PredictAndGenerate.py:196); one warp per image row.
-__global__ void __launch_bounds__(256) k_strip_restore(BlurArgs a) {
-    const int lane = threadIdx.x & 31;
-    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+// plane -> SBS frame for the listed holes right of the strip, then result_img[:, 0:strip] = img[:, 0:strip]
+// (PredictAndGenerate.py:196).  A warp takes 32 list entries at a time: lane l fetches entry l's word index, mask
+// and strip (one round of dependent loads for 32 entries), then the warp walks the entries, lane = pixel.
+__global__ void __launch_bounds__(256) k_blur_commit(BlurArgs a, int do_commit) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t count = do_commit ? *a.hole_count : 0u;
+    for (uint32_t e0 = (blockIdx.x * nwarps + warp) * 32u; e0 < count; e0 += gridDim.x * nwarps * 32u) {
+        uint32_t gw = 0, m = 0, strip = 0;
+        if (e0 + lane < count) {
+            gw = a.hole_list[e0 + lane];
+            m = a.hole_mask[(size_t)(gw >> 8) * a.Wwords + (gw & 0xffu)];
+            strip = (uint32_t)a.tabs[(int)(((unsigned long long)(gw >> 8) * a.magic_h) >> 40)].strip;
+        }
+        const int n = min(32u, count - e0);
+#pragma unroll 4
+        for (int k = 0; k < n; ++k) {
+            const uint32_t g = __shfl_sync(0xffffffffu, gw, k), mk = __shfl_sync(0xffffffffu, m, k), st = __shfl_sync(0xffffffffu, strip, k);
+            const uint32_t row = g >> 8, w = g & 0xffu;
+            const uint32_t x = w * 32u + lane;
+            if (((mk >> lane) & 1u) && x >= st) {
+                const uint8_t *src = a.plane + ((size_t)row * a.W + x) * 3;
+                uint8_t *dst = a.sbs + ((size_t)row * 2 * a.W + x) * 3;
+                const uint8_t r0 = src[0], r1 = src[1], r2 = src[2];
+                dst[0] = r0; dst[1] = r1; dst[2] = r2;
+            }
+        }
+    }
+    const long long tw = (long long)gridDim.x * nwarps;
     const long long rows = (long long)a.B * a.H;
-    for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += nwarps) {
-        const int nbytes = a.tabs[r / a.H].strip * 3;
+    for (long long r = (long long)blockIdx.x * nwarps + warp; r < rows; r += tw) {
+        const int nbytes = a.tabs[(int)(((unsigned long long)r * a.magic_h) >> 40)].strip * 3;
         const uint8_t *src = a.frames + r * (size_t)a.W * 3;
         uint8_t *dst = a.sbs + r * (size_t)a.W * 6;
         for (int c = lane; c < nbytes; c += 32) dst[c] = src[c];

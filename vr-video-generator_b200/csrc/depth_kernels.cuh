@@ -132,53 +132,90 @@ struct DepthMaxArgs {
     size_t n;                            // H*W, multiple of 8
 };
 
+// 16-bit order-preserving key of an fp16 bit pattern (NaN -> 0x1ffff, above every number)
+__device__ __forceinline__ uint32_t h16_key(uint32_t u) {
+    const uint32_t k = (u & 0x8000u) ? (~u & 0xffffu) : (u | 0x8000u);
+    return ((u & 0x7fffu) > 0x7c00u) ? 0x1ffffu : k;
+}
+
 __global__ void __launch_bounds__(256) k_depth_max(DepthMaxArgs a) {
-    extern __shared__ uint32_t s_red[];          // [B] max | [B] nan
-    uint32_t *s_max = s_red, *s_nan = s_red + a.B;
-    for (int i = threadIdx.x; i < 2 * a.B; i += blockDim.x) s_red[i] = 0;
+    extern __shared__ uint32_t s_red[];          // [B] keys
+    for (int i = threadIdx.x; i < a.B; i += blockDim.x) s_red[i] = 0;
     __syncthreads();
     const size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = v * 8 < a.n;
     const size_t base = active ? v * 8 : 0;
     union V { uint4 u; __half2 h[4]; };
-    V p1, p2, cur;
-    p1.u = p2.u = make_uint4(0, 0, 0, 0);
+    // raw depth of t-1 / t-2 as floats (each raw value is converted once and used by three frames)
+    float p1[8], p2[8];
+    V praw1, praw2;
+    praw1.u = praw2.u = make_uint4(0, 0, 0, 0);
     if (active && !a.first) {
-        p1.u = __ldg(reinterpret_cast<const uint4 *>(a.hist1 + base));
-        p2.u = __ldg(reinterpret_cast<const uint4 *>(a.hist2 + base));
+        praw1.u = __ldg(reinterpret_cast<const uint4 *>(a.hist1 + base));
+        praw2.u = __ldg(reinterpret_cast<const uint4 *>(a.hist2 + base));
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float2 f1 = __half22float2(praw1.h[e]), f2 = __half22float2(praw2.h[e]);
+        p1[2 * e] = f1.x; p1[2 * e + 1] = f1.y; p2[2 * e] = f2.x; p2[2 * e + 1] = f2.y;
     }
     const int lane = threadIdx.x & 31;
-#pragma unroll 4
-    for (int t = 0; t < a.B; ++t) {
-        uint32_t enc = 0;
-        bool nan = false;
-        if (active) {
-            cur.u = __ldg(reinterpret_cast<const uint4 *>(a.raw + (size_t)t * a.n + base));
-            if (a.first && t == 0) { p1.u = cur.u; p2.u = cur.u; }
-            __half2 m = smooth3x2(cur.h[0], p1.h[0], p2.h[0], a.sw);
+    const float w0 = a.sw.w_now, w1 = a.sw.w_prev1, w2 = a.sw.w_prev2;
+    // 4 frames per step: their four 16-byte loads are issued together (the kernel is latency bound otherwise)
+    constexpr int PF = 4;
+    for (int tb = 0; tb < a.B; tb += PF) {
+        V q[PF];
 #pragma unroll
-            for (int e = 1; e < 4; ++e) m = __hmax2_nan(m, smooth3x2(cur.h[e], p1.h[e], p2.h[e], a.sw));
-            const float2 f = __half22float2(m);
-            nan = (f.x != f.x) || (f.y != f.y);
-            enc = nan ? 0u : max(f2ord(f.x), f2ord(f.y));
-            p2.u = p1.u;
-            p1.u = cur.u;
+        for (int i = 0; i < PF; ++i) {
+            q[i].u = make_uint4(0, 0, 0, 0);
+            if (active && tb + i < a.B) q[i].u = __ldg(reinterpret_cast<const uint4 *>(a.raw + (size_t)(tb + i) * a.n + base));
         }
-        enc = __reduce_max_sync(0xffffffffu, enc);
-        const unsigned any_nan = __ballot_sync(0xffffffffu, nan);
-        if (lane == 0) {
-            atomicMax(&s_max[t], enc);
-            if (any_nan) s_nan[t] = 1;
+#pragma unroll
+        for (int i = 0; i < PF; ++i) {
+            const int t = tb + i;
+            if (t >= a.B) break;                              // uniform
+            uint32_t key = 0;
+            if (active) {
+                V cur; cur.u = q[i].u;
+                float c[8];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(cur.h[e]); c[2 * e] = f.x; c[2 * e + 1] = f.y; }
+                if (a.first && t == 0) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) p1[e] = p2[e] = c[e];
+                    praw1.u = praw2.u = cur.u;
+                }
+                __half2 m;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    __half2 d = __hadd2(__floats2half2_rn(__fmul_rn(c[2 * e], w0), __fmul_rn(c[2 * e + 1], w0)),
+                                        __floats2half2_rn(__fmul_rn(p1[2 * e], w1), __fmul_rn(p1[2 * e + 1], w1)));
+                    d = __hadd2(d, __floats2half2_rn(__fmul_rn(p2[2 * e], w2), __fmul_rn(p2[2 * e + 1], w2)));
+                    m = e ? __hmax2_nan(m, d) : d;
+                }
+                m = __hmax2_nan(m, __lowhigh2highlow(m));
+                key = h16_key((uint32_t)__half_as_ushort(__low2half(m)));
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { p2[e] = p1[e]; p1[e] = c[e]; }
+                praw2.u = praw1.u;
+                praw1.u = cur.u;
+            }
+            key = __reduce_max_sync(0xffffffffu, key);
+            if (lane == 0 && key) atomicMax(&s_red[t], key);
         }
     }
     if (active) {
-        *reinterpret_cast<uint4 *>(a.hist1_out + base) = p1.u;
-        *reinterpret_cast<uint4 *>(a.hist2_out + base) = p2.u;
+        *reinterpret_cast<uint4 *>(a.hist1_out + base) = praw1.u;
+        *reinterpret_cast<uint4 *>(a.hist2_out + base) = praw2.u;
     }
     __syncthreads();
     for (int t = threadIdx.x; t < a.B; t += blockDim.x) {
-        if (s_max[t]) atomicMax(&a.frame_max[t], s_max[t]);
-        if (s_nan[t]) atomicOr(&a.frame_nan[t], 1u);
+        const uint32_t key = s_red[t];
+        if (key == 0x1ffffu) atomicOr(&a.frame_nan[t], 1u);
+        else if (key) {
+            const uint32_t u = (key & 0x8000u) ? (key & 0x7fffu) : (~key & 0xffffu);
+            atomicMax(&a.frame_max[t], f2ord(__half2float(__ushort_as_half((unsigned short)u))));
+        }
     }
 }
 

@@ -52,8 +52,9 @@ __device__ __forceinline__ int clamp_int(double v) {
 }
 
 __global__ void __launch_bounds__(256) k_build_tables(TableArgs a) {
-    extern __shared__ double s_val[];          // [Lcap+2] unsorted marks, then [Lcap+2] sorted
-    double *s_sorted = s_val + (a.Lcap + 2);
+    extern __shared__ double s_val[];          // [max(Lcap+2,B)] unsorted marks, then as many sorted
+    const int sstride = max(a.Lcap + 2, a.B);
+    double *s_sorted = s_val + sstride;
     __shared__ double s_r0, s_r1, s_span, s_top;
     __shared__ int s_limit, s_start, s_nneg, s_E, s_bad;
     __shared__ float s_max;
@@ -61,25 +62,33 @@ __global__ void __launch_bounds__(256) k_build_tables(TableArgs a) {
     const int b = blockIdx.x;
     FrameTab *tab = a.tabs + b;
 
+    // this frame's own range for every frame up to b, in parallel (the divisions are the expensive part) ...
+    double *s_cur0 = s_val, *s_cur1 = s_sorted;                      // both reused as mark buffers afterwards
+    for (int t = threadIdx.x; t <= b; t += blockDim.x) {
+        const float fm = ord2f(a.frame_max[t]);
+        const double c = ceil((double)fm);
+        const int lim = (a.frame_nan[t] || !(c == c)) ? 0 : clamp_int(c);
+        // bg * H * limit / 14, left to right
+        s_cur0[t] = __ddiv_rn(__dmul_rn(__dmul_rn(a.offset_bg, (double)a.H), (double)lim), 14.0);
+        s_cur1[t] = __ddiv_rn(__dmul_rn(__dmul_rn(a.offset_fg, (double)a.H), (double)lim), 14.0);
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
         double l0 = a.state_in->range[0], l1 = a.state_in->range[1];
         int has = a.state_in->has_last;
         double r0 = 0, r1 = 0;
-        int limit = 0;
-        float fmax = 0.f;
+        // ... then the EMA chain: (last + cur) / 2 is exact as a multiplication by 0.5
         for (int t = 0; t <= b; ++t) {
-            fmax = ord2f(a.frame_max[t]);
-            double c = ceil((double)fmax);
-            limit = (a.frame_nan[t] || !(c == c)) ? 0 : clamp_int(c);
-            // bg * H * limit / 14, left to right
-            r0 = __ddiv_rn(__dmul_rn(__dmul_rn(a.offset_bg, (double)a.H), (double)limit), 14.0);
-            r1 = __ddiv_rn(__dmul_rn(__dmul_rn(a.offset_fg, (double)a.H), (double)limit), 14.0);
+            r0 = s_cur0[t]; r1 = s_cur1[t];
             if (has) {
-                r0 = __ddiv_rn(__dadd_rn(l0, r0), 2.0);
-                r1 = __ddiv_rn(__dadd_rn(l1, r1), 2.0);
+                r0 = __dmul_rn(__dadd_rn(l0, r0), 0.5);
+                r1 = __dmul_rn(__dadd_rn(l1, r1), 0.5);
             }
             l0 = r0; l1 = r1; has = 1;
         }
+        const float fmax = ord2f(a.frame_max[b]);
+        const double cb = ceil((double)fmax);
+        const int limit = (a.frame_nan[b] || !(cb == cb)) ? 0 : clamp_int(cb);
         if (b == a.B - 1) {
             a.state_out->range[0] = r0;
             a.state_out->range[1] = r1;

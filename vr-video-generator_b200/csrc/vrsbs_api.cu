@@ -64,6 +64,7 @@ struct vrsbs_ctx {
     Scratch scratch[2];
     float *weights = nullptr;
     uint32_t *wq = nullptr;              // integer blur weights [parts][(ky/2+1)*(kx/2+1)]
+    std::vector<uint32_t> wq_host;
     int kx = 0, ky = 0, wparts = 0, wshift = 0;
     int ent_cap = 0, lut_cap = 0;        // fast-path table capacities of the last vrsbs_build_tables
     int fused = 1;                       // option: use the fused route in vrsbs_process_batch when possible
@@ -144,6 +145,7 @@ int alloc_scratch(vrsbs_ctx *c, Scratch &s) {
 int check_dims(vrsbs_ctx *c, int B, int H, int W) {
     if (!c) return VRSBS_E_INVALID;
     if (B < 1 || B > c->max_batch) return fail(c, VRSBS_E_INVALID, "batch %d outside [1,%d]", B, c->max_batch);
+    if ((long long)B * H >= (1 << 24)) return fail(c, VRSBS_E_INVALID, "batch of %d frames x %d rows exceeds 2^24 rows", B, H);
     if (H < 2 || H > c->max_h || W < 2 || W > c->max_w)
         return fail(c, VRSBS_E_INVALID, "frame %dx%d outside the context limit %dx%d", H, W, c->max_h, c->max_w);
     return VRSBS_OK;
@@ -271,7 +273,7 @@ int launch_tables(vrsbs_ctx *c, Scratch &s, int B, int H, int W, cudaStream_t st
     a.B = B; a.H = H; a.W = W; a.Lcap = c->max_layers;
     fast_caps(c, H, &c->ent_cap, &c->lut_cap);
     a.blobs = s.blobs; a.ent_cap = c->ent_cap; a.lut_cap = c->lut_cap;
-    const size_t smem = sizeof(double) * 2 * (c->max_layers + 2);
+    const size_t smem = sizeof(double) * 2 * (size_t)(c->max_layers + 2 > B ? c->max_layers + 2 : B);
     StageTimer timer(c, st, 1);
     k_build_tables<<<B, 256, smem, st>>>(a);
     CU_TRY(c, cudaGetLastError());
@@ -330,40 +332,75 @@ bool fused_capable(const vrsbs_ctx *c, const void *frames, const void *depth, co
            ((uintptr_t)sbs % 16 == 0) && smem <= 200 * 1024;
 }
 
+// hole values -> SBS frame (when blur is on) and strip restore, one kernel
+int launch_commit(vrsbs_ctx *c, const BlurArgs &b, int do_commit, cudaStream_t st) {
+    StageTimer timer(c, st, 4);
+    k_blur_commit<<<(unsigned)(c->sm_count * 8), 256, 0, st>>>(b, do_commit);
+    CU_TRY(c, cudaGetLastError());
+    c->launches++;
+    return VRSBS_OK;
+}
+
+template <int PARTS, int CX, int CY>
+int launch_blur_fixed(vrsbs_ctx *c, const BlurArgs &b, cudaStream_t st) {
+    BlurWeights<PARTS, CX, CY> wts;
+    memcpy(wts.q, c->wq_host.data(), sizeof(wts.q));
+    auto kern = k_blur_holes_fixed<PARTS, CX, CY>;
+    const size_t per_warp = blur_fixed_warp_smem<CX, CY>();
+    const int warps = 8;
+    const size_t bsmem = per_warp * warps;
+    CU_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+    int occ = 0;
+    CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, bsmem));
+    if (occ < 1) occ = 1;
+    kern<<<(unsigned)(c->sm_count * occ), warps * 32, bsmem, st>>>(b, wts);
+    return VRSBS_OK;
+}
+
 int launch_blur(vrsbs_ctx *c, Scratch &s, const uint8_t *frames, int B, int H, int W, uint8_t *sbs, cudaStream_t st) {
     if (!s.plane) CU_TRY(c, dmalloc(&s.plane, (size_t)c->max_batch * c->max_h * c->max_w * 3));
     BlurArgs b{};
     b.frames = frames; b.sbs = sbs; b.tabs = s.tabs; b.hole_mask = s.hole_mask; b.hole_list = s.hole_list;
     b.hole_count = s.hole_count; b.plane = s.plane; b.wq = c->wq; b.weights = c->weights;
     b.B = B; b.H = H; b.W = W; b.Wwords = (W + 31) / 32; b.kx = c->kx; b.ky = c->ky; b.wshift = c->wshift;
-    const size_t per_warp = blur_warp_smem(c->kx, c->ky, c->wparts > 0);
-    int warps = 8;
-    while (warps > 1 && per_warp * warps > 96 * 1024) warps >>= 1;
-    const size_t bsmem = per_warp * warps;
-    if (bsmem > 200 * 1024) return fail(c, VRSBS_E_INVALID, "blur kernel %dx%d needs %zu B shared memory per warp", c->kx, c->ky, per_warp);
-    auto kern = c->wparts == 2 ? k_blur_holes<2> : (c->wparts == 3 ? k_blur_holes<3> : k_blur_holes<0>);
-    CU_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
-    int occ = 0;
-    CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, bsmem));
-    if (occ < 1) occ = 1;
+    b.magic_h = ((1ull << 40) + (unsigned long long)H - 1) / (unsigned long long)H;
+    const int cx = c->kx / 2, cy = c->ky / 2;
+    const bool aligned = (W % 2 == 0) && ((uintptr_t)sbs % 4 == 0);
     {
         StageTimer timer(c, st, 3);
-        kern<<<(unsigned)(c->sm_count * occ), warps * 32, bsmem, st>>>(b);
+        bool done = false;
+#define VRSBS_BLUR_FIXED(P, CXv, CYv)                                                   \
+        if (!done && aligned && c->wparts == P && cx == CXv && cy == CYv) {             \
+            int rc = launch_blur_fixed<P, CXv, CYv>(c, b, st);                          \
+            if (rc) return rc;                                                          \
+            done = true;                                                                \
+        }
+        VRSBS_BLUR_FIXED(2, 5, 4)      // 1080p: 11 x 9
+        VRSBS_BLUR_FIXED(3, 5, 4)
+        VRSBS_BLUR_FIXED(2, 9, 8)      // 4K: 19 x 17
+        VRSBS_BLUR_FIXED(3, 9, 8)
+        VRSBS_BLUR_FIXED(2, 4, 3)      // 720p: 9 x 7
+        VRSBS_BLUR_FIXED(3, 4, 3)
+        VRSBS_BLUR_FIXED(2, 6, 5)      // 1440p: 13 x 11
+        VRSBS_BLUR_FIXED(3, 6, 5)
+#undef VRSBS_BLUR_FIXED
+        if (!done) {
+            const size_t per_warp = blur_warp_smem(c->kx, c->ky, c->wparts > 0);
+            int warps = 8;
+            while (warps > 1 && per_warp * warps > 96 * 1024) warps >>= 1;
+            const size_t bsmem = per_warp * warps;
+            if (bsmem > 200 * 1024) return fail(c, VRSBS_E_INVALID, "blur kernel %dx%d needs %zu B shared memory per warp", c->kx, c->ky, per_warp);
+            auto kern = c->wparts == 2 ? k_blur_holes<2> : (c->wparts == 3 ? k_blur_holes<3> : k_blur_holes<0>);
+            CU_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+            int occ = 0;
+            CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, bsmem));
+            if (occ < 1) occ = 1;
+            kern<<<(unsigned)(c->sm_count * occ), warps * 32, bsmem, st>>>(b);
+        }
         CU_TRY(c, cudaGetLastError());
-        k_blur_commit<<<(unsigned)(c->sm_count * 8), 256, 0, st>>>(b);
-        CU_TRY(c, cudaGetLastError());
+        c->launches++;
     }
-    c->launches += 2;
-    long long rblocks = ((long long)B * H + 7) / 8;
-    const long long cap = (long long)c->sm_count * 8;
-    if (rblocks > cap) rblocks = cap;
-    {
-        StageTimer timer(c, st, 4);
-        k_strip_restore<<<(unsigned)rblocks, 256, 0, st>>>(b);
-    }
-    CU_TRY(c, cudaGetLastError());
-    c->launches++;
-    return VRSBS_OK;
+    return launch_commit(c, b, 1, st);
 }
 
 int check_blur_ready(vrsbs_ctx *c, int H, int W) {
@@ -641,6 +678,7 @@ int vrsbs_set_blur_weights(vrsbs_ctx *c, const float *w, int kx, int ky) {
                     unsigned long long v = (unsigned long long)ldexp((double)w[(cy - i) * kx + (cx - j)], S);
                     for (int p = 0; p < parts; ++p) { q[(size_t)p * nu + i * (cx + 1) + j] = (uint32_t)(v & ((1ull << pbits) - 1ull)); v >>= pbits; }
                 }
+            c->wq_host = q;
             CU_TRY(c, dmalloc(&c->wq, q.size()));
             CU_TRY(c, cudaMemcpy(c->wq, q.data(), sizeof(uint32_t) * q.size(), cudaMemcpyHostToDevice));
             c->wparts = parts; c->wshift = S;

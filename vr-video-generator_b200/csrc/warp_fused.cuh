@@ -23,6 +23,8 @@
 //   * scatter phase: lane <-> pixel interleaved (conflict-free atomics); destination phase: 4 pixels per
 //     thread (128-bit key reads, keys zeroed in the same pass, 3 packed 32-bit stores).
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace vrsbs {
@@ -38,7 +40,7 @@ struct FusedArgs {
     const float2 *bounds;      // [B][Lcap]    (slow path)
     const int *offm;           // [B][Lcap+1]  (slow path)
     uint32_t *hole_mask;       // [B][H][Wwords]
-    uint32_t *hole_list;       // global index of every mask word that has a hole (any order)
+    uint32_t *hole_list;       // (global row << 8 | word) of every mask word that has a hole (any order)
     uint32_t *hole_count;      // pre-zeroed
     int B, H, W, Lcap, Wwords;
     int first;                 // frame 0 of the batch is the first frame of the clip range
@@ -73,7 +75,7 @@ __device__ __forceinline__ uint32_t fetch_rgb(const uint8_t *row, int x) {
 }
 
 template <bool SMOOTH, int NT>
-__global__ void __launch_bounds__(NT) k_warp_fused(FusedArgs a) {
+__global__ void __launch_bounds__(NT, 1024 / NT) k_warp_fused(FusedArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const FusedSmem lay = fused_smem_layout(a.W, a.blob_bytes);
     uint32_t *keys = reinterpret_cast<uint32_t *>(smem + lay.keys);
@@ -154,52 +156,116 @@ __global__ void __launch_bounds__(NT) k_warp_fused(FusedArgs a) {
         const BlobHdr hdr = *reinterpret_cast<const BlobHdr *>(blob);
         const bool fast = hdr.flags & 1u;
         const int fill = hdr.fill_off;
-        const uint32_t *img32 = reinterpret_cast<const uint32_t *>(img_row);
 
-        auto smoothed = [&](int x) -> __half2 {                 // both halves = the smoothed depth of pixel x
+        const uint32_t sa_cur = smem_u32(dcur), sa_p1 = smem_u32(dp1), sa_p2 = smem_u32(dp2);
+        const uint32_t sa_img = smem_u32(img_row) + 4u * (uint32_t)wofs, sa_keys = smem_u32(keys);
+
+        // smoothed depth of pixel x (both halves of the result hold it), from raw halves
+        auto smooth_px = [&](uint32_t c, uint32_t p1, uint32_t p2) -> uint32_t {
             if (SMOOTH) {
-                const float c = __half2float(__ushort_as_half(dcur[x]));
-                const float p1 = __half2float(__ushort_as_half(dp1[x]));
-                const float p2 = __half2float(__ushort_as_half(dp2[x]));
-                const float m0 = __fmul_rn(c, a.w0), m1 = __fmul_rn(p1, a.w1), m2 = __fmul_rn(p2, a.w2);
+                const float m0 = __fmul_rn(__half2float(__ushort_as_half((unsigned short)c)), a.w0);
+                const float m1 = __fmul_rn(__half2float(__ushort_as_half((unsigned short)p1)), a.w1);
+                const float m2 = __fmul_rn(__half2float(__ushort_as_half((unsigned short)p2)), a.w2);
                 __half2 d = __hadd2(__floats2half2_rn(m0, m0), __floats2half2_rn(m1, m1));
-                return __hadd2(d, __floats2half2_rn(m2, m2));
+                d = __hadd2(d, __floats2half2_rn(m2, m2));
+                return *reinterpret_cast<uint32_t *>(&d);
             } else {
-                const uint32_t v = dcur[x];
-                uint32_t r = v | (v << 16);
-                return *reinterpret_cast<__half2 *>(&r);
+                return c | (c << 16);
             }
         };
 
         // ---- scatter ------------------------------------------------------------------------------------
         if (fast) {
-            const LayerEnt *ent = reinterpret_cast<const LayerEnt *>(blob + 16);
-            const uint8_t *lut = blob + 16 + a.ent_bytes;
-            const uint32_t shift = hdr.shift, ncells = hdr.ncells;
-#pragma unroll 4
-            for (int seg = warp; seg < nseg; seg += NW) {
-                const int x = (seg << 5) + lane;
-                if (x < W) {
-                    const __half2 dd = smoothed(x);
-                    const uint32_t ddu = *reinterpret_cast<const uint32_t *>(&dd);
-                    const uint32_t idx = min((ddu & 0xffffu) >> shift, ncells);
-                    const uint32_t e = lut[idx];
-                    const uint2 en = *reinterpret_cast<const uint2 *>(ent + e);
-                    uint32_t in_lo, below_next;             // d < hi(e-1) ; d < lo(e)
+            const uint32_t sa_ent = smem_u32(blob) + 16u, sa_lut = sa_ent + a.ent_bytes;
+            // LUT address = sa_lut + min(bits >> shift, ncells); dd holds the fp16 bits twice, so dd >> (16 + shift)
+            // = umulhi(dd, 2^(16 - shift)) folds the shift and the base add into one IMAD.HI
+            const uint32_t lut_mul = 1u << (16u - hdr.shift), lut_last = sa_lut + hdr.ncells;
+            const uint32_t nW4 = 0u - W4;
+            // U segments of 32 pixels per step, all loads of a step issued before their uses
+            auto batch = [&](auto Uc, int round0, bool tail) {
+                constexpr int U = decltype(Uc)::value;
+                uint32_t c[U], p1[U], p2[U], w0[U], w1[U], x4[U], ok[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int seg = (round0 + u) * NW + warp;
+                    const int x = (seg << 5) + lane;
+                    ok[u] = (!tail || x < W) ? 1u : 0u;
+                    const int xc = tail ? min(x, W - 1) : x;
+                    x4[u] = (uint32_t)xc * 4u;
+                    c[u] = lds_u16(sa_cur + 2u * xc);
+                    if (SMOOTH) { p1[u] = lds_u16(sa_p1 + 2u * xc); p2[u] = lds_u16(sa_p2 + 2u * xc); }
+                    else { p1[u] = p2[u] = 0u; }
+                    const uint32_t ia = sa_img + 96u * (uint32_t)(tail ? min(seg, nseg - 1) : seg);
+                    w0[u] = lds_u32(ia);
+                    w1[u] = lds_u32(ia + 4u);
+                }
+                uint32_t dd[U], e[U];
+                if (SMOOTH) {
+                    // d = rn16(rn16(rn16(c*w0) + rn16(p1*w1)) + rn16(p2*w2)); the fp32->fp16 roundings are packed two
+                    // per F2FP (c/p1 products of one pixel, p2 products of two pixels), the adds are fp16 adds whose
+                    // operand selectors replicate the result into both halves
+                    __half2 d01[U];
+                    float m2[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const float m0 = __fmul_rn(__half2float(__ushort_as_half((unsigned short)c[u])), a.w0);
+                        const float m1 = __fmul_rn(__half2float(__ushort_as_half((unsigned short)p1[u])), a.w1);
+                        m2[u] = __fmul_rn(__half2float(__ushort_as_half((unsigned short)p2[u])), a.w2);
+                        const __half2 v = __floats2half2_rn(m0, m1);
+                        d01[u] = __hadd2(__low2half2(v), __high2half2(v));
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; u += 2) {
+                        const __half2 v = __floats2half2_rn(m2[u], m2[u + 1 < U ? u + 1 : u]);
+                        __half2 r0 = __hadd2(d01[u], __low2half2(v));
+                        dd[u] = *reinterpret_cast<uint32_t *>(&r0);
+                        if (u + 1 < U) {
+                            __half2 r1 = __hadd2(d01[u + 1], __high2half2(v));
+                            dd[u + 1] = *reinterpret_cast<uint32_t *>(&r1);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) dd[u] = c[u] | (c[u] << 16);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) e[u] = lds_u8(min(__umulhi(dd[u], lut_mul) + sa_lut, lut_last));
+                uint2 en[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) en[u] = lds_u64(sa_ent + 8u * e[u]);
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const uint32_t px = __funnelshift_r(w0[u], w1[u], wsh) & 0x00ffffffu;
+                    const uint32_t key0 = px | (e[u] << 24);
+                    uint32_t a0 = x4[u] + (en[u].y & 0xffffu), a1 = x4[u] + (en[u].y >> 16);
+                    a0 = sa_keys + min(a0, a0 + nW4);
+                    a1 = sa_keys + min(a1, a1 + nW4);
+                    // paint layer e-1 iff d < hi(e-1); paint layer e iff !(d < lo(e)).  Non-members still issue the
+                    // atomic, with key 0 (a no-op for max): cheaper than the branch ptxas wraps a predicated ATOMS in.
+                    uint32_t k0, k1;
                     asm("{\n\t.reg .pred p, q;\n\t"
                         "setp.lt.f16x2 p|q, %2, %3;\n\t"
-                        "selp.u32 %0, 1, 0, p;\n\t"
-                        "selp.u32 %1, 1, 0, q;\n\t}"
-                        : "=r"(in_lo), "=r"(below_next) : "r"(ddu), "r"(en.x));
-                    const uint32_t px = __funnelshift_r(img32[seg * 24 + wofs], img32[seg * 24 + wofs + 1], wsh) & 0x00ffffffu;
-                    const uint32_t key0 = px | (e << 24);
-                    const uint32_t x4 = (uint32_t)x * 4u;
-                    uint32_t a0 = x4 + (en.y & 0xffffu), a1 = x4 + (en.y >> 16);
-                    a0 = min(a0, a0 - W4);
-                    a1 = min(a1, a1 - W4);
-                    if (in_lo) atomicMax(reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(keys) + a0), key0);
-                    if (!below_next) atomicMax(reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(keys) + a1), key0 + 0x01000000u);
+                        "selp.u32 %0, %4, 0, p;\n\t"
+                        "selp.u32 %1, 0, %5, q;\n\t}"
+                        : "=r"(k0), "=r"(k1) : "r"(dd[u]), "r"(en[u].x), "r"(key0), "r"(key0 + 0x01000000u));
+                    if (tail) { k0 = ok[u] ? k0 : 0u; k1 = ok[u] ? k1 : 0u; }
+                    asm volatile("red.shared.max.u32 [%0], %1;" :: "r"(a0), "r"(k0) : "memory");
+                    asm volatile("red.shared.max.u32 [%0], %1;" :: "r"(a1), "r"(k1) : "memory");
                 }
+            };
+            if ((W & 31) == 0) {
+                // whole segments only: this warp owns segments warp, warp + NW, ... (nw of them), 4 at a time
+                const int nw = nseg / NW + ((warp < nseg % NW) ? 1 : 0);
+                int r = 0;
+                for (; r + 4 <= nw; r += 4) batch(std::integral_constant<int, 4>{}, r, false);
+                switch (nw - r) {                             // warp-uniform
+                    case 3: batch(std::integral_constant<int, 3>{}, r, false); break;
+                    case 2: batch(std::integral_constant<int, 2>{}, r, false); break;
+                    case 1: batch(std::integral_constant<int, 1>{}, r, false); break;
+                    default: break;
+                }
+            } else {
+                for (int r = 0; r * NW + warp < nseg; ++r) batch(std::integral_constant<int, 1>{}, r, true);
             }
         } else {
             // slow path (L > 255, non-monotone bounds, LUT too coarse): brute-force membership, layer-only keys
@@ -210,7 +276,8 @@ __global__ void __launch_bounds__(NT) k_warp_fused(FusedArgs a) {
             for (int seg = warp; seg < nseg; seg += NW) {
                 const int x = (seg << 5) + lane;
                 if (x < W) {
-                    const float d = __low2float(smoothed(x));
+                    const uint32_t du = smooth_px(dcur[x], SMOOTH ? dp1[x] : 0, SMOOTH ? dp2[x] : 0);
+                    const float d = __half2float(__ushort_as_half((unsigned short)(du & 0xffffu)));
                     for (int k = 0; k < L; ++k) {
                         const float2 b = __ldg(gb + k);
                         if (b.x <= d && d < b.y) {
@@ -296,7 +363,7 @@ __global__ void __launch_bounds__(NT) k_warp_fused(FusedArgs a) {
                     atomicAdd(&a.tabs[t0].holes, (unsigned long long)holes);
                 }
                 base = __shfl_sync(0xffffffffu, base, 0);
-                if (v) a.hole_list[base + __popc(nz & ((1u << lane) - 1u))] = (uint32_t)(row * Wwords + w);
+                if (v) a.hole_list[base + __popc(nz & ((1u << lane) - 1u))] = ((uint32_t)row << 8) | (uint32_t)w;
             }
         }
         // advance the uniform state

@@ -34,7 +34,7 @@ struct WarpArgs {
     const float2 *bounds;      // [B][Lcap]
     const int *offm;           // [B][Lcap+1]
     uint32_t *hole_mask;       // [B][H][Wwords]
-    uint32_t *hole_list;       // global index of every mask word that has a hole (blur work list, any order)
+    uint32_t *hole_list;       // (global row << 8 | word) of every mask word that has a hole (blur work list, any order)
     uint32_t *hole_count;      // pre-zeroed
     int B, H, W, Lcap, Wwords;
 };
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(NT) k_warp_rows(WarpArgs a) {
                 mask_row[sg] = hm;
                 if (hm) {
                     hole_acc += __popc(hm);
-                    a.hole_list[atomicAdd(a.hole_count, 1u)] = (uint32_t)(row * a.Wwords + sg);
+                    a.hole_list[atomicAdd(a.hole_count, 1u)] = ((uint32_t)row << 8) | (uint32_t)sg;
                 }
             }
             if (((sg + 1) << 5) <= W) {
