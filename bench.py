@@ -194,6 +194,8 @@ def run_ours(args, wl, name):
     # end to end: the public batch API with pinned host buffers (H2D + D2H inside the timed region)
     ns = argparse.Namespace(offset_fg=wl["fg"], offset_bg=wl["bg"], offset_step_size=wl["step"])
     proc = pkg.SbsProcessor(None, 0, ns, device=dev, max_batch=16)
+    if args.host_chunk:
+        proc._context(H, W).set_option("host_chunk", args.host_chunk)
     f_pin = torch.from_numpy(frames_h).pin_memory()
     d_pin = torch.from_numpy(raw_h).pin_memory()
     o_pin = torch.empty((B, H, 2 * W, 3), dtype=torch.uint8).pin_memory()
@@ -214,6 +216,13 @@ def run_ours(args, wl, name):
            "h2d_bytes_per_step": int(frames_h.nbytes + raw_h.nbytes), "d2h_bytes_per_step": int(o_np.nbytes),
            "steps": e2e_steps, "api": "SbsProcessor.left_side_sbs_batch (vrsbs_process_host), pinned buffers"}
     same = bool(np.array_equal(o_np[0], sbs_d[0].cpu().numpy())) if e2e_steps else None
+    # the same call with ordinary (pageable) numpy arrays, as nibba_woka's FrameList holds them: one step, reported aside
+    if args.pageable:
+        o_pg = np.empty_like(o_np)
+        proc.left_side_sbs_batch(frames_h, raw_h, out=o_pg)
+        t0 = time.perf_counter()
+        proc.left_side_sbs_batch(frames_h, raw_h, out=o_pg)
+        e2e["pageable_value"] = world * B / reduce_max(time.perf_counter() - t0)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -323,6 +332,8 @@ def main():
     ap.add_argument("--workload", default="1080p_b64", choices=sorted(WORKLOADS))
     ap.add_argument("--scatter-mode", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--host-chunk", type=int, default=0)
+    ap.add_argument("--pageable", action="store_true", help="also time the host API with pageable numpy buffers")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

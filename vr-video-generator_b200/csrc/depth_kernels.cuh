@@ -146,67 +146,71 @@ __global__ void __launch_bounds__(256) k_depth_max(DepthMaxArgs a) {
     const bool active = v * 8 < a.n;
     const size_t base = active ? v * 8 : 0;
     union V { uint4 u; __half2 h[4]; };
-    // raw depth of t-1 / t-2 as floats (each raw value is converted once and used by three frames)
-    float p1[8], p2[8];
-    V praw1, praw2;
-    praw1.u = praw2.u = make_uint4(0, 0, 0, 0);
-    if (active && !a.first) {
-        praw1.u = __ldg(reinterpret_cast<const uint4 *>(a.hist1 + base));
-        praw2.u = __ldg(reinterpret_cast<const uint4 *>(a.hist2 + base));
-    }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const float2 f1 = __half22float2(praw1.h[e]), f2 = __half22float2(praw2.h[e]);
-        p1[2 * e] = f1.x; p1[2 * e + 1] = f1.y; p2[2 * e] = f2.x; p2[2 * e + 1] = f2.y;
-    }
     const int lane = threadIdx.x & 31;
     const float w0 = a.sw.w_now, w1 = a.sw.w_prev1, w2 = a.sw.w_prev2;
-    // 4 frames per step: their four 16-byte loads are issued together (the kernel is latency bound otherwise)
-    constexpr int PF = 4;
-    for (int tb = 0; tb < a.B; tb += PF) {
-        V q[PF];
+
+    // Raw depth as floats in three rotating register sets X, Y, Z (each raw value is converted once and used by
+    // three frames).  Frames are processed in trios so that the roles (current, t-1, t-2) rotate by renaming only.
+    float X[8], Y[8], Z[8];
+    auto unpack = [](const uint4 &u, float *f) {
+        V t; t.u = u;
 #pragma unroll
-        for (int i = 0; i < PF; ++i) {
-            q[i].u = make_uint4(0, 0, 0, 0);
-            if (active && tb + i < a.B) q[i].u = __ldg(reinterpret_cast<const uint4 *>(a.raw + (size_t)(tb + i) * a.n + base));
-        }
+        for (int e = 0; e < 4; ++e) { const float2 g = __half22float2(t.h[e]); f[2 * e] = g.x; f[2 * e + 1] = g.y; }
+    };
+    auto pack = [](const float *f) -> uint4 {
+        V t;
 #pragma unroll
-        for (int i = 0; i < PF; ++i) {
-            const int t = tb + i;
-            if (t >= a.B) break;                              // uniform
-            uint32_t key = 0;
-            if (active) {
-                V cur; cur.u = q[i].u;
-                float c[8];
+        for (int e = 0; e < 4; ++e) t.h[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);   // exact: the values are fp16 values
+        return t.u;
+    };
+    auto frame = [&](const float *c, const float *p1, const float *p2, int t) {
+        uint32_t key = 0;
+        if (active) {
+            __half2 m;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(cur.h[e]); c[2 * e] = f.x; c[2 * e + 1] = f.y; }
-                if (a.first && t == 0) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) p1[e] = p2[e] = c[e];
-                    praw1.u = praw2.u = cur.u;
-                }
-                __half2 m;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    __half2 d = __hadd2(__floats2half2_rn(__fmul_rn(c[2 * e], w0), __fmul_rn(c[2 * e + 1], w0)),
-                                        __floats2half2_rn(__fmul_rn(p1[2 * e], w1), __fmul_rn(p1[2 * e + 1], w1)));
-                    d = __hadd2(d, __floats2half2_rn(__fmul_rn(p2[2 * e], w2), __fmul_rn(p2[2 * e + 1], w2)));
-                    m = e ? __hmax2_nan(m, d) : d;
-                }
-                m = __hmax2_nan(m, __lowhigh2highlow(m));
-                key = h16_key((uint32_t)__half_as_ushort(__low2half(m)));
-#pragma unroll
-                for (int e = 0; e < 8; ++e) { p2[e] = p1[e]; p1[e] = c[e]; }
-                praw2.u = praw1.u;
-                praw1.u = cur.u;
+            for (int e = 0; e < 4; ++e) {
+                __half2 d = __hadd2(__floats2half2_rn(__fmul_rn(c[2 * e], w0), __fmul_rn(c[2 * e + 1], w0)),
+                                    __floats2half2_rn(__fmul_rn(p1[2 * e], w1), __fmul_rn(p1[2 * e + 1], w1)));
+                d = __hadd2(d, __floats2half2_rn(__fmul_rn(p2[2 * e], w2), __fmul_rn(p2[2 * e + 1], w2)));
+                m = e ? __hmax2_nan(m, d) : d;
             }
-            key = __reduce_max_sync(0xffffffffu, key);
-            if (lane == 0 && key) atomicMax(&s_red[t], key);
+            m = __hmax2_nan(m, __lowhigh2highlow(m));
+            key = h16_key((uint32_t)__half_as_ushort(__low2half(m)));
+        }
+        key = __reduce_max_sync(0xffffffffu, key);
+        if (lane == 0 && key) atomicMax(&s_red[t], key);
+    };
+    auto load = [&](int t) -> uint4 {
+        return (active && t < a.B) ? __ldg(reinterpret_cast<const uint4 *>(a.raw + (size_t)t * a.n + base)) : make_uint4(0, 0, 0, 0);
+    };
+    {   // history: X = raw t-1, Y = raw t-2 (clip start: both are the first raw frame)
+        const uint4 h1 = active ? __ldg(reinterpret_cast<const uint4 *>((a.first ? a.raw : a.hist1) + base)) : make_uint4(0, 0, 0, 0);
+        const uint4 h2 = active ? __ldg(reinterpret_cast<const uint4 *>((a.first ? a.raw : a.hist2) + base)) : make_uint4(0, 0, 0, 0);
+        unpack(h1, X);
+        unpack(h2, Y);
+    }
+    // at the top of every trio: t-1 is in X, t-2 in Y
+    for (int tb = 0; tb < a.B; tb += 6) {
+        uint4 q[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) q[i] = load(tb + i);       // six independent 16-byte loads in flight
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const int t = tb + 3 * g;
+            if (t < a.B)     { unpack(q[3 * g], Z);     frame(Z, X, Y, t); }
+            if (t + 1 < a.B) { unpack(q[3 * g + 1], Y); frame(Y, Z, X, t + 1); }
+            if (t + 2 < a.B) { unpack(q[3 * g + 2], X); frame(X, Y, Z, t + 2); }
         }
     }
     if (active) {
-        *reinterpret_cast<uint4 *>(a.hist1_out + base) = praw1.u;
-        *reinterpret_cast<uint4 *>(a.hist2_out + base) = praw2.u;
+        // after B frames the newest two raw frames sit in (X,Y), (Z,X) or (Y,Z) depending on B mod 3
+        const int r = a.B % 3;
+        const float *n1 = r == 0 ? X : (r == 1 ? Z : Y), *n2 = r == 0 ? Y : (r == 1 ? X : Z);
+        uint4 o1, o2;
+        if (r == 0) { o1 = pack(X); o2 = pack(Y); } else if (r == 1) { o1 = pack(Z); o2 = pack(X); } else { o1 = pack(Y); o2 = pack(Z); }
+        (void)n1; (void)n2;
+        *reinterpret_cast<uint4 *>(a.hist1_out + base) = o1;
+        *reinterpret_cast<uint4 *>(a.hist2_out + base) = o2;
     }
     __syncthreads();
     for (int t = threadIdx.x; t < a.B; t += blockDim.x) {

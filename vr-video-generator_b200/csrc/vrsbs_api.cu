@@ -37,13 +37,15 @@ struct Scratch {                 // per-batch device scratch; one per pipeline s
 
 constexpr int kEntCapMax = 255, kLutCapMax = 8192;
 
-struct HostSlot {                // double-buffered host<->device staging for vrsbs_process_host
-    cudaStream_t stream = nullptr;
-    cudaEvent_t done = nullptr, state_ready = nullptr;
+constexpr int kSlots = 3;         // chunks in flight in vrsbs_process_host
+
+struct HostSlot {                // one chunk of host<->device staging for vrsbs_process_host
+    cudaEvent_t in_done = nullptr, k_done = nullptr, out_done = nullptr;
+    FrameTab *pin_tabs = nullptr;    // [max_batch] pinned copy of the chunk's frame records
     uint8_t *pin_frames = nullptr, *pin_depth = nullptr, *pin_sbs = nullptr;
     uint8_t *dev_frames = nullptr, *dev_depth_in = nullptr, *dev_depth = nullptr, *dev_sbs = nullptr;
     size_t cap_frames = 0, cap_depth_in = 0, cap_depth = 0, cap_sbs = 0;
-    bool pin_ok = false;
+    size_t cap_pin_frames = 0, cap_pin_depth = 0, cap_pin_sbs = 0;
 };
 
 }  // namespace
@@ -61,7 +63,8 @@ struct vrsbs_ctx {
     long long depth_frames = 0;          // frames pushed through stage 1 since reset
     int state_h = 0, state_w = 0;
     // scratch
-    Scratch scratch[2];
+    Scratch scratch[kSlots];
+    cudaStream_t st_in = nullptr, st_k = nullptr, st_out = nullptr;   // H2D / kernels / D2H of the host pipeline
     float *weights = nullptr;
     uint32_t *wq = nullptr;              // integer blur weights [parts][(ky/2+1)*(kx/2+1)]
     std::vector<uint32_t> wq_host;
@@ -70,9 +73,10 @@ struct vrsbs_ctx {
     int fused = 1;                       // option: use the fused route in vrsbs_process_batch when possible
     int fast_tables = 1;                 // option (tests): 0 forces the slow membership path of k_warp_fused
     // host pipeline
-    HostSlot slot[2];
-    int host_chunk = 8;
-    int copy_threads = 4;
+    HostSlot slot[kSlots];
+    int host_chunk = 4;
+    int copy_threads = 8;
+    int pageable_direct = 0;             // option: 1 = hand pageable host pointers to cudaMemcpyAsync instead of staging them
     // options / accounting
     int scatter_mode = 2;
     int bicubic_contract = 1;
@@ -484,36 +488,51 @@ bool is_pinned(const void *p) {
     return at.type == cudaMemoryTypeHost;
 }
 
-int ensure_slot(vrsbs_ctx *c, HostSlot &s, size_t frames_b, size_t depth_in_b, size_t depth_b, size_t sbs_b) {
-    if (!s.stream) {
-        CU_TRY(c, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-        CU_TRY(c, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
-        CU_TRY(c, cudaEventCreateWithFlags(&s.state_ready, cudaEventDisableTiming));
+int ensure_slot(vrsbs_ctx *c, HostSlot &s, size_t frames_b, size_t depth_in_b, size_t depth_b, size_t sbs_b, bool need_pin_in,
+                bool need_pin_out) {
+    if (!c->st_in) {
+        CU_TRY(c, cudaStreamCreateWithFlags(&c->st_in, cudaStreamNonBlocking));
+        CU_TRY(c, cudaStreamCreateWithFlags(&c->st_k, cudaStreamNonBlocking));
+        CU_TRY(c, cudaStreamCreateWithFlags(&c->st_out, cudaStreamNonBlocking));
     }
-    auto grow = [&](uint8_t *&dev, uint8_t **pin, size_t &cap, size_t need) -> cudaError_t {
+    if (!s.in_done) {
+        CU_TRY(c, cudaEventCreateWithFlags(&s.in_done, cudaEventDisableTiming));
+        CU_TRY(c, cudaEventCreateWithFlags(&s.k_done, cudaEventDisableTiming));
+        CU_TRY(c, cudaEventCreateWithFlags(&s.out_done, cudaEventDisableTiming));
+        CU_TRY(c, cudaHostAlloc(reinterpret_cast<void **>(&s.pin_tabs), sizeof(FrameTab) * c->max_batch, cudaHostAllocDefault));
+    }
+    auto grow_dev = [&](uint8_t *&dev, size_t &cap, size_t need) -> cudaError_t {
         if (need <= cap) return cudaSuccess;
-        cudaFree(dev); dev = nullptr;
-        if (pin) { cudaFreeHost(*pin); *pin = nullptr; }
-        cap = 0;
+        cudaFree(dev); dev = nullptr; cap = 0;
         cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&dev), need);
-        if (e != cudaSuccess) return e;
-        if (pin) { e = cudaHostAlloc(reinterpret_cast<void **>(pin), need, cudaHostAllocDefault); if (e != cudaSuccess) return e; }
-        cap = need;
-        return cudaSuccess;
+        if (e == cudaSuccess) cap = need;
+        return e;
     };
-    CU_TRY(c, grow(s.dev_frames, &s.pin_frames, s.cap_frames, frames_b));
-    CU_TRY(c, grow(s.dev_depth_in, &s.pin_depth, s.cap_depth_in, depth_in_b));
-    CU_TRY(c, grow(s.dev_depth, nullptr, s.cap_depth, depth_b));
-    CU_TRY(c, grow(s.dev_sbs, &s.pin_sbs, s.cap_sbs, sbs_b));
+    auto grow_pin = [&](uint8_t *&pin, size_t &cap, size_t need) -> cudaError_t {
+        if (need <= cap) return cudaSuccess;
+        cudaFreeHost(pin); pin = nullptr; cap = 0;
+        cudaError_t e = cudaHostAlloc(reinterpret_cast<void **>(&pin), need, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = need;
+        return e;
+    };
+    CU_TRY(c, grow_dev(s.dev_frames, s.cap_frames, frames_b));
+    CU_TRY(c, grow_dev(s.dev_depth_in, s.cap_depth_in, depth_in_b));
+    CU_TRY(c, grow_dev(s.dev_depth, s.cap_depth, depth_b));
+    CU_TRY(c, grow_dev(s.dev_sbs, s.cap_sbs, sbs_b));
+    if (need_pin_in) {
+        CU_TRY(c, grow_pin(s.pin_frames, s.cap_pin_frames, frames_b));
+        CU_TRY(c, grow_pin(s.pin_depth, s.cap_pin_depth, depth_in_b));
+    }
+    if (need_pin_out) CU_TRY(c, grow_pin(s.pin_sbs, s.cap_pin_sbs, sbs_b));
     return VRSBS_OK;
 }
 
 void free_slot(HostSlot &s) {
-    if (s.stream) cudaStreamDestroy(s.stream);
-    if (s.done) cudaEventDestroy(s.done);
-    if (s.state_ready) cudaEventDestroy(s.state_ready);
+    if (s.in_done) cudaEventDestroy(s.in_done);
+    if (s.k_done) cudaEventDestroy(s.k_done);
+    if (s.out_done) cudaEventDestroy(s.out_done);
     cudaFree(s.dev_frames); cudaFree(s.dev_depth_in); cudaFree(s.dev_depth); cudaFree(s.dev_sbs);
-    cudaFreeHost(s.pin_frames); cudaFreeHost(s.pin_depth); cudaFreeHost(s.pin_sbs);
+    cudaFreeHost(s.pin_frames); cudaFreeHost(s.pin_depth); cudaFreeHost(s.pin_sbs); cudaFreeHost(s.pin_tabs);
     s = HostSlot{};
 }
 
@@ -586,8 +605,8 @@ int vrsbs_destroy(vrsbs_ctx *c) {
     for (int i = 0; i < 2; ++i)
         for (int j = 0; j < 2; ++j) cudaFree(c->hist[i][j]);
     cudaFree(c->state); cudaFree(c->weights); cudaFree(c->wq);
-    free_scratch(c->scratch[0]); free_scratch(c->scratch[1]);
-    free_slot(c->slot[0]); free_slot(c->slot[1]);
+    for (int i = 0; i < kSlots; ++i) { free_scratch(c->scratch[i]); free_slot(c->slot[i]); }
+    if (c->st_in) { cudaStreamDestroy(c->st_in); cudaStreamDestroy(c->st_k); cudaStreamDestroy(c->st_out); }
     for (auto &s : c->stamps) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (auto e : c->event_pool) cudaEventDestroy(e);
     delete c;
@@ -751,67 +770,68 @@ int vrsbs_process_host(vrsbs_ctx *c, const uint8_t *frames, const void *depth, i
     if (chunk < 1) chunk = 1;
     const size_t fb = (size_t)H * W * 3, sb = fb * 2, db = (size_t)H * W * 2;
     const size_t dib = lowres ? (size_t)lh * lw * 2 : db;
-    if (!c->scratch[1].tabs && (rc = alloc_scratch(c, c->scratch[1]))) return rc;
-    for (int i = 0; i < 2; ++i)
-        if ((rc = ensure_slot(c, c->slot[i], fb * chunk, dib * chunk, db * chunk, sb * chunk))) return rc;
-    const bool pin_f = is_pinned(frames), pin_d = is_pinned(depth), pin_s = is_pinned(sbs);
+    const bool direct = c->pageable_direct != 0;
+    const bool pin_f = direct || is_pinned(frames), pin_d = direct || is_pinned(depth), pin_s = direct || is_pinned(sbs);
+    for (int i = 0; i < kSlots; ++i) {
+        if (!c->scratch[i].tabs && (rc = alloc_scratch(c, c->scratch[i]))) return rc;
+        if ((rc = ensure_slot(c, c->slot[i], fb * chunk, dib * chunk, db * chunk, sb * chunk, !pin_f || !pin_d, !pin_s))) return rc;
+    }
     fast_caps(c, H, &c->ent_cap, &c->lut_cap);
-    const int want_blur = c->params.blur;
     if ((rc = check_blur_ready(c, H, W))) return rc;
     const bool use_fused = !lowres && c->fused && ((size_t)H * W) % 8 == 0 &&
                            fused_capable(c, c->slot[0].dev_frames, c->slot[0].dev_depth_in, c->slot[0].dev_sbs, W);
 
-    std::vector<FrameTab> tabs(chunk);
-    int nchunks = (B + chunk - 1) / chunk;
-    int pending_n[2] = {0, 0}, pending_first[2] = {0, 0};
-    auto drain = [&](int si) -> int {     // wait for slot si's chunk, deliver its output, check status
+    // Three streams: st_in copies chunk i+1 in while st_k runs the kernels of chunk i and st_out copies chunk i-1
+    // out.  All kernels run on st_k in clip order, so the clip-range state needs no extra synchronisation.
+    const int nchunks = (B + chunk - 1) / chunk;
+    int pending_n[kSlots] = {0}, pending_first[kSlots] = {0};
+    auto drain = [&](int si) -> int {     // wait for slot si's chunk, deliver its output, check its status
         HostSlot &s = c->slot[si];
         if (!pending_n[si]) return VRSBS_OK;
-        CU_TRY(c, cudaEventSynchronize(s.done));
+        CU_TRY(c, cudaEventSynchronize(s.out_done));
         const int n = pending_n[si], first = pending_first[si];
         if (!pin_s) parallel_memcpy(sbs + (size_t)first * sb, s.pin_sbs, sb * n, c->copy_threads);
-        CU_TRY(c, cudaMemcpy(tabs.data(), c->scratch[si].tabs, sizeof(FrameTab) * n, cudaMemcpyDeviceToHost));
         pending_n[si] = 0;
-        return frame_status_error(c, tabs.data(), n, first);
+        return frame_status_error(c, s.pin_tabs, n, first);
+    };
+    auto drain_all = [&](int rc_in) -> int {          // never leave work in flight behind an error return
+        for (int i = 0; i < kSlots; ++i) { int r = drain(i); if (!rc_in) rc_in = r; }
+        return rc_in;
     };
     for (int ci = 0; ci < nchunks; ++ci) {
-        const int si = ci & 1, first = ci * chunk, n = (B - first < chunk) ? B - first : chunk;
+        const int si = ci % kSlots, first = ci * chunk, n = (B - first < chunk) ? B - first : chunk;
         HostSlot &s = c->slot[si];
-        if ((rc = drain(si))) return rc;
+        if ((rc = drain(si))) return drain_all(rc);
         const uint8_t *hf = frames + (size_t)first * fb;
         const uint8_t *hd = (const uint8_t *)depth + (size_t)first * dib;
         if (!pin_f) { parallel_memcpy(s.pin_frames, hf, fb * n, c->copy_threads); hf = s.pin_frames; }
         if (!pin_d) { parallel_memcpy(s.pin_depth, hd, dib * n, c->copy_threads); hd = s.pin_depth; }
-        CU_TRY(c, cudaMemcpyAsync(s.dev_frames, hf, fb * n, cudaMemcpyHostToDevice, s.stream));
-        CU_TRY(c, cudaMemcpyAsync(s.dev_depth_in, hd, dib * n, cudaMemcpyHostToDevice, s.stream));
-        // stage 1/2 carry clip-range state from the previous chunk, which ran on the other stream
-        if (ci > 0) CU_TRY(c, cudaStreamWaitEvent(s.stream, c->slot[si ^ 1].state_ready, 0));
+        CU_TRY(c, cudaMemcpyAsync(s.dev_frames, hf, fb * n, cudaMemcpyHostToDevice, c->st_in));
+        CU_TRY(c, cudaMemcpyAsync(s.dev_depth_in, hd, dib * n, cudaMemcpyHostToDevice, c->st_in));
+        CU_TRY(c, cudaEventRecord(s.in_done, c->st_in));
+        CU_TRY(c, cudaStreamWaitEvent(c->st_k, s.in_done, 0));
         Scratch &sc = c->scratch[si];
         if (use_fused) {
-            // the warp kernel itself reads the depth history, so the next chunk may only start after it
-            c->params.blur = 0;
-            rc = launch_process_fused(c, sc, s.dev_frames, (const __half *)s.dev_depth_in, n, H, W, s.dev_sbs, s.stream);
-            c->params.blur = want_blur;
-            if (rc) return rc;
-            CU_TRY(c, cudaEventRecord(s.state_ready, s.stream));
-            if (want_blur && (rc = launch_blur(c, sc, s.dev_frames, n, H, W, s.dev_sbs, s.stream))) return rc;
+            rc = launch_process_fused(c, sc, s.dev_frames, (const __half *)s.dev_depth_in, n, H, W, s.dev_sbs, c->st_k);
         } else {
-            if (lowres) rc = launch_depth(c, sc, nullptr, (const __half *)s.dev_depth_in, n, H, W, lh, lw, scaler, (__half *)s.dev_depth, s.stream);
-            else rc = launch_depth(c, sc, (const __half *)s.dev_depth_in, nullptr, n, H, W, 0, 0, 1.f, (__half *)s.dev_depth, s.stream);
-            if (rc) return rc;
-            if ((rc = launch_tables(c, sc, n, H, W, s.stream))) return rc;
-            CU_TRY(c, cudaEventRecord(s.state_ready, s.stream));
-            if ((rc = launch_warp(c, sc, s.dev_frames, (const __half *)s.dev_depth, n, H, W, s.dev_sbs, s.stream))) return rc;
+            if (lowres) rc = launch_depth(c, sc, nullptr, (const __half *)s.dev_depth_in, n, H, W, lh, lw, scaler, (__half *)s.dev_depth, c->st_k);
+            else rc = launch_depth(c, sc, (const __half *)s.dev_depth_in, nullptr, n, H, W, 0, 0, 1.f, (__half *)s.dev_depth, c->st_k);
+            if (!rc) rc = launch_tables(c, sc, n, H, W, c->st_k);
+            if (!rc) rc = launch_warp(c, sc, s.dev_frames, (const __half *)s.dev_depth, n, H, W, s.dev_sbs, c->st_k);
         }
+        if (rc) return drain_all(rc);
+        CU_TRY(c, cudaMemcpyAsync(s.pin_tabs, sc.tabs, sizeof(FrameTab) * n, cudaMemcpyDeviceToHost, c->st_k));
+        CU_TRY(c, cudaEventRecord(s.k_done, c->st_k));
+        CU_TRY(c, cudaStreamWaitEvent(c->st_out, s.k_done, 0));
         uint8_t *ho = pin_s ? sbs + (size_t)first * sb : s.pin_sbs;
-        CU_TRY(c, cudaMemcpyAsync(ho, s.dev_sbs, sb * n, cudaMemcpyDeviceToHost, s.stream));
-        CU_TRY(c, cudaEventRecord(s.done, s.stream));
+        CU_TRY(c, cudaMemcpyAsync(ho, s.dev_sbs, sb * n, cudaMemcpyDeviceToHost, c->st_out));
+        CU_TRY(c, cudaEventRecord(s.out_done, c->st_out));
         pending_n[si] = n; pending_first[si] = first;
     }
     // drain in submission order
-    const int last = (nchunks - 1) & 1;
-    if (nchunks > 1 && (rc = drain(last ^ 1))) return rc;
-    return drain(last);
+    for (int k = 0; k < kSlots; ++k)
+        if ((rc = drain((nchunks + k) % kSlots))) return drain_all(rc);
+    return VRSBS_OK;
 }
 
 int vrsbs_get_frame_info(vrsbs_ctx *c, int B, vrsbs_frame_info *info, void *stream) {
@@ -884,6 +904,7 @@ int vrsbs_set_option(vrsbs_ctx *c, const char *name, int value) {
     else if (!strcmp(name, "host_chunk")) { if (value < 1) return fail(c, VRSBS_E_INVALID, "host_chunk >= 1"); c->host_chunk = value; }
     else if (!strcmp(name, "stage_timing")) c->stage_timing = value != 0;
     else if (!strcmp(name, "copy_threads")) c->copy_threads = value < 1 ? 1 : value;
+    else if (!strcmp(name, "pageable_direct")) c->pageable_direct = value != 0;
     else if (!strcmp(name, "fused")) c->fused = value != 0;
     else if (!strcmp(name, "fast_tables")) c->fast_tables = value != 0;
     else return fail(c, VRSBS_E_INVALID, "unknown option %s", name);
