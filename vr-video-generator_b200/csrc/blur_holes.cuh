@@ -140,6 +140,10 @@ __global__ void __launch_bounds__(256) k_blur_holes(BlurArgs a) {
 template <int PARTS, int CX, int CY>
 struct BlurWeights { uint32_t q[PARTS][(CY + 1) * (CX + 1)]; };
 
+// list entries staged per warp before their holes are evaluated together (fewer for the large 4K footprint, whose
+// staging buffers would otherwise cost occupancy)
+template <int CX> __host__ __device__ constexpr int blur_group() { return CX <= 6 ? 4 : 2; }
+
 template <int PARTS, int CX, int CY>
 __global__ void __launch_bounds__(256) k_blur_holes_fixed(BlurArgs a, const __grid_constant__ BlurWeights<PARTS, CX, CY> wts) {
     constexpr int PBITS = PARTS == 2 ? 15 : 13;
@@ -147,71 +151,99 @@ __global__ void __launch_bounds__(256) k_blur_holes_fixed(BlurArgs a, const __gr
     constexpr int PHASE = ((-3 * CX) % 4 + 4) % 4;                    // (96 w - 3 CX) mod 4: the same for every word
     constexpr int NWORDS = (PHASE + 3 * NPX + 3) / 4;                 // aligned 32-bit words that cover the footprint
     constexpr int COLS = (NWORDS * 4 + 7) / 8 * 8;                    // u16 columns per T row (16-byte multiple)
+    constexpr int TSZ = (CY + 1) * COLS + 32;                         // u16 per staged entry: T rows + rank->bit table
+    constexpr int G = blur_group<CX>();
     static_assert(NWORDS <= 64, "footprint wider than two words per lane");
     extern __shared__ __align__(16) uint8_t blur_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int W = a.W, H = a.H;
-    uint16_t *T = reinterpret_cast<uint16_t *>(blur_smem) + (size_t)warp * ((CY + 1) * COLS + 32);
-    uint16_t *pos = T + (CY + 1) * COLS;                              // hole rank -> bit position
+    uint16_t *Tw = reinterpret_cast<uint16_t *>(blur_smem) + (size_t)warp * (G * TSZ);
     const uint32_t count = *a.hole_count;
     const size_t pitch = (size_t)W * 6;
 
-    for (uint32_t ei = blockIdx.x * nwarps + warp; ei < count; ei += gridDim.x * nwarps) {
-        const uint32_t ent = a.hole_list[ei];
-        const uint32_t row = ent >> 8, w = ent & 0xffu;
-        const int b = (int)(((unsigned long long)row * a.magic_h) >> 40), y = (int)row - b * H;
-        const int strip = a.tabs[b].strip;
-        uint32_t m = a.hole_mask[(size_t)row * a.Wwords + w];
-        const int xw = (int)w * 32;
-        if (strip > xw) m = (strip - xw >= 32) ? 0u : (m & ~((1u << (strip - xw)) - 1u));
-        if (m == 0u) continue;
+    for (uint32_t e0 = (blockIdx.x * nwarps + warp) * G; e0 < count; e0 += gridDim.x * nwarps * G) {
         __syncwarp();
-        if ((m >> lane) & 1u) pos[__popc(m & ((1u << lane) - 1u))] = (uint16_t)lane;
-        const uint8_t *left = a.sbs + (size_t)b * H * pitch;
-        const int s0 = 3 * (xw - CX);                                 // byte offset of the footprint in its row
-        int phase;                                                    // byte column of footprint byte 0 inside T
-        if (xw - CX >= 0 && xw + 31 + CX < W) {
-            // interior: aligned words, packed vertical pair sums
-            const int A = s0 - PHASE;
-            phase = PHASE;
+        // ---- stage up to G entries; remember (row, first pixel, phase) and the running task count of each ----
+        uint32_t g_row[G], g_xw[G], g_phase[G], g_end[G];
+        uint32_t tasks = 0;
 #pragma unroll
-            for (int half = 0; half < (NWORDS + 31) / 32; ++half) {
-                const int k = lane + 32 * half;
-                if (k < NWORDS) {
-                    const uint8_t *colp = left + A + 4 * k;
-                    uint32_t v[2 * CY + 1];
+        for (int g = 0; g < G; ++g) {
+            g_row[g] = 0; g_xw[g] = 0; g_phase[g] = 0; g_end[g] = tasks;
+            if (e0 + g >= count) continue;
+            const uint32_t ent = a.hole_list[e0 + g];
+            const uint32_t row = ent >> 8, w = ent & 0xffu;
+            const int b = (int)(((unsigned long long)row * a.magic_h) >> 40), y = (int)row - b * H;
+            const int strip = a.tabs[b].strip;
+            uint32_t m = a.hole_mask[(size_t)row * a.Wwords + w];
+            const int xw = (int)w * 32;
+            if (strip > xw) m = (strip - xw >= 32) ? 0u : (m & ~((1u << (strip - xw)) - 1u));
+            if (m == 0u) continue;
+            uint16_t *T = Tw + g * TSZ;
+            uint16_t *pos = T + (CY + 1) * COLS;
+            if ((m >> lane) & 1u) pos[__popc(m & ((1u << lane) - 1u))] = (uint16_t)lane;
+            const uint8_t *left = a.sbs + (size_t)b * H * pitch;
+            const int s0 = 3 * (xw - CX);                             // byte offset of the footprint in its row
+            if (xw - CX >= 0 && xw + 31 + CX < W) {
+                // interior columns: aligned words, packed vertical pair sums
+                g_phase[g] = PHASE;
+                const bool rows_in = (y - CY >= 0) && (y + CY < H);
 #pragma unroll
-                    for (int i = 0; i <= 2 * CY; ++i)
-                        v[i] = __ldg(reinterpret_cast<const uint32_t *>(colp + (size_t)reflect_idx(y + i - CY, H) * pitch));
+                for (int half = 0; half < (NWORDS + 31) / 32; ++half) {
+                    const int k = lane + 32 * half;
+                    if (k < NWORDS) {
+                        const uint8_t *colp = left + (s0 - PHASE) + 4 * k;
+                        uint32_t v[2 * CY + 1];
+                        if (rows_in) {
+                            const uint8_t *p0 = colp + (size_t)(y - CY) * pitch;
 #pragma unroll
-                    for (int i = 0; i <= CY; ++i) {
-                        const uint32_t p = v[CY - i], q = v[CY + i];
-                        uint32_t lo = p & 0x00ff00ffu, hi = (p >> 8) & 0x00ff00ffu;
-                        if (i) { lo += q & 0x00ff00ffu; hi += (q >> 8) & 0x00ff00ffu; }
-                        *reinterpret_cast<uint2 *>(T + i * COLS + 4 * k) = make_uint2(__byte_perm(lo, hi, 0x5410), __byte_perm(lo, hi, 0x7632));
+                            for (int i = 0; i <= 2 * CY; ++i) v[i] = __ldg(reinterpret_cast<const uint32_t *>(p0 + (size_t)i * pitch));
+                        } else {
+#pragma unroll
+                            for (int i = 0; i <= 2 * CY; ++i)
+                                v[i] = __ldg(reinterpret_cast<const uint32_t *>(colp + (size_t)reflect_idx(y + i - CY, H) * pitch));
+                        }
+#pragma unroll
+                        for (int i = 0; i <= CY; ++i) {
+                            const uint32_t p = v[CY - i], q = v[CY + i];
+                            uint32_t lo = p & 0x00ff00ffu, hi = (p >> 8) & 0x00ff00ffu;
+                            if (i) { lo += q & 0x00ff00ffu; hi += (q >> 8) & 0x00ff00ffu; }
+                            *reinterpret_cast<uint2 *>(T + i * COLS + 4 * k) = make_uint2(__byte_perm(lo, hi, 0x5410), __byte_perm(lo, hi, 0x7632));
+                        }
                     }
                 }
-            }
-        } else {
-            // border words: byte by byte with reflect padding
-            phase = 0;
-            for (int c = lane; c < 3 * NPX; c += 32) {
-                const int px = c / 3, ch = c - px * 3;
-                const int X = min(max(reflect_idx(xw - CX + px, W), 0), W - 1);
-                const uint8_t *colp = left + (size_t)X * 3 + ch;
-                T[c] = colp[(size_t)y * pitch];
+            } else {
+                // border words: byte by byte with reflect padding
+                for (int c = lane; c < 3 * NPX; c += 32) {
+                    const int px = c / 3, ch = c - px * 3;
+                    const int X = min(max(reflect_idx(xw - CX + px, W), 0), W - 1);
+                    const uint8_t *colp = left + (size_t)X * 3 + ch;
+                    T[c] = colp[(size_t)y * pitch];
 #pragma unroll
-                for (int i = 1; i <= CY; ++i)
-                    T[i * COLS + c] = (uint16_t)colp[(size_t)reflect_idx(y - i, H) * pitch] + (uint16_t)colp[(size_t)reflect_idx(y + i, H) * pitch];
+                    for (int i = 1; i <= CY; ++i)
+                        T[i * COLS + c] = (uint16_t)colp[(size_t)reflect_idx(y - i, H) * pitch] + (uint16_t)colp[(size_t)reflect_idx(y + i, H) * pitch];
+                }
             }
+            g_row[g] = row; g_xw[g] = (uint32_t)xw;
+            tasks += 3u * (uint32_t)__popc(m);
+            g_end[g] = tasks;
         }
         __syncwarp();
-        const int nh = __popc(m);
-        const int slot = lane / 3, ch = lane - slot * 3;
-        for (int h0 = 0; h0 < nh; h0 += 10) {
-            const int hi_ = h0 + slot;
-            if (lane < 30 && hi_ < nh) {
-                const int xo = pos[hi_];
+        // ---- evaluate: task = (entry, hole rank, channel), 32 tasks per pass ----
+        for (uint32_t t0 = 0; t0 < tasks; t0 += 32) {
+            const uint32_t task = t0 + lane;
+            if (task < tasks) {
+                int g = 0;
+                uint32_t start = 0;
+#pragma unroll
+                for (int k = 0; k < G - 1; ++k)
+                    if (task >= g_end[k]) { g = k + 1; start = g_end[k]; }
+                uint32_t row = g_row[0], xw = g_xw[0], phase = g_phase[0];
+#pragma unroll
+                for (int k = 1; k < G; ++k)
+                    if (g == k) { row = g_row[k]; xw = g_xw[k]; phase = g_phase[k]; }
+                const uint32_t rel = task - start, rank = rel / 3u, ch = rel - rank * 3u;
+                const uint16_t *T = Tw + g * TSZ;
+                const int xo = T[(CY + 1) * COLS + rank];
                 const uint16_t *Tc = T + phase + 3 * (xo + CX) + ch;
                 uint32_t acc[PARTS];
 #pragma unroll
@@ -241,7 +273,7 @@ template <int CX, int CY>
 __host__ __device__ constexpr size_t blur_fixed_warp_smem() {
     constexpr int PHASE = ((-3 * CX) % 4 + 4) % 4;
     constexpr int NWORDS = (PHASE + 3 * (32 + 2 * CX) + 3) / 4, COLS = (NWORDS * 4 + 7) / 8 * 8;
-    return ((size_t)(CY + 1) * COLS + 32) * sizeof(uint16_t);
+    return (size_t)blur_group<CX>() * ((size_t)(CY + 1) * COLS + 32) * sizeof(uint16_t);
 }
 
 // plane -> SBS frame for the listed holes right of the strip, then result_img[:, 0:strip] = img[:, 0:strip]

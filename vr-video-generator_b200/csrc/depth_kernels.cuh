@@ -205,10 +205,10 @@ __global__ void __launch_bounds__(256) k_depth_max(DepthMaxArgs a) {
     if (active) {
         // after B frames the newest two raw frames sit in (X,Y), (Z,X) or (Y,Z) depending on B mod 3
         const int r = a.B % 3;
-        const float *n1 = r == 0 ? X : (r == 1 ? Z : Y), *n2 = r == 0 ? Y : (r == 1 ? X : Z);
+
         uint4 o1, o2;
         if (r == 0) { o1 = pack(X); o2 = pack(Y); } else if (r == 1) { o1 = pack(Z); o2 = pack(X); } else { o1 = pack(Y); o2 = pack(Z); }
-        (void)n1; (void)n2;
+
         *reinterpret_cast<uint4 *>(a.hist1_out + base) = o1;
         *reinterpret_cast<uint4 *>(a.hist2_out + base) = o2;
     }

@@ -182,12 +182,13 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_fused(FusedArgs a) {
             const uint32_t lut_mul = 1u << (16u - hdr.shift), lut_last = sa_lut + hdr.ncells;
             const uint32_t nW4 = 0u - W4;
             // U segments of 32 pixels per step, all loads of a step issued before their uses
-            auto batch = [&](auto Uc, int round0, bool tail) {
+            // w_last: warp index used for the LAST segment of the batch (differs from `warp` only for the left-over segment)
+            auto batch = [&](auto Uc, int round0, bool tail, int w_last) {
                 constexpr int U = decltype(Uc)::value;
                 uint32_t c[U], p1[U], p2[U], w0[U], w1[U], x4[U], ok[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const int seg = (round0 + u) * NW + warp;
+                    const int seg = (round0 + u) * NW + (u == U - 1 ? w_last : warp);
                     const int x = (seg << 5) + lane;
                     ok[u] = (!tail || x < W) ? 1u : 0u;
                     const int xc = tail ? min(x, W - 1) : x;
@@ -254,18 +255,23 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_fused(FusedArgs a) {
                 }
             };
             if ((W & 31) == 0) {
-                // whole segments only: this warp owns segments warp, warp + NW, ... (nw of them), 4 at a time
-                const int nw = nseg / NW + ((warp < nseg % NW) ? 1 : 0);
+                // whole segments only: this warp owns segments warp, warp + NW, ... 4 at a time.  The nseg % NW left-over
+                // segments go to the LAST warps: warp 0 also issues the TMA traffic and warps 0.. flush the mask row.
+                const int full = nseg / NW, rem = nseg - full * NW;
+                const bool extra = NW - 1 - warp < rem;
+                const int nw = full + (extra ? 1 : 0);
                 int r = 0;
-                for (; r + 4 <= nw; r += 4) batch(std::integral_constant<int, 4>{}, r, false);
+                for (; r + 4 < nw; r += 4) batch(std::integral_constant<int, 4>{}, r, false, warp);
+                const int w_last = extra ? NW - 1 - warp : warp;      // the final batch ends with the left-over segment
                 switch (nw - r) {                             // warp-uniform
-                    case 3: batch(std::integral_constant<int, 3>{}, r, false); break;
-                    case 2: batch(std::integral_constant<int, 2>{}, r, false); break;
-                    case 1: batch(std::integral_constant<int, 1>{}, r, false); break;
+                    case 4: batch(std::integral_constant<int, 4>{}, r, false, w_last); break;
+                    case 3: batch(std::integral_constant<int, 3>{}, r, false, w_last); break;
+                    case 2: batch(std::integral_constant<int, 2>{}, r, false, w_last); break;
+                    case 1: batch(std::integral_constant<int, 1>{}, r, false, w_last); break;
                     default: break;
                 }
             } else {
-                for (int r = 0; r * NW + warp < nseg; ++r) batch(std::integral_constant<int, 1>{}, r, true);
+                for (int r = 0; r * NW + warp < nseg; ++r) batch(std::integral_constant<int, 1>{}, r, true, warp);
             }
         } else {
             // slow path (L > 255, non-monotone bounds, LUT too coarse): brute-force membership, layer-only keys
