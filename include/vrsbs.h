@@ -124,7 +124,11 @@ int  vrsbs_build_tables(vrsbs_ctx *ctx, int B, int H, int W, void *stream);
 int  vrsbs_warp_batch(vrsbs_ctx *ctx, const uint8_t *frames_dev, const void *depth_dev,
                       int B, int H, int W, uint8_t *sbs_dev, void *stream);
 
-/* Stage 1(full-res)+2+3 in one call on device buffers (the "warp stage" bench.py times). */
+/* Stage 1(full-res)+2+3 in one call on device buffers (the "warp stage" bench.py times).  When the
+ * frame width is a multiple of 16 and the pointers are 16-byte aligned this runs the FUSED route: a
+ * max-only pass over the raw depth, the tables, and one warp kernel that recomputes the smoothing
+ * from the raw rows - depth_scratch_dev is then not touched (it may be NULL).  Otherwise the staged
+ * route runs and the smoothed depth is written to depth_scratch_dev ([B,H,W] fp16, required). */
 int  vrsbs_process_batch(vrsbs_ctx *ctx, const uint8_t *frames_dev, const void *depth_raw_dev,
                          int B, int H, int W, void *depth_scratch_dev, uint8_t *sbs_dev, void *stream);
 
@@ -132,9 +136,9 @@ int  vrsbs_process_batch(vrsbs_ctx *ctx, const uint8_t *frames_dev, const void *
  * Replaces the H2D copies (PredictAndGenerate.py:133,158), the whole warp and the blocking D2H
  * (`.cpu().numpy()`, PredictAndGenerate.py:197) for B frames with HOST buffers.  depth_host is
  * either full-res raw depth [B,H,W] fp16 (lowres_h = lowres_w = 0) or DPT low-res [B,h,w] fp16.
- * Internally double-buffered: pinned staging + two streams; frames are processed in chunks so
- * copy-in, kernels and copy-out of neighbouring chunks overlap.  Returns after sbs_host is
- * complete (like the reference's blocking D2H). */
+ * Internally pipelined: three streams (H2D / kernels / D2H) and three pinned slots; frames are
+ * processed in chunks ("host_chunk", default 4) so copy-in, kernels and copy-out of neighbouring
+ * chunks overlap.  Returns after sbs_host is complete (like the reference's blocking D2H). */
 int  vrsbs_process_host(vrsbs_ctx *ctx, const uint8_t *frames_host, const void *depth_host,
                         int B, int H, int W, int lowres_h, int lowres_w, float scaler,
                         uint8_t *sbs_host);
@@ -153,13 +157,14 @@ uint64_t vrsbs_launch_count(const vrsbs_ctx *ctx);
 
 /* Per-stage device time (CUDA events recorded on the launching stream around every kernel while the
  * option "stage_timing" is 1).  Synchronises, then ADDS the elapsed milliseconds of all launches
- * recorded since the previous call to ms[0..4] = {depth, tables, warp, blur, strip} and the number
+ * recorded since the previous call to ms[0..4] = {depth, tables, warp, blur, commit+strip} and the number
  * of launches to count[0..4]; the caller zeroes the arrays.  bench.py's roofline uses ms[2]. */
 #define VRSBS_NUM_STAGES 5
 int  vrsbs_get_stage_times(vrsbs_ctx *ctx, double ms[VRSBS_NUM_STAGES], uint64_t count[VRSBS_NUM_STAGES]);
 
-/* Tuning knobs: "scatter_mode" 2 (default) = shared-memory atomicMax for every key, 1 = plain store +
- * verify + atomicMax on conflicts; "bicubic_contract", "blocks_per_sm", "host_chunk", "copy_threads",
+/* Tuning knobs: "fused" (1 = fused route when possible), "fast_tables" (0 forces the slow membership
+ * path, tests), "scatter_mode" of the general row kernel (2 = atomicMax for every key, 1 = plain store +
+ * verify), "bicubic_contract", "blocks_per_sm", "host_chunk", "copy_threads", "pageable_direct",
  * "stage_timing". */
 int  vrsbs_set_option(vrsbs_ctx *ctx, const char *name, int value);
 
