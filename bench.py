@@ -133,6 +133,9 @@ def run_ours(args, wl, name):
     if args.scatter_mode:                      # 1/2: the general row kernel instead of the fused route (A/B runs)
         ctx.set_option("fused", 0)
         ctx.set_option("scatter_mode", args.scatter_mode)
+    for kv in args.opt:                        # tuning experiments: --opt name=value
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
     stream = torch.cuda.current_stream().cuda_stream
 
     # device-resident inputs: frames + RAW full-res fp16 depth (what SbsProcessor.get_depth receives),
@@ -333,6 +336,7 @@ def main():
     ap.add_argument("--scatter-mode", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--host-chunk", type=int, default=0)
+    ap.add_argument("--opt", action="append", default=[], help="library option name=value (vrsbs_set_option)")
     ap.add_argument("--pageable", action="store_true", help="also time the host API with pageable numpy buffers")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -282,26 +282,33 @@ __host__ __device__ constexpr size_t blur_fixed_warp_smem() {
 __global__ void __launch_bounds__(256) k_blur_commit(BlurArgs a, int do_commit) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const uint32_t count = do_commit ? *a.hole_count : 0u;
-    for (uint32_t e0 = (blockIdx.x * nwarps + warp) * 32u; e0 < count; e0 += gridDim.x * nwarps * 32u) {
+    constexpr int E = 4;                                   // entries per warp step: four independent load chains in flight
+    for (uint32_t e0 = (blockIdx.x * nwarps + warp) * E; e0 < count; e0 += gridDim.x * nwarps * E) {
         uint32_t gw = 0, m = 0, strip = 0;
-        if (e0 + lane < count) {
+        if (lane < E && e0 + lane < count) {
             gw = a.hole_list[e0 + lane];
             m = a.hole_mask[(size_t)(gw >> 8) * a.Wwords + (gw & 0xffu)];
             strip = (uint32_t)a.tabs[(int)(((unsigned long long)(gw >> 8) * a.magic_h) >> 40)].strip;
         }
-        const int n = min(32u, count - e0);
-#pragma unroll 4
-        for (int k = 0; k < n; ++k) {
+        uint32_t val[E];
+        uint8_t *dst[E];
+        bool on[E];
+#pragma unroll
+        for (int k = 0; k < E; ++k) {
             const uint32_t g = __shfl_sync(0xffffffffu, gw, k), mk = __shfl_sync(0xffffffffu, m, k), st = __shfl_sync(0xffffffffu, strip, k);
             const uint32_t row = g >> 8, w = g & 0xffu;
             const uint32_t x = w * 32u + lane;
-            if (((mk >> lane) & 1u) && x >= st) {
+            on[k] = ((mk >> lane) & 1u) && x >= st;
+            dst[k] = a.sbs + ((size_t)row * 2 * a.W + x) * 3;
+            val[k] = 0;
+            if (on[k]) {
                 const uint8_t *src = a.plane + ((size_t)row * a.W + x) * 3;
-                uint8_t *dst = a.sbs + ((size_t)row * 2 * a.W + x) * 3;
-                const uint8_t r0 = src[0], r1 = src[1], r2 = src[2];
-                dst[0] = r0; dst[1] = r1; dst[2] = r2;
+                val[k] = (uint32_t)src[0] | ((uint32_t)src[1] << 8) | ((uint32_t)src[2] << 16);
             }
         }
+#pragma unroll
+        for (int k = 0; k < E; ++k)
+            if (on[k]) { dst[k][0] = (uint8_t)val[k]; dst[k][1] = (uint8_t)(val[k] >> 8); dst[k][2] = (uint8_t)(val[k] >> 16); }
     }
     const long long tw = (long long)gridDim.x * nwarps;
     const long long rows = (long long)a.B * a.H;

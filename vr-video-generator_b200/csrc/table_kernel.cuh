@@ -195,6 +195,12 @@ __global__ void __launch_bounds__(256) k_build_tables(TableArgs a) {
     uint8_t *lut = blob + 16 + ent_bytes;
     const float fmax = s_max;
     bool ok = mono && !s_bad && !a.frame_nan[b] && L <= a.ent_cap && L <= 255 && a.W * 4 <= 65535 && fmax < 60000.f;
+    // the LUT search binary-searches the bounds thousands of times: keep them in shared memory (the mark buffers
+    // are free again; 2 * sstride doubles >= Lcap float2)
+    float2 *s_bounds = reinterpret_cast<float2 *>(s_val);
+    __syncthreads();
+    if (ok) for (int k = threadIdx.x; k < L; k += blockDim.x) s_bounds[k] = bounds[k];
+    __syncthreads();
     const uint32_t maxbits = (fmax > 0.f) ? (uint32_t)__half_as_ushort(__float2half_rn(fmax)) : 0u;
     int shift = -1;
     uint32_t ncells = 0;
@@ -212,7 +218,7 @@ __global__ void __launch_bounds__(256) k_build_tables(TableArgs a) {
                 } else {                           // every negative value (and -0.0)
                     vmin = -INFINITY; vmax = 0.f;
                 }
-                int e = cell_entry(bounds, L, vmin, vmax);
+                int e = cell_entry(s_bounds, L, vmin, vmax);
                 if (e < 0) valid = 0; else lut[q] = (uint8_t)e;
             }
             if (__syncthreads_and(valid)) { shift = sh; ncells = nc; break; }
