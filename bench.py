@@ -227,6 +227,25 @@ def run_ours(args, wl, name):
         proc.left_side_sbs_batch(frames_h, raw_h, out=o_pg)
         e2e["pageable_value"] = world * B / reduce_max(time.perf_counter() - t0)
 
+    # BASELINE.json configs[4]: a synthetic N-frame video sharded by clip range over the ranks (main_func's split,
+    # PredictAndGenerate.py:274-275), every rank streaming its range through the host API from a cycled pinned pool
+    video = None
+    if args.video_frames:
+        from vr_video_generator_b200 import shard
+        ranges = tables.clip_ranges(0, args.video_frames, args.video_frames, world)
+        begin, end = ranges[rank] if rank < len(ranges) else (0, 0)
+        proc.reset_state()
+        barrier()
+        t0 = time.perf_counter()
+        for b0 in range(begin, end, B):
+            n = min(B, end - b0)
+            proc.left_side_sbs_batch(f_pin[:n], d_pin[:n], out=o_np[:n])
+        torch.cuda.synchronize()
+        dt = reduce_max(time.perf_counter() - t0)
+        barrier()
+        video = {"frames": args.video_frames, "seconds": dt, "frames_per_sec": args.video_frames / dt,
+                 "ranges": [list(r) for r in ranges], "batch": B}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_port_fps(wl, frames_h, raw_h, budget_s=args.cpu_budget)
@@ -251,6 +270,8 @@ def run_ours(args, wl, name):
             "stage_ms_per_step": {k: v[0] / args.steps for k, v in stage.items()},
             "e2e_equals_device_output": same,
         }
+        if video:
+            line["video"] = video
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
@@ -336,6 +357,8 @@ def main():
     ap.add_argument("--scatter-mode", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--host-chunk", type=int, default=0)
+    ap.add_argument("--video-frames", type=int, default=0,
+                    help="also stream an N-frame synthetic video (e.g. 18000 = 10 min of 1080p30), sharded by clip range over the ranks")
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (vrsbs_set_option)")
     ap.add_argument("--pageable", action="store_true", help="also time the host API with pageable numpy buffers")
     ap.add_argument("--cpu-budget", type=float, default=20.0)

@@ -91,3 +91,59 @@ def clip_ranges(start_frame, end_frame, video_length, num_workers):
         return []
     step = math.ceil((stop - start_frame) / num_workers)
     return [(b, min(end_frame, b + step)) for b in range(start_frame, stop, step)]
+
+
+# ---- host mirror of the fast-path membership tables (csrc/table_kernel.cuh: cell_entry + the LUT loop) --------
+def cell_entry(lo, hi, vmin, vmax):
+    """LUT value for the depth cell [vmin, vmax] given monotone fp16 bounds lo[k] <= d < hi[k]:
+    e such that a value of the cell can only be in layer e-1 (iff v < hi[e-1]) or layer e (iff v >= lo[e]);
+    -1 if the cell is too coarse.  Same case analysis as the device function of the same name."""
+    L = len(lo)
+    a = int(sum(1 for k in range(L) if hi[k] <= vmin))           # hi is monotone: first layer whose hi exceeds vmin
+    if a >= L:
+        return L
+    if vmin >= lo[a] and (a + 2 > L - 1 or vmax < lo[a + 2]) and (a + 1 > L - 1 or vmax < hi[a + 1]):
+        return a + 1
+    if vmax < hi[a] and (a + 1 > L - 1 or vmax < lo[a + 1]):
+        return a
+    return -1
+
+
+def cell_lut(lo, hi, depth_max, lut_cap=8192):
+    """(shift, ncells, lut) or None.  cell = fp16 bits >> shift for non-negative values; index ncells = every
+    negative value.  lo/hi: float arrays holding exact fp16 values, monotone."""
+    import numpy as np
+    maxbits = int(np.float16(depth_max).view(np.uint16)) if depth_max > 0 else 0
+    for shift in range(9, -1, -1):
+        ncells = (maxbits >> shift) + 1
+        if ncells + 1 > lut_cap:
+            return None
+        lut = []
+        for q in range(ncells + 1):
+            if q < ncells:
+                b0, b1 = q << shift, min(((q + 1) << shift) - 1, maxbits)
+                vmin = float(np.uint16(b0).view(np.float16))
+                vmax = float(np.uint16(b1).view(np.float16))
+            else:
+                vmin, vmax = -math.inf, 0.0
+            e = cell_entry(lo, hi, vmin, vmax)
+            if e < 0:
+                break
+            lut.append(e)
+        else:
+            return shift, ncells, lut
+    return None
+
+
+def lut_members(lo, hi, shift, ncells, lut, value):
+    """Layers the device's two-compare test paints for one fp16 value (warp_fused.cuh scatter)."""
+    import numpy as np
+    bits = int(np.float16(value).view(np.uint16))
+    e = lut[min(bits >> shift, ncells)]
+    L = len(lo)
+    out = []
+    if e >= 1 and value < hi[e - 1]:
+        out.append(e - 1)
+    if e <= L - 1 and not (value < lo[e]):
+        out.append(e)
+    return out
