@@ -258,7 +258,7 @@ def run_ours(args, wl, name):
             "config": {"workload": f"{name}: {W}x{H}, {B}-frame batch per GPU, fg={wl['fg']} bg={wl['bg']} step={wl['step']}, "
                                    f"D-{wl['depth']} depth (limit_step {infos[0].limit_step}, {infos[0].layers} layers, "
                                    f"{100.0 * infos[0].holes / (H * W):.2f}% holes)",
-                       "timed_region": "depth max pass, device tables, fused smoothing+warp+fill+pack, hole blur, strip; inputs/outputs in HBM",
+                       "timed_region": "depth smoothing+max pass, device tables, warp+fill+pack, hole blur, commit+strip; inputs/outputs in HBM",
                        "l2": f"inputs per step {int((frames_h.nbytes + raw_h.nbytes) / 2**20)} MiB + outputs "
                              f"{int(o_np.nbytes / 2**20)} MiB per GPU > 126 MB L2 (no flush needed)",
                        "sharding": "independent clip range per GPU, no collective",

@@ -124,11 +124,11 @@ int  vrsbs_build_tables(vrsbs_ctx *ctx, int B, int H, int W, void *stream);
 int  vrsbs_warp_batch(vrsbs_ctx *ctx, const uint8_t *frames_dev, const void *depth_dev,
                       int B, int H, int W, uint8_t *sbs_dev, void *stream);
 
-/* Stage 1(full-res)+2+3 in one call on device buffers (the "warp stage" bench.py times).  When the
- * frame width is a multiple of 16 and the pointers are 16-byte aligned this runs the FUSED route: a
- * max-only pass over the raw depth, the tables, and one warp kernel that recomputes the smoothing
- * from the raw rows - depth_scratch_dev is then not touched (it may be NULL).  Otherwise the staged
- * route runs and the smoothed depth is written to depth_scratch_dev ([B,H,W] fp16, required). */
+/* Stage 1(full-res)+2+3 in one call on device buffers (the "warp stage" bench.py times).  The
+ * smoothed depth is written to depth_scratch_dev ([B,H,W] fp16, required) and consumed by the warp
+ * kernel.  With the option "smooth_in_warp" = 1 (and a frame width that is a multiple of 16, 16-byte
+ * aligned pointers) the depth pass computes the maxima only and the warp kernel recomputes the
+ * smoothing from the raw rows; depth_scratch_dev is then not touched and may be NULL. */
 int  vrsbs_process_batch(vrsbs_ctx *ctx, const uint8_t *frames_dev, const void *depth_raw_dev,
                          int B, int H, int W, void *depth_scratch_dev, uint8_t *sbs_dev, void *stream);
 
@@ -162,8 +162,8 @@ uint64_t vrsbs_launch_count(const vrsbs_ctx *ctx);
 #define VRSBS_NUM_STAGES 5
 int  vrsbs_get_stage_times(vrsbs_ctx *ctx, double ms[VRSBS_NUM_STAGES], uint64_t count[VRSBS_NUM_STAGES]);
 
-/* Tuning knobs: "fused" (1 = fused route when possible), "fast_tables" (0 forces the slow membership
- * path, tests), "scatter_mode" of the general row kernel (2 = atomicMax for every key, 1 = plain store +
+/* Tuning knobs: "fused" (1 = TMA warp kernel k_warp_fused when the shape allows, 0 = general row kernel),
+ * "smooth_in_warp" (see vrsbs_process_batch), "fast_tables" (0 forces the slow membership path, tests), "scatter_mode" of the general row kernel (2 = atomicMax for every key, 1 = plain store +
  * verify), "bicubic_contract", "blocks_per_sm", "host_chunk", "copy_threads", "pageable_direct",
  * "stage_timing". */
 int  vrsbs_set_option(vrsbs_ctx *ctx, const char *name, int value);

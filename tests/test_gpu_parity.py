@@ -23,7 +23,10 @@ def _sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
-MODES = [0, 1, 2, 3]   # 0 fused fast route; 1/2 general row kernel (store+verify / atomicMax); 3 fused route, slow membership
+# 0 default route (depth pass stores the smoothed depth, k_warp_fused<false>, LUT membership); 1/2 general row kernel
+# (store+verify / atomicMax); 3 default route with the slow membership path; 4 smoothing inside the warp kernel
+# (k_warp_fused<true>, no smoothed depth in HBM); 5 = 4 with the slow membership path
+MODES = [0, 1, 2, 3, 4, 5]
 
 
 def _ctx(H, W, fg, bg, step, weights=None, blur=True, max_batch=8, max_layers=512, mode=0):
@@ -33,8 +36,9 @@ def _ctx(H, W, fg, bg, step, weights=None, blur=True, max_batch=8, max_layers=51
     if weights is None:
         weights = tables.gaussian_weights(*tables.blur_kernel_shape(H))
     ctx.set_blur_weights(weights)
-    ctx.set_option("fused", 1 if mode in (0, 3) else 0)
-    ctx.set_option("fast_tables", 0 if mode == 3 else 1)
+    ctx.set_option("fused", 0 if mode in (1, 2) else 1)
+    ctx.set_option("fast_tables", 0 if mode in (3, 5) else 1)
+    ctx.set_option("smooth_in_warp", 1 if mode in (4, 5) else 0)
     if mode in (1, 2):
         ctx.set_option("scatter_mode", mode)
     return ctx
@@ -85,8 +89,8 @@ def test_small_cases_match_reference(name, mode, oracle_lib):
     want, stages = _oracle_run(oracle_lib, p, frames, raw, w)
     for t in range(p["n"]):
         fm = meta["frames"][t]
-        # T7 (smoothing half): fp16 bit-exact (the fused route never materialises the smoothed depth)
-        if mode in (1, 2):
+        # T7 (smoothing half): fp16 bit-exact (modes 4/5 never materialise the smoothed depth)
+        if mode in (0, 1, 2, 3):
             assert np.array_equal(dep[t].view(np.uint16), stages[t]["depth"].view(np.uint16))
         # T1 (summary; the full lists are checked in test_device_tables_equal_reference_lists)
         assert infos[t].layers == fm["layers"] and infos[t].limit_step == fm["limit"]

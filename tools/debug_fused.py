@@ -14,7 +14,7 @@ def run(name, mode, blur):
     H, W, n = p["H"], p["W"], p["n"]
     ctx = _native.Context(0, H, W, 4, 512)
     ctx.reset(p["fg"], p["bg"], p["step"], blur); ctx.set_blur_weights(w)
-    ctx.set_option("fused", 1 if mode in (0, 3) else 0); ctx.set_option("fast_tables", 0 if mode == 3 else 1)
+    ctx.set_option("fused", 0 if mode in (1, 2) else 1); ctx.set_option("fast_tables", 0 if mode in (3, 5) else 1); ctx.set_option("smooth_in_warp", 1 if mode in (4, 5) else 0)
     if mode in (1, 2): ctx.set_option("scatter_mode", mode)
     f = torch.from_numpy(np.ascontiguousarray(frames)).cuda(); r = torch.from_numpy(np.ascontiguousarray(raw)).cuda()
     out = torch.zeros((n, H, 2 * W, 3), dtype=torch.uint8, device="cuda"); dep = torch.empty((n, H, W), dtype=torch.float16, device="cuda")

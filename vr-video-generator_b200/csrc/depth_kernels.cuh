@@ -118,11 +118,13 @@ __device__ __forceinline__ __half2 smooth3x2(__half2 cur, __half2 p1, __half2 p2
     return __hadd2(d, mul_w(p2, sw.w_prev2));
 }
 
-// ---- pass 1 of the fused pipeline: per-frame max of the SMOOTHED depth, nothing else written -------------
-// Reads raw [B,n] once; the smoothed frames are recomputed inside k_warp_fused from the same raw rows,
-// so the smoothed depth never exists in HBM.  Also writes the next batch's history (raw B-1, raw B-2) into
-// the ping-pong history buffers hist1_out/hist2_out.
+// ---- depth pass: temporal smoothing + per-frame max of the SMOOTHED depth ---------------------------------
+// Reads raw [B,n] once.  STORE = true (default route): also writes the smoothed depth the warp kernel consumes.
+// STORE = false (option smooth_in_warp): max only; k_warp_fused<true> then recomputes the smoothing from the same
+// raw rows and the smoothed depth never exists in HBM.  Writes the next batch's history (raw B-1, raw B-2) to
+// hist1_out/hist2_out (the same buffers in place, or the other ping-pong set when the warp kernel still reads them).
 struct DepthMaxArgs {
+    __half *out;                         // [B, n] smoothed depth (STORE variant) or nullptr
     const __half *raw;                   // [B, n]
     const __half *hist1, *hist2;         // [n] raw t-1, t-2 of the previous batch
     __half *hist1_out, *hist2_out;       // [n]
@@ -138,7 +140,8 @@ __device__ __forceinline__ uint32_t h16_key(uint32_t u) {
     return ((u & 0x7fffu) > 0x7c00u) ? 0x1ffffu : k;
 }
 
-__global__ void __launch_bounds__(256) k_depth_max(DepthMaxArgs a) {
+template <bool STORE>
+__global__ void __launch_bounds__(256) k_depth_pass(DepthMaxArgs a) {
     extern __shared__ uint32_t s_red[];          // [B] keys
     for (int i = threadIdx.x; i < a.B; i += blockDim.x) s_red[i] = 0;
     __syncthreads();
@@ -167,13 +170,16 @@ __global__ void __launch_bounds__(256) k_depth_max(DepthMaxArgs a) {
         uint32_t key = 0;
         if (active) {
             __half2 m;
+            V sm;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 __half2 d = __hadd2(__floats2half2_rn(__fmul_rn(c[2 * e], w0), __fmul_rn(c[2 * e + 1], w0)),
                                     __floats2half2_rn(__fmul_rn(p1[2 * e], w1), __fmul_rn(p1[2 * e + 1], w1)));
                 d = __hadd2(d, __floats2half2_rn(__fmul_rn(p2[2 * e], w2), __fmul_rn(p2[2 * e + 1], w2)));
+                sm.h[e] = d;
                 m = e ? __hmax2_nan(m, d) : d;
             }
+            if (STORE) *reinterpret_cast<uint4 *>(a.out + (size_t)t * a.n + base) = sm.u;
             m = __hmax2_nan(m, __lowhigh2highlow(m));
             key = h16_key((uint32_t)__half_as_ushort(__low2half(m)));
         }

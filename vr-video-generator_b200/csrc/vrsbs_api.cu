@@ -72,6 +72,8 @@ struct vrsbs_ctx {
     int ent_cap = 0, lut_cap = 0;        // fast-path table capacities of the last vrsbs_build_tables
     int fused = 1;                       // option: use the fused route in vrsbs_process_batch when possible
     int fast_tables = 1;                 // option (tests): 0 forces the slow membership path of k_warp_fused
+    int smooth_in_warp = 0;              // option: 1 = smoothing recomputed inside the warp kernel (no smoothed depth in HBM);
+                                         // measured slower than materialising it, so off by default
     // host pipeline
     HostSlot slot[kSlots];
     int host_chunk = 4;
@@ -208,7 +210,11 @@ int launch_depth(vrsbs_ctx *c, Scratch &s, const __half *raw, const __half *lowr
     if (raw) {
         const bool vec = (n % 8 == 0) && ((uintptr_t)raw % 16 == 0) && ((uintptr_t)out % 16 == 0);
         if (vec) {
-            k_depth_full<8><<<(unsigned)((n / 8 + 255) / 256), 256, smem, st>>>(a);
+            // same kernel as the fused route's max pass, additionally storing the smoothed depth; history in place
+            DepthMaxArgs m{};
+            m.out = out; m.raw = raw; m.hist1 = a.hist1; m.hist2 = a.hist2; m.hist1_out = a.hist1; m.hist2_out = a.hist2;
+            m.frame_max = s.frame_max; m.frame_nan = s.frame_nan; m.sw = c->sw; m.B = B; m.first = a.first; m.n = n;
+            k_depth_pass<true><<<(unsigned)((n / 8 + 255) / 256), 256, smem, st>>>(m);
         } else {
             k_depth_full<1><<<(unsigned)((n + 255) / 256), 256, smem, st>>>(a);
         }
@@ -235,7 +241,7 @@ int launch_depth_max(vrsbs_ctx *c, Scratch &s, const __half *raw, int B, int H, 
     a.frame_max = s.frame_max; a.frame_nan = s.frame_nan; a.sw = c->sw;
     a.B = B; a.first = c->depth_frames == 0; a.n = (size_t)H * W;
     StageTimer timer(c, st, 0);
-    k_depth_max<<<(unsigned)((a.n / 8 + 255) / 256), 256, sizeof(uint32_t) * 2 * B, st>>>(a);
+    k_depth_pass<false><<<(unsigned)((a.n / 8 + 255) / 256), 256, sizeof(uint32_t) * 2 * B, st>>>(a);
     CU_TRY(c, cudaGetLastError());
     c->launches++;
     return VRSBS_OK;
@@ -462,7 +468,7 @@ int launch_process_fused(vrsbs_ctx *c, Scratch &s, const uint8_t *frames, const 
     a.first = first ? 1 : 0;
     rc = W <= 2048 ? launch_fused_inst<true, 256>(c, a, st) : launch_fused_inst<true, 512>(c, a, st);
     if (rc) return rc;
-    c->hist_idx ^= 1;                        // k_depth_max wrote the next batch's history into the other set
+    c->hist_idx ^= 1;                        // k_depth_pass wrote the next batch's history into the other set
     c->depth_frames += B;
     c->state_h = H; c->state_w = W;
     if (!c->params.blur) return VRSBS_OK;
@@ -749,7 +755,7 @@ int vrsbs_process_batch(vrsbs_ctx *c, const uint8_t *frames, const void *raw, in
     cudaStream_t st = (cudaStream_t)stream;
     Scratch &s = c->scratch[0];
     fast_caps(c, H, &c->ent_cap, &c->lut_cap);
-    if (c->fused && ((size_t)H * W) % 8 == 0 && fused_capable(c, frames, raw, sbs, W))
+    if (c->fused && c->smooth_in_warp && ((size_t)H * W) % 8 == 0 && fused_capable(c, frames, raw, sbs, W))
         return launch_process_fused(c, s, frames, (const __half *)raw, B, H, W, sbs, st);
     if (!depth_scratch) return fail(c, VRSBS_E_INVALID, "depth_scratch_dev is required for this frame size / alignment");
     if ((rc = launch_depth(c, s, (const __half *)raw, nullptr, B, H, W, 0, 0, 1.f, (__half *)depth_scratch, st))) return rc;
@@ -778,7 +784,7 @@ int vrsbs_process_host(vrsbs_ctx *c, const uint8_t *frames, const void *depth, i
     }
     fast_caps(c, H, &c->ent_cap, &c->lut_cap);
     if ((rc = check_blur_ready(c, H, W))) return rc;
-    const bool use_fused = !lowres && c->fused && ((size_t)H * W) % 8 == 0 &&
+    const bool use_fused = !lowres && c->fused && c->smooth_in_warp && ((size_t)H * W) % 8 == 0 &&
                            fused_capable(c, c->slot[0].dev_frames, c->slot[0].dev_depth_in, c->slot[0].dev_sbs, W);
 
     // Three streams: st_in copies chunk i+1 in while st_k runs the kernels of chunk i and st_out copies chunk i-1
@@ -907,6 +913,7 @@ int vrsbs_set_option(vrsbs_ctx *c, const char *name, int value) {
     else if (!strcmp(name, "pageable_direct")) c->pageable_direct = value != 0;
     else if (!strcmp(name, "fused")) c->fused = value != 0;
     else if (!strcmp(name, "fast_tables")) c->fast_tables = value != 0;
+    else if (!strcmp(name, "smooth_in_warp")) c->smooth_in_warp = value != 0;
     else return fail(c, VRSBS_E_INVALID, "unknown option %s", name);
     return VRSBS_OK;
 }
