@@ -227,6 +227,20 @@ def run_ours(args, wl, name):
         proc.left_side_sbs_batch(frames_h, raw_h, out=o_pg)
         e2e["pageable_value"] = world * B / reduce_max(time.perf_counter() - t0)
 
+    # the reference's own per-frame call (left_side_sbs with the depth arriving on a queue), as nibba_woka makes it
+    import queue
+    q = queue.Queue()
+    proc.reset_state()
+    nper = min(B, 16)
+    for t in range(nper + 2):
+        q.put(torch.from_numpy(raw_h[t % B]))
+    proc.left_side_sbs(frames_h[0], None, q)
+    proc.left_side_sbs(frames_h[1], None, q)
+    t0 = time.perf_counter()
+    for t in range(nper):
+        proc.left_side_sbs(frames_h[t], None, q)
+    e2e["per_frame_call_fps"] = nper / (time.perf_counter() - t0)
+
     # BASELINE.json configs[4]: a synthetic N-frame video sharded by clip range over the ranks (main_func's split,
     # PredictAndGenerate.py:274-275), every rank streaming its range through the host API from a cycled pinned pool
     video = None

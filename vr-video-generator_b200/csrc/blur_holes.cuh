@@ -310,13 +310,23 @@ __global__ void __launch_bounds__(256) k_blur_commit(BlurArgs a, int do_commit) 
         for (int k = 0; k < E; ++k)
             if (on[k]) { dst[k][0] = (uint8_t)val[k]; dst[k][1] = (uint8_t)(val[k] >> 8); dst[k][2] = (uint8_t)(val[k] >> 16); }
     }
-    const long long tw = (long long)gridDim.x * nwarps;
+    // strip restore: 4 threads per image row, 64 bytes each per round (16-byte copies when the rows are aligned)
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
     const long long rows = (long long)a.B * a.H;
-    for (long long r = (long long)blockIdx.x * nwarps + warp; r < rows; r += tw) {
+    const bool vec = (a.W % 16 == 0) && ((reinterpret_cast<uintptr_t>(a.frames) | reinterpret_cast<uintptr_t>(a.sbs)) % 16 == 0);
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < rows * 4; idx += nthreads) {
+        const long long r = idx >> 2;
+        const int part = (int)(idx & 3);
         const int nbytes = a.tabs[(int)(((unsigned long long)r * a.magic_h) >> 40)].strip * 3;
         const uint8_t *src = a.frames + r * (size_t)a.W * 3;
         uint8_t *dst = a.sbs + r * (size_t)a.W * 6;
-        for (int c = lane; c < nbytes; c += 32) dst[c] = src[c];
+        for (int c0 = part * 64; c0 < nbytes; c0 += 256) {
+            const int c1 = min(c0 + 64, nbytes);
+            int c = c0;
+            if (vec)
+                for (; c + 16 <= c1; c += 16) *reinterpret_cast<uint4 *>(dst + c) = __ldg(reinterpret_cast<const uint4 *>(src + c));
+            for (; c < c1; ++c) dst[c] = src[c];
+        }
     }
 }
 

@@ -138,20 +138,23 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_fused(FusedArgs a) {
 
     const int wofs = (3 * lane) >> 2, wsh = ((3 * lane) & 3) * 8;       // lane-constant part of the pixel fetch
 
+    int i3 = 0;                 // n % 3: image slot and mbarrier of iteration n
+    uint32_t par = 0;           // (n / 3) & 1: phase parity of that mbarrier
     for (int n = 0; n < N; ++n) {
         // slots of iteration n+1's history and of cur(n+2)
         const bool bnd1 = SMOOTH && (t1 == 0);
         int h1_1, h2_1, c2;
-        if (bnd1) { h2_1 = (c1 + 1) & 3; h1_1 = (c1 + 2) & 3; c2 = (c1 + 3) & 3; }
+        if (!SMOOTH) { h1_1 = c0; h2_1 = h1_0; c2 = (c1 + 1) & 3; }
+        else if (bnd1) { h2_1 = (c1 + 1) & 3; h1_1 = (c1 + 2) & 3; c2 = (c1 + 3) & 3; }
         else      { h1_1 = c0; h2_1 = h1_0; c2 = c1 ^ c0 ^ h1_0; }
 
-        const uint8_t *img_row = smem + lay.img + (n % kImgSlots) * lay.img_stride;
+        const uint8_t *img_row = smem + lay.img + i3 * lay.img_stride;
         const uint8_t *blob = smem + lay.blob + (n & 1) * lay.blob_stride;
         const uint16_t *dcur = reinterpret_cast<const uint16_t *>(smem + lay.dep + c0 * lay.dep_stride);
         const uint16_t *dp1 = reinterpret_cast<const uint16_t *>(smem + lay.dep + h1_0 * lay.dep_stride);
         const uint16_t *dp2 = reinterpret_cast<const uint16_t *>(smem + lay.dep + h2_0 * lay.dep_stride);
 
-        mbar_wait(&bars[n % kBars], (n / kBars) & 1);
+        mbar_wait(&bars[i3], par);
 
         const BlobHdr hdr = *reinterpret_cast<const BlobHdr *>(blob);
         const bool fast = hdr.flags & 1u;
@@ -373,6 +376,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_fused(FusedArgs a) {
             }
         }
         // advance the uniform state
+        if (++i3 == 3) { i3 = 0; par ^= 1u; }
         y0 = y1; t0 = t1; y1 = y2; t1 = t2; next_yt(y2, t2);
         h2_0 = h2_1; h1_0 = h1_1; c0 = c1; c1 = c2;
     }
