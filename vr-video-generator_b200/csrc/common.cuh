@@ -44,7 +44,7 @@ struct BlobHdr {
 };
 struct LayerEnt {
     uint32_t hi_lo;         // half2: .x (low 16) = hi of layer e-1 (-inf for e = 0), .y = lo of layer e (+inf for e = L)
-    uint32_t off4;          // low 16: 4*(offset of layer e-1 mod W); high 16: 4*(offset of layer e mod W)
+    uint32_t off4;          // low 16: 4*(signed offset of layer e-1 + key_pad); high 16: same for layer e
 };
 __host__ __device__ inline uint32_t blob_ent_bytes(int ent_cap) { return (uint32_t)(((ent_cap + 1) * 8 + 15) / 16 * 16); }
 __host__ __device__ inline uint32_t blob_bytes(int ent_cap, int lut_cap) {

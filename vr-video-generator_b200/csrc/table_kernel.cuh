@@ -27,6 +27,7 @@ struct TableArgs {
     double offset_fg, offset_bg;
     int step, B, H, W, Lcap;
     int ent_cap, lut_cap;        // capacity of the blob's entry table (layers) and cell LUT (bytes)
+    int key_pad;                 // fast path: every signed offset (shortest way round the row) must satisfy |off| <= key_pad
 };
 
 // LUT value for the cell of depth values [vmin, vmax] (monotone bounds required): e such that every
@@ -202,6 +203,14 @@ __global__ void __launch_bounds__(256) k_build_tables(TableArgs a) {
     if (ok) for (int k = threadIdx.x; k < L; k += blockDim.x) s_bounds[k] = bounds[k];
     __syncthreads();
     const uint32_t maxbits = (fmax > 0.f) ? (uint32_t)__half_as_ushort(__float2half_rn(fmax)) : 0u;
+    {
+        int fits = 1;
+        for (int k = threadIdx.x; k < L; k += blockDim.x) {
+            const int o = offm[k + 1], so = o * 2 < a.W ? o : o - a.W;
+            if (so > a.key_pad || so < -a.key_pad) fits = 0;
+        }
+        ok = __syncthreads_and(fits) && ok;
+    }
     int shift = -1;
     uint32_t ncells = 0;
     if (ok) {
@@ -229,8 +238,9 @@ __global__ void __launch_bounds__(256) k_build_tables(TableArgs a) {
         LayerEnt le;
         const uint32_t hi = e >= 1 ? a.hi16[(size_t)b * a.Lcap + e - 1] : 0xFC00u;        // -inf
         const uint32_t lo = e <= L - 1 ? a.lo16[(size_t)b * a.Lcap + e] : 0x7C00u;        // +inf
-        const uint32_t o0 = e >= 1 ? (uint32_t)offm[e] * 4u : 0u;
-        const uint32_t o1 = e <= L - 1 ? (uint32_t)offm[e + 1] * 4u : 0u;
+        auto biased4 = [&](int o) { return (uint32_t)(((o * 2 < a.W ? o : o - a.W) + a.key_pad) * 4) & 0xffffu; };
+        const uint32_t o0 = e >= 1 ? biased4(offm[e]) : 0u;
+        const uint32_t o1 = e <= L - 1 ? biased4(offm[e + 1]) : 0u;
         le.hi_lo = hi | (lo << 16);
         le.off4 = (o0 & 0xffffu) | (o1 << 16);
         ent[e] = le;

@@ -70,6 +70,7 @@ struct vrsbs_ctx {
     std::vector<uint32_t> wq_host;
     int kx = 0, ky = 0, wparts = 0, wshift = 0;
     int ent_cap = 0, lut_cap = 0;        // fast-path table capacities of the last vrsbs_build_tables
+    int key_pad = 0;                     // fast path: bound on |signed layer offset| in pixels (multiple of 32)
     int fused = 1;                       // option: use the fused route in vrsbs_process_batch when possible
     int fast_tables = 1;                 // option (tests): 0 forces the slow membership path of k_warp_fused
     int smooth_in_warp = 0;              // option: 1 = smoothing recomputed inside the warp kernel (no smoothed depth in HBM);
@@ -249,7 +250,7 @@ int launch_depth_max(vrsbs_ctx *c, Scratch &s, const __half *raw, int B, int H, 
 
 // Capacities of the fast-path tables, from the parameters alone (no device round trip): enough layers and
 // LUT cells for limit_step <= 32; frames that need more take the slow path inside k_warp_fused.
-void fast_caps(const vrsbs_ctx *c, int H, int *ent_cap, int *lut_cap) {
+void fast_caps(vrsbs_ctx *c, int H, int W, int *ent_cap, int *lut_cap) {
     const double span_per_limit = fabs(c->params.offset_fg - c->params.offset_bg) * H / 14.0;   // pixels of offset per unit of limit
     const int step = c->params.offset_step_size;
     double layers = span_per_limit * 32.0 / step + 6.0;
@@ -268,6 +269,12 @@ void fast_caps(const vrsbs_ctx *c, int H, int *ent_cap, int *lut_cap) {
     }
     if (cells > kLutCapMax) cells = kLutCapMax;
     if (cells > 5120 && ec > 128) cells = 5120;            // keep two 4K CTAs per SM
+    // bound on the signed layer offsets for limit_step <= 32, in whole 32-pixel segments
+    const double far = fabs(c->params.offset_fg) > fabs(c->params.offset_bg) ? fabs(c->params.offset_fg) : fabs(c->params.offset_bg);
+    long long pad = ((long long)ceil(far * H * 32.0 / 14.0) + 2 + 31) / 32 * 32;
+    // (the warp kernel relies on pad <= 32 * warps per CTA: 256 threads up to W = 2048, 512 above)
+    if (pad * 4 > W || pad * 8 > 65535 || pad > 32 * (W <= 2048 ? 8 : 16)) { pad = 0; ec = 0; cells = 16; }   // slow path
+    c->key_pad = (int)pad;
     if (!c->fast_tables) { ec = 0; cells = 16; }
     *ent_cap = ec;
     *lut_cap = (cells + 15) / 16 * 16;
@@ -281,8 +288,8 @@ int launch_tables(vrsbs_ctx *c, Scratch &s, int B, int H, int W, cudaStream_t st
     a.lo16 = s.lo16; a.hi16 = s.hi16;
     a.offset_fg = c->params.offset_fg; a.offset_bg = c->params.offset_bg; a.step = c->params.offset_step_size;
     a.B = B; a.H = H; a.W = W; a.Lcap = c->max_layers;
-    fast_caps(c, H, &c->ent_cap, &c->lut_cap);
-    a.blobs = s.blobs; a.ent_cap = c->ent_cap; a.lut_cap = c->lut_cap;
+    fast_caps(c, H, W, &c->ent_cap, &c->lut_cap);
+    a.blobs = s.blobs; a.ent_cap = c->ent_cap; a.lut_cap = c->lut_cap; a.key_pad = c->key_pad;
     const size_t smem = sizeof(double) * 2 * (size_t)(c->max_layers + 2 > B ? c->max_layers + 2 : B);
     StageTimer timer(c, st, 1);
     k_build_tables<<<B, 256, smem, st>>>(a);
@@ -428,7 +435,7 @@ FusedArgs make_fused_args(vrsbs_ctx *c, Scratch &s, const uint8_t *frames, const
     a.hole_mask = s.hole_mask; a.hole_list = s.hole_list; a.hole_count = s.hole_count;
     a.B = B; a.H = H; a.W = W; a.Lcap = c->max_layers; a.Wwords = (W + 31) / 32;
     a.first = 0;
-    a.blob_bytes = blob_bytes(c->ent_cap, c->lut_cap); a.ent_bytes = blob_ent_bytes(c->ent_cap);
+    a.blob_bytes = blob_bytes(c->ent_cap, c->lut_cap); a.ent_bytes = blob_ent_bytes(c->ent_cap); a.key_pad = c->key_pad;
     a.w0 = c->sw.w_now; a.w1 = c->sw.w_prev1; a.w2 = c->sw.w_prev2;
     return a;
 }
@@ -754,7 +761,7 @@ int vrsbs_process_batch(vrsbs_ctx *c, const uint8_t *frames, const void *raw, in
     DeviceGuard g(c->device);
     cudaStream_t st = (cudaStream_t)stream;
     Scratch &s = c->scratch[0];
-    fast_caps(c, H, &c->ent_cap, &c->lut_cap);
+    fast_caps(c, H, W, &c->ent_cap, &c->lut_cap);
     if (c->fused && c->smooth_in_warp && ((size_t)H * W) % 8 == 0 && fused_capable(c, frames, raw, sbs, W))
         return launch_process_fused(c, s, frames, (const __half *)raw, B, H, W, sbs, st);
     if (!depth_scratch) return fail(c, VRSBS_E_INVALID, "depth_scratch_dev is required for this frame size / alignment");
@@ -782,7 +789,7 @@ int vrsbs_process_host(vrsbs_ctx *c, const uint8_t *frames, const void *depth, i
         if (!c->scratch[i].tabs && (rc = alloc_scratch(c, c->scratch[i]))) return rc;
         if ((rc = ensure_slot(c, c->slot[i], fb * chunk, dib * chunk, db * chunk, sb * chunk, !pin_f || !pin_d, !pin_s))) return rc;
     }
-    fast_caps(c, H, &c->ent_cap, &c->lut_cap);
+    fast_caps(c, H, W, &c->ent_cap, &c->lut_cap);
     if ((rc = check_blur_ready(c, H, W))) return rc;
     const bool use_fused = !lowres && c->fused && c->smooth_in_warp && ((size_t)H * W) % 8 == 0 &&
                            fused_capable(c, c->slot[0].dev_frames, c->slot[0].dev_depth_in, c->slot[0].dev_sbs, W);

@@ -45,6 +45,8 @@ struct FusedArgs {
     int B, H, W, Lcap, Wwords;
     int first;                 // frame 0 of the batch is the first frame of the clip range
     uint32_t blob_bytes, ent_bytes;
+    int key_pad;               // fast path: |signed offset| <= key_pad pixels (multiple of 32); only segments closer than
+                               // that to a row end can wrap
     float w0, w1, w2;          // smoothing weights (fp32 narrowing of the python doubles)
 };
 
@@ -138,6 +140,22 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_fused(FusedArgs a) {
 
     const int wofs = (3 * lane) >> 2, wsh = ((3 * lane) & 3) * 8;       // lane-constant part of the pixel fetch
 
+    // per-warp scatter schedule (row independent): this warp owns segments warp, warp + NW, ... plus, for the LAST
+    // nseg % NW warps, one left-over segment; a batch needs the wrap fix-up only if one of its segments lies within
+    // key_pad pixels of a row end
+    const int sch_full = nseg / NW, sch_rem = nseg - sch_full * NW;
+    const bool sch_extra = NW - 1 - warp < sch_rem;
+    const int sch_nw = sch_full + (sch_extra ? 1 : 0);
+    const int sch_w_last = sch_extra ? NW - 1 - warp : warp;
+    const int sch_eseg = a.key_pad >> 5;                          // segments [0, eseg) and [nseg - eseg, nseg) are edge segments
+    auto batch_edge = [&](int r0, int cnt, int wl) {
+        const int first = r0 * NW + warp, last = (r0 + cnt - 1) * NW + wl;
+        return first < sch_eseg || last >= nseg - sch_eseg;
+    };
+    const int sch_r_last = sch_nw > 4 ? 4 * ((sch_nw - 1) / 4) : 0;
+    const bool sch_wrap_first = batch_edge(0, 4, warp);
+    const bool sch_wrap_last = batch_edge(sch_r_last, sch_nw - sch_r_last, sch_w_last);
+
     int i3 = 0;                 // n % 3: image slot and mbarrier of iteration n
     uint32_t par = 0;           // (n / 3) & 1: phase parity of that mbarrier
     for (int n = 0; n < N; ++n) {
@@ -183,11 +201,12 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_fused(FusedArgs a) {
             // LUT address = sa_lut + min(bits >> shift, ncells); dd holds the fp16 bits twice, so dd >> (16 + shift)
             // = umulhi(dd, 2^(16 - shift)) folds the shift and the base add into one IMAD.HI
             const uint32_t lut_mul = 1u << (16u - hdr.shift), lut_last = sa_lut + hdr.ncells;
-            const uint32_t nW4 = 0u - W4;
+            const uint32_t sa_keys_lo = sa_keys - 4u * (uint32_t)a.key_pad;
             // U segments of 32 pixels per step, all loads of a step issued before their uses
             // w_last: warp index used for the LAST segment of the batch (differs from `warp` only for the left-over segment)
-            auto batch = [&](auto Uc, int round0, bool tail, int w_last) {
+            auto batch = [&](auto Uc, auto Wc, int round0, bool tail, int w_last) {
                 constexpr int U = decltype(Uc)::value;
+                constexpr bool WRAP = decltype(Wc)::value;        // some segment of the batch is within key_pad of a row end
                 uint32_t c[U], p1[U], p2[U], w0[U], w1[U], x4[U], ok[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -241,9 +260,19 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_fused(FusedArgs a) {
                 for (int u = 0; u < U; ++u) {
                     const uint32_t px = __funnelshift_r(w0[u], w1[u], wsh) & 0x00ffffffu;
                     const uint32_t key0 = px | (e[u] << 24);
-                    uint32_t a0 = x4[u] + (en[u].y & 0xffffu), a1 = x4[u] + (en[u].y >> 16);
-                    a0 = sa_keys + min(a0, a0 + nW4);
-                    a1 = sa_keys + min(a1, a1 + nW4);
+                    // offsets are signed (shortest way round the row) and biased by key_pad: interior segments cannot wrap
+                    const uint32_t kb = sa_keys_lo + x4[u];
+                    uint32_t a0 = kb + (en[u].y & 0xffffu), a1 = kb + (en[u].y >> 16);
+                    if (WRAP) {
+                        // relative byte offsets in [-4 pad, 4 W + 4 pad).  Only the first segment of a batch can lie at the
+                        // left end of the row (negative = huge unsigned: min(t, t + 4W) brings it back) and only the last
+                        // two at the right end (min(t, t - 4W)); key_pad <= 32 * NW guarantees that (host check).
+                        uint32_t t0 = a0 - sa_keys, t1 = a1 - sa_keys;
+                        if (u == 0) { t0 = min(t0, t0 + W4); t1 = min(t1, t1 + W4); }
+                        if (u >= U - 2) { t0 = min(t0, t0 - W4); t1 = min(t1, t1 - W4); }
+                        a0 = sa_keys + t0;
+                        a1 = sa_keys + t1;
+                    }
                     // paint layer e-1 iff d < hi(e-1); paint layer e iff !(d < lo(e)).  Non-members still issue the
                     // atomic, with key 0 (a no-op for max): cheaper than the branch ptxas wraps a predicated ATOMS in.
                     uint32_t k0, k1;
@@ -260,21 +289,22 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_fused(FusedArgs a) {
             if ((W & 31) == 0) {
                 // whole segments only: this warp owns segments warp, warp + NW, ... 4 at a time.  The nseg % NW left-over
                 // segments go to the LAST warps: warp 0 also issues the TMA traffic and warps 0.. flush the mask row.
-                const int full = nseg / NW, rem = nseg - full * NW;
-                const bool extra = NW - 1 - warp < rem;
-                const int nw = full + (extra ? 1 : 0);
+                using T = std::true_type; using F = std::false_type;
                 int r = 0;
-                for (; r + 4 < nw; r += 4) batch(std::integral_constant<int, 4>{}, r, false, warp);
-                const int w_last = extra ? NW - 1 - warp : warp;      // the final batch ends with the left-over segment
-                switch (nw - r) {                             // warp-uniform
-                    case 4: batch(std::integral_constant<int, 4>{}, r, false, w_last); break;
-                    case 3: batch(std::integral_constant<int, 3>{}, r, false, w_last); break;
-                    case 2: batch(std::integral_constant<int, 2>{}, r, false, w_last); break;
-                    case 1: batch(std::integral_constant<int, 1>{}, r, false, w_last); break;
+                for (; r + 4 < sch_nw; r += 4) {
+                    const bool ew = r == 0 ? sch_wrap_first : batch_edge(r, 4, warp);
+                    if (ew) batch(std::integral_constant<int, 4>{}, T{}, r, false, warp);
+                    else batch(std::integral_constant<int, 4>{}, F{}, r, false, warp);
+                }
+                switch (sch_nw - r) {                         // warp-uniform; the final batch ends with the left-over segment
+                    case 4: if (sch_wrap_last) batch(std::integral_constant<int, 4>{}, T{}, r, false, sch_w_last); else batch(std::integral_constant<int, 4>{}, F{}, r, false, sch_w_last); break;
+                    case 3: if (sch_wrap_last) batch(std::integral_constant<int, 3>{}, T{}, r, false, sch_w_last); else batch(std::integral_constant<int, 3>{}, F{}, r, false, sch_w_last); break;
+                    case 2: batch(std::integral_constant<int, 2>{}, T{}, r, false, sch_w_last); break;
+                    case 1: batch(std::integral_constant<int, 1>{}, T{}, r, false, sch_w_last); break;
                     default: break;
                 }
             } else {
-                for (int r = 0; r * NW + warp < nseg; ++r) batch(std::integral_constant<int, 1>{}, r, true, warp);
+                for (int r = 0; r * NW + warp < nseg; ++r) batch(std::integral_constant<int, 1>{}, std::true_type{}, r, true, warp);
             }
         } else {
             // slow path (L > 255, non-monotone bounds, LUT too coarse): brute-force membership, layer-only keys
