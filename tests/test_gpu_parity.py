@@ -441,3 +441,62 @@ def test_host_pipeline_lowres():
     # the two routes share everything but the bicubic, whose fp32 rounding may differ in 1e-3 of pixels
     assert np.mean(got == want) > 0.999
     proc.close(), proc2.close()
+
+
+def test_worker_loop_matches_per_frame_reference(oracle_lib):
+    """sbs_worker (the batched nibba_woka): every frame of every sub-clip equals the per-frame oracle, the depth
+    history / range EMA carrying across sub-clips; a failed read becomes a black frame."""
+    from vr_video_generator_b200 import worker
+    meta, frames, raw, _ = load_case("medium")
+    p = meta["params"]
+    H, W = p["H"], p["W"]
+    n = 11
+    fr = np.concatenate([frames] * 3)[:n]
+    rw = np.concatenate([raw] * 3)[:n]
+    missing = {6}
+    def read(i):
+        return None if i in missing else np.ascontiguousarray(fr[i][:, :, ::-1])     # the loop receives BGR
+    depth_of = {}
+    def depth_for(rgb):
+        out = []
+        for f in rgb:
+            k = next((i for i in range(n) if i not in missing and np.array_equal(f, fr[i])), None)
+            out.append(rw[6] if k is None else rw[k])
+        return np.stack(out)
+    got = {}
+    args = argparse.Namespace(offset_fg=p["fg"], offset_bg=p["bg"], offset_step_size=p["step"], Max_Frame_Count=4)
+    names = worker.sbs_worker(0, 10**9, read, depth_for, lambda nm, sbs: got.__setitem__(nm, sbs.copy()), args, n, H, W)
+    assert names == ["0_4.mp4", "5_8.mp4", "9_10.mp4"]
+    st = O.WarpState(p["fg"], p["bg"], p["step"])
+    w = golden_weights(meta)
+    want = []
+    for i in range(n):
+        img = np.zeros_like(fr[0]) if i in missing else fr[i]
+        want.append(oracle_lib.process_frame(st, img, rw[i], weights=w))
+    out = np.concatenate([got[nm] for nm in names])
+    assert len(out) == n
+    for i in range(n):
+        assert np.array_equal(out[i], want[i]), i
+
+
+def test_repeated_warp_batch_is_idempotent():
+    """vrsbs_warp_batch twice on the same smoothed depth / tables: same frame, the hole work list starts empty."""
+    meta, frames, raw, ref_left = load_case("small_a")
+    p = meta["params"]
+    H, W, n = p["H"], p["W"], p["n"]
+    ctx = _ctx(H, W, p["fg"], p["bg"], p["step"], golden_weights(meta))
+    f = torch.from_numpy(np.ascontiguousarray(frames)).cuda()
+    r = torch.from_numpy(np.ascontiguousarray(raw)).cuda()
+    dep = torch.empty((n, H, W), dtype=torch.float16, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    ctx.depth_from_full(r.data_ptr(), n, H, W, dep.data_ptr(), s)
+    ctx.build_tables(n, H, W, s)
+    outs = []
+    for _ in range(3):
+        out = torch.zeros((n, H, 2 * W, 3), dtype=torch.uint8, device="cuda")
+        ctx.warp_batch(f.data_ptr(), dep.data_ptr(), n, H, W, out.data_ptr(), s)
+        torch.cuda.synchronize()
+        outs.append(out.cpu().numpy())
+    assert np.array_equal(outs[0][:, :, :W], ref_left)
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    ctx.close()

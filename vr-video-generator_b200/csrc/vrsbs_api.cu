@@ -33,6 +33,7 @@ struct Scratch {                 // per-batch device scratch; one per pipeline s
     uint32_t *hole_count = nullptr;  // points into frame_max's allocation: one memset clears all three
     uint8_t *blobs = nullptr;        // [B][kBlobMax] fast-path tables
     uint8_t *plane = nullptr;        // [B,H,W,3] blurred hole values (allocated on first blur)
+    bool holes_dirty = false;        // a warp kernel has appended to hole_list since hole_count was last cleared
 };
 
 constexpr int kEntCapMax = 255, kLutCapMax = 8192;
@@ -183,6 +184,14 @@ struct StageTimer {
 int clear_counters(vrsbs_ctx *c, Scratch &s, int B, cudaStream_t st) {
     (void)B;
     CU_TRY(c, cudaMemsetAsync(s.frame_max, 0, sizeof(uint32_t) * (2 * c->max_batch + 1), st));
+    s.holes_dirty = false;
+    return VRSBS_OK;
+}
+
+// the hole work list must start empty for every warp launch (a second vrsbs_warp_batch without a depth call in between)
+int fresh_hole_list(vrsbs_ctx *c, Scratch &s, cudaStream_t st) {
+    if (s.holes_dirty) CU_TRY(c, cudaMemsetAsync(s.hole_count, 0, sizeof(uint32_t), st));
+    s.holes_dirty = true;
     return VRSBS_OK;
 }
 
@@ -445,6 +454,7 @@ int launch_warp(vrsbs_ctx *c, Scratch &s, const uint8_t *frames, const __half *d
                 cudaStream_t st) {
     int rc = check_blur_ready(c, H, W);
     if (rc) return rc;
+    if ((rc = fresh_hole_list(c, s, st))) return rc;
     if (c->fused && fused_capable(c, frames, depth, sbs, W)) {
         FusedArgs a = make_fused_args(c, s, frames, depth, B, H, W, sbs);
         rc = W <= 2048 ? launch_fused_inst<false, 256>(c, a, st) : launch_fused_inst<false, 512>(c, a, st);
@@ -471,6 +481,7 @@ int launch_process_fused(vrsbs_ctx *c, Scratch &s, const uint8_t *frames, const 
     const bool first = c->depth_frames == 0;
     if ((rc = launch_depth_max(c, s, raw, B, H, W, st))) return rc;
     if ((rc = launch_tables(c, s, B, H, W, st))) return rc;
+    if ((rc = fresh_hole_list(c, s, st))) return rc;
     FusedArgs a = make_fused_args(c, s, frames, raw, B, H, W, sbs);
     a.first = first ? 1 : 0;
     rc = W <= 2048 ? launch_fused_inst<true, 256>(c, a, st) : launch_fused_inst<true, 512>(c, a, st);
