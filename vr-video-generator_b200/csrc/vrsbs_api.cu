@@ -361,7 +361,7 @@ bool fused_capable(const vrsbs_ctx *c, const void *frames, const void *depth, co
 // hole values -> SBS frame (when blur is on) and strip restore, one kernel
 int launch_commit(vrsbs_ctx *c, const BlurArgs &b, int do_commit, cudaStream_t st) {
     StageTimer timer(c, st, 4);
-    k_blur_commit<<<(unsigned)(c->sm_count * 8), 256, 0, st>>>(b, do_commit);
+    k_blur_commit<<<(unsigned)(c->sm_count * 32), 256, 0, st>>>(b, do_commit);   // short latency-bound tasks: one or two per warp
     CU_TRY(c, cudaGetLastError());
     c->launches++;
     return VRSBS_OK;
