@@ -138,7 +138,10 @@ int  vrsbs_process_batch(vrsbs_ctx *ctx, const uint8_t *frames_dev, const void *
  * either full-res raw depth [B,H,W] fp16 (lowres_h = lowres_w = 0) or DPT low-res [B,h,w] fp16.
  * Internally pipelined: three streams (H2D / kernels / D2H) and three pinned slots; frames are
  * processed in chunks ("host_chunk", default 4) so copy-in, kernels and copy-out of neighbouring
- * chunks overlap.  Returns after sbs_host is complete (like the reference's blocking D2H). */
+ * chunks overlap.  Only the synthesised (left) half of every SBS row crosses PCIe on the way back;
+ * the right half is the caller's own frame and is copied host-to-host by the library's copy threads
+ * (option "host_right_half", default 1).  Returns after sbs_host is complete (like the reference's
+ * blocking D2H). */
 int  vrsbs_process_host(vrsbs_ctx *ctx, const uint8_t *frames_host, const void *depth_host,
                         int B, int H, int W, int lowres_h, int lowres_w, float scaler,
                         uint8_t *sbs_host);
@@ -164,7 +167,7 @@ int  vrsbs_get_stage_times(vrsbs_ctx *ctx, double ms[VRSBS_NUM_STAGES], uint64_t
 
 /* Tuning knobs: "fused" (1 = TMA warp kernel k_warp_fused when the shape allows, 0 = general row kernel),
  * "smooth_in_warp" (see vrsbs_process_batch), "fast_tables" (0 forces the slow membership path, tests), "scatter_mode" of the general row kernel (2 = atomicMax for every key, 1 = plain store +
- * verify), "bicubic_contract", "blocks_per_sm", "host_chunk", "copy_threads", "pageable_direct",
+ * verify), "bicubic_contract", "blocks_per_sm", "host_chunk", "copy_threads", "pageable_direct", "host_right_half",
  * "stage_timing". */
 int  vrsbs_set_option(vrsbs_ctx *ctx, const char *name, int value);
 

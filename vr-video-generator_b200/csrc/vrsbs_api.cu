@@ -3,7 +3,14 @@
 #include <cstdio>
 #include <cmath>
 #include <cstring>
+#if defined(__x86_64__) || defined(_M_X64)
+#include <emmintrin.h>
+#define VRSBS_HAVE_SSE2 1
+#endif
 #include <new>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -49,6 +56,106 @@ struct HostSlot {                // one chunk of host<->device staging for vrsbs
     size_t cap_pin_frames = 0, cap_pin_depth = 0, cap_pin_sbs = 0;
 };
 
+// Row copy with non-temporal stores: the destinations are large, written once and read much later (by ffmpeg or
+// the DMA engine), so bypassing the cache avoids the read-for-ownership and leaves host DRAM bandwidth to PCIe.
+inline void stream_copy(char *dst, const char *src, size_t n) {
+#ifdef VRSBS_HAVE_SSE2
+    if (n >= 256 && ((uintptr_t)dst & 15) == 0) {
+        size_t i = 0;
+        for (; i + 64 <= n; i += 64) {
+            const __m128i a = _mm_loadu_si128((const __m128i *)(src + i)), b = _mm_loadu_si128((const __m128i *)(src + i + 16));
+            const __m128i c = _mm_loadu_si128((const __m128i *)(src + i + 32)), d = _mm_loadu_si128((const __m128i *)(src + i + 48));
+            _mm_stream_si128((__m128i *)(dst + i), a);      _mm_stream_si128((__m128i *)(dst + i + 16), b);
+            _mm_stream_si128((__m128i *)(dst + i + 32), c); _mm_stream_si128((__m128i *)(dst + i + 48), d);
+        }
+        if (i < n) memcpy(dst + i, src + i, n - i);
+        return;
+    }
+#endif
+    memcpy(dst, src, n);
+}
+
+// Persistent host threads for the row copies of the host pipeline (staging of pageable buffers, and the right half
+// of the SBS frame, which is the caller's own input and never needs to cross PCIe).
+class CopyPool {
+public:
+    explicit CopyPool(int nthreads) {
+        for (int i = 0; i < nthreads; ++i) workers_.emplace_back([this] { run(); });
+    }
+    ~CopyPool() {
+        { std::lock_guard<std::mutex> g(m_); stop_ = true; }
+        cv_.notify_all();
+        for (auto &t : workers_) t.join();
+    }
+    int threads() const { return (int)workers_.size(); }
+    // rows x width bytes from src (pitch spitch) to dst (pitch dpitch); returns a ticket for wait()
+    int submit(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows) {
+        if (rows == 0 || width == 0) return -1;
+        size_t tail;
+        if (dpitch == width && spitch == width) {               // contiguous: re-shape into 256 KiB pieces
+            const size_t total = width * rows, piece = 256u << 10;
+            width = total < piece ? total : piece;
+            rows = (total + width - 1) / width;
+            tail = total - (rows - 1) * width;
+            dpitch = spitch = width;
+        } else {
+            tail = width;
+        }
+        const size_t parts = rows < (size_t)workers_.size() * 2 ? rows : (size_t)workers_.size() * 2;
+        std::lock_guard<std::mutex> g(m_);
+        const int ticket = next_ticket_++;
+        pending_.push_back({ticket, (int)parts});
+        for (size_t p = 0; p < parts; ++p) {
+            const size_t r0 = rows * p / parts, r1 = rows * (p + 1) / parts;
+            jobs_.push_back({ticket, (char *)dst + r0 * dpitch, (const char *)src + r0 * spitch, dpitch, spitch, width, r1 - r0,
+                             (r1 == rows) ? tail : width});
+        }
+        cv_.notify_all();
+        return ticket;
+    }
+    void wait(int ticket) {
+        if (ticket < 0) return;
+        std::unique_lock<std::mutex> g(m_);
+        done_cv_.wait(g, [&] {
+            for (auto &p : pending_) if (p.ticket == ticket) return false;
+            return true;
+        });
+    }
+private:
+    struct Job { int ticket; char *dst; const char *src; size_t dpitch, spitch, width, rows, last_width; };
+    struct Pending { int ticket, left; };
+    void run() {
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> g(m_);
+                cv_.wait(g, [&] { return stop_ || !jobs_.empty(); });
+                if (jobs_.empty()) return;
+                j = jobs_.front();
+                jobs_.pop_front();
+            }
+            for (size_t r = 0; r < j.rows; ++r)
+                stream_copy(j.dst + r * j.dpitch, j.src + r * j.spitch, r + 1 == j.rows ? j.last_width : j.width);
+#ifdef VRSBS_HAVE_SSE2
+            _mm_sfence();
+#endif
+            {
+                std::lock_guard<std::mutex> g(m_);
+                for (size_t i = 0; i < pending_.size(); ++i)
+                    if (pending_[i].ticket == j.ticket && --pending_[i].left == 0) { pending_.erase(pending_.begin() + i); break; }
+            }
+            done_cv_.notify_all();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::deque<Job> jobs_;
+    std::vector<Pending> pending_;
+    std::mutex m_;
+    std::condition_variable cv_, done_cv_;
+    int next_ticket_ = 0;
+    bool stop_ = false;
+};
+
 }  // namespace
 
 struct vrsbs_ctx {
@@ -81,6 +188,8 @@ struct vrsbs_ctx {
     int host_chunk = 4;
     int copy_threads = 8;
     int pageable_direct = 0;             // option: 1 = hand pageable host pointers to cudaMemcpyAsync instead of staging them
+    int host_right_half = 1;             // option: 1 = the right half of the SBS frame (= the caller's input) is copied on the host
+    CopyPool *pool = nullptr;            // created on first use by vrsbs_process_host
     // options / accounting
     int scatter_mode = 2;
     int bicubic_contract = 1;
@@ -631,6 +740,7 @@ int vrsbs_destroy(vrsbs_ctx *c) {
     cudaFree(c->state); cudaFree(c->weights); cudaFree(c->wq);
     for (int i = 0; i < kSlots; ++i) { free_scratch(c->scratch[i]); free_slot(c->slot[i]); }
     if (c->st_in) { cudaStreamDestroy(c->st_in); cudaStreamDestroy(c->st_k); cudaStreamDestroy(c->st_out); }
+    delete c->pool;
     for (auto &s : c->stamps) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (auto e : c->event_pool) cudaEventDestroy(e);
     delete c;
@@ -794,45 +904,79 @@ int vrsbs_process_host(vrsbs_ctx *c, const uint8_t *frames, const void *depth, i
     if (chunk < 1) chunk = 1;
     const size_t fb = (size_t)H * W * 3, sb = fb * 2, db = (size_t)H * W * 2;
     const size_t dib = lowres ? (size_t)lh * lw * 2 : db;
+    const size_t row3 = (size_t)W * 3;
     const bool direct = c->pageable_direct != 0;
     const bool pin_f = direct || is_pinned(frames), pin_d = direct || is_pinned(depth), pin_s = direct || is_pinned(sbs);
+    // the right half of every SBS row is the caller's own input row: copy it host to host and move only the
+    // synthesised half across PCIe (halves the D2H traffic, which is the longer leg)
+    const bool host_right = c->host_right_half != 0;
     for (int i = 0; i < kSlots; ++i) {
         if (!c->scratch[i].tabs && (rc = alloc_scratch(c, c->scratch[i]))) return rc;
         if ((rc = ensure_slot(c, c->slot[i], fb * chunk, dib * chunk, db * chunk, sb * chunk, !pin_f || !pin_d, !pin_s))) return rc;
     }
+    const bool need_pool = !pin_f || !pin_d || !pin_s || host_right;
+    if (!c->pool && need_pool) c->pool = new (std::nothrow) CopyPool(c->copy_threads);
+    if (need_pool && !c->pool) return fail(c, VRSBS_E_NOMEM, "cannot start the host copy threads");
+    CopyPool *pool = c->pool;
     fast_caps(c, H, W, &c->ent_cap, &c->lut_cap);
     if ((rc = check_blur_ready(c, H, W))) return rc;
     const bool use_fused = !lowres && c->fused && c->smooth_in_warp && ((size_t)H * W) % 8 == 0 &&
                            fused_capable(c, c->slot[0].dev_frames, c->slot[0].dev_depth_in, c->slot[0].dev_sbs, W);
 
     // Three streams: st_in copies chunk i+1 in while st_k runs the kernels of chunk i and st_out copies chunk i-1
-    // out.  All kernels run on st_k in clip order, so the clip-range state needs no extra synchronisation.
+    // out.  All kernels run on st_k in clip order, so the clip-range state needs no extra synchronisation.  Host
+    // copies (staging of pageable buffers, right halves) run on the copy pool and are waited for by ticket.
     const int nchunks = (B + chunk - 1) / chunk;
     int pending_n[kSlots] = {0}, pending_first[kSlots] = {0};
+    int tk_in[kSlots], tk_in2[kSlots], tk_out[kSlots], tk_right[kSlots];
+    for (int i = 0; i < kSlots; ++i) tk_in[i] = tk_in2[i] = tk_out[i] = tk_right[i] = -1;
+    auto count_of = [&](int ci) { const int first = ci * chunk; return (B - first < chunk) ? B - first : chunk; };
+    auto stage_in = [&](int ci) {                      // pageable inputs of chunk ci -> the slot's pinned buffers (async)
+        const int si = ci % kSlots, first = ci * chunk, n = count_of(ci);
+        HostSlot &s = c->slot[si];
+        if (pin_f && pin_d) return;
+        cudaEventSynchronize(s.in_done);               // the slot's previous H2D has left the pinned buffers (no-op if never recorded)
+        if (!pin_f) tk_in[si] = pool->submit(s.pin_frames, fb * n, frames + (size_t)first * fb, fb * n, fb * n, 1);
+        if (!pin_d) tk_in2[si] = pool->submit(s.pin_depth, dib * n, (const uint8_t *)depth + (size_t)first * dib, dib * n, dib * n, 1);
+    };
     auto drain = [&](int si) -> int {     // wait for slot si's chunk, deliver its output, check its status
         HostSlot &s = c->slot[si];
         if (!pending_n[si]) return VRSBS_OK;
         CU_TRY(c, cudaEventSynchronize(s.out_done));
         const int n = pending_n[si], first = pending_first[si];
-        if (!pin_s) parallel_memcpy(sbs + (size_t)first * sb, s.pin_sbs, sb * n, c->copy_threads);
+        if (!pin_s) {
+            uint8_t *dst = sbs + (size_t)first * sb;
+            if (host_right) tk_out[si] = pool->submit(dst, 2 * row3, s.pin_sbs, row3, row3, (size_t)n * H);   // compact left halves
+            else tk_out[si] = pool->submit(dst, sb * n, s.pin_sbs, sb * n, sb * n, 1);
+        }
         pending_n[si] = 0;
         return frame_status_error(c, s.pin_tabs, n, first);
     };
     auto drain_all = [&](int rc_in) -> int {          // never leave work in flight behind an error return
         for (int i = 0; i < kSlots; ++i) { int r = drain(i); if (!rc_in) rc_in = r; }
+        if (pool) for (int i = 0; i < kSlots; ++i) { pool->wait(tk_in[i]); pool->wait(tk_in2[i]); pool->wait(tk_out[i]); pool->wait(tk_right[i]); }
         return rc_in;
     };
+    stage_in(0);
     for (int ci = 0; ci < nchunks; ++ci) {
-        const int si = ci % kSlots, first = ci * chunk, n = (B - first < chunk) ? B - first : chunk;
+        const int si = ci % kSlots, first = ci * chunk, n = count_of(ci);
         HostSlot &s = c->slot[si];
-        if ((rc = drain(si))) return drain_all(rc);
+        if ((rc = drain(si))) return drain_all(rc);            // frees the slot's device + pinned output buffers
+        if (ci + 1 < nchunks) {
+            // pageable output: hand finished chunks to the copy pool as early as possible
+            if (!pin_s && (rc = drain((ci + 1) % kSlots))) return drain_all(rc);
+            stage_in(ci + 1);                                   // overlaps with this chunk's enqueue and the GPU
+        }
         const uint8_t *hf = frames + (size_t)first * fb;
         const uint8_t *hd = (const uint8_t *)depth + (size_t)first * dib;
-        if (!pin_f) { parallel_memcpy(s.pin_frames, hf, fb * n, c->copy_threads); hf = s.pin_frames; }
-        if (!pin_d) { parallel_memcpy(s.pin_depth, hd, dib * n, c->copy_threads); hd = s.pin_depth; }
+        if (pool) { pool->wait(tk_in[si]); pool->wait(tk_in2[si]); }
+        if (!pin_f) hf = s.pin_frames;
+        if (!pin_d) hd = s.pin_depth;
         CU_TRY(c, cudaMemcpyAsync(s.dev_frames, hf, fb * n, cudaMemcpyHostToDevice, c->st_in));
         CU_TRY(c, cudaMemcpyAsync(s.dev_depth_in, hd, dib * n, cudaMemcpyHostToDevice, c->st_in));
         CU_TRY(c, cudaEventRecord(s.in_done, c->st_in));
+        if (host_right && c->host_right_half != 2)               // right halves: caller's frames -> caller's output, on the pool
+            { pool->wait(tk_right[si]); tk_right[si] = pool->submit(sbs + (size_t)first * sb + row3, 2 * row3, frames + (size_t)first * fb, row3, row3, (size_t)n * H); }
         CU_TRY(c, cudaStreamWaitEvent(c->st_k, s.in_done, 0));
         Scratch &sc = c->scratch[si];
         if (use_fused) {
@@ -847,15 +991,19 @@ int vrsbs_process_host(vrsbs_ctx *c, const uint8_t *frames, const void *depth, i
         CU_TRY(c, cudaMemcpyAsync(s.pin_tabs, sc.tabs, sizeof(FrameTab) * n, cudaMemcpyDeviceToHost, c->st_k));
         CU_TRY(c, cudaEventRecord(s.k_done, c->st_k));
         CU_TRY(c, cudaStreamWaitEvent(c->st_out, s.k_done, 0));
-        uint8_t *ho = pin_s ? sbs + (size_t)first * sb : s.pin_sbs;
-        CU_TRY(c, cudaMemcpyAsync(ho, s.dev_sbs, sb * n, cudaMemcpyDeviceToHost, c->st_out));
+        if (pool) pool->wait(tk_out[si]);                        // the slot's pinned output has been delivered
+        if (host_right) {
+            // left halves only: [n*H rows] x W*3 bytes out of rows of 2*W*3
+            if (pin_s) CU_TRY(c, cudaMemcpy2DAsync(sbs + (size_t)first * sb, 2 * row3, s.dev_sbs, 2 * row3, row3, (size_t)n * H, cudaMemcpyDeviceToHost, c->st_out));
+            else CU_TRY(c, cudaMemcpy2DAsync(s.pin_sbs, row3, s.dev_sbs, 2 * row3, row3, (size_t)n * H, cudaMemcpyDeviceToHost, c->st_out));
+        } else {
+            uint8_t *ho = pin_s ? sbs + (size_t)first * sb : s.pin_sbs;
+            CU_TRY(c, cudaMemcpyAsync(ho, s.dev_sbs, sb * n, cudaMemcpyDeviceToHost, c->st_out));
+        }
         CU_TRY(c, cudaEventRecord(s.out_done, c->st_out));
         pending_n[si] = n; pending_first[si] = first;
     }
-    // drain in submission order
-    for (int k = 0; k < kSlots; ++k)
-        if ((rc = drain((nchunks + k) % kSlots))) return drain_all(rc);
-    return VRSBS_OK;
+    return drain_all(VRSBS_OK);
 }
 
 int vrsbs_get_frame_info(vrsbs_ctx *c, int B, vrsbs_frame_info *info, void *stream) {
@@ -929,6 +1077,7 @@ int vrsbs_set_option(vrsbs_ctx *c, const char *name, int value) {
     else if (!strcmp(name, "stage_timing")) c->stage_timing = value != 0;
     else if (!strcmp(name, "copy_threads")) c->copy_threads = value < 1 ? 1 : value;
     else if (!strcmp(name, "pageable_direct")) c->pageable_direct = value != 0;
+    else if (!strcmp(name, "host_right_half")) c->host_right_half = value;   // 2 (experiments): left half only, right half not delivered
     else if (!strcmp(name, "fused")) c->fused = value != 0;
     else if (!strcmp(name, "fast_tables")) c->fast_tables = value != 0;
     else if (!strcmp(name, "smooth_in_warp")) c->smooth_in_warp = value != 0;
