@@ -5,7 +5,8 @@ timeout -k 10 1200 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovid
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -4 gpurun_out/pytest_gpu.log
 for wl in 1080p_b64 4k_wide_b16 1080p_stress_b64 1080p_step2_b64; do
-timeout -k 10 600 python bench.py --steps 10 --warmup 3 --workload $wl --no-cpu-baseline > gpurun_out/bench_$wl.json 2> gpurun_out/bench_$wl.err
+[ "$wl" = 1080p_step2_b64 ] && EXTRA="--depth-input lowres" || EXTRA=""
+timeout -k 10 600 python bench.py --steps 10 --warmup 3 --workload $wl $EXTRA --no-cpu-baseline > gpurun_out/bench_$wl.json 2> gpurun_out/bench_$wl.err
 python - gpurun_out/bench_$wl.json <<'PY'
 import json,sys
 try:

@@ -323,4 +323,199 @@ __global__ void __launch_bounds__(256) k_depth_lowres(DepthArgs a) {
     }
 }
 
+// ---- low-res DPT output in, tiled: horizontal interpolations shared by the output rows that use them --------
+// Same arithmetic as k_depth_lowres (ATen's: four row interpolations, then one column interpolation, every
+// mul/add in the same order), but a CTA owns a 64 x 16 output tile and first computes the row interpolation
+// R[iy][x] once per (input row, output column) into shared memory: upscaling by ~2.1 means each R is used by ~8
+// output rows, so the 16 gathers + 16 FMAs per output pixel shrink to ~3 + 4 LDS + 8.  One thread owns 2 x 2
+// output pixels (two adjacent columns, rows ty and ty + 8) for all frames of the batch, history in registers.
+constexpr int kLrTileW = 64, kLrTileH = 16;
+
+template <bool CONTRACT, bool INTERIOR>
+__device__ __forceinline__ void depth_lowres_tile(const DepthArgs &a, int rmax, int cmax, uint8_t *lr_smem) {
+    float *R = reinterpret_cast<float *>(lr_smem);                          // [rmax][64] row interpolations
+    float *Tin = R + rmax * kLrTileW;                                       // [2][rmax][cmax] staged input tile (as fp32)
+    uint32_t *s_key = reinterpret_cast<uint32_t *>(Tin + 2 * rmax * cmax);  // [B] 17-bit max keys (h16_key)
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tx0 = blockIdx.x * kLrTileW, x0 = tx0 + 2 * lane, ty0 = blockIdx.y * kLrTileH;
+    const size_t n = (size_t)a.H * a.W;
+
+    // input region of this tile: rows [rbase, rbase + nrows), columns [cbase, cbase + ncols)
+    const int xlast = min(tx0 + kLrTileW - 1, a.W - 1), ylast = min(ty0 + kLrTileH - 1, a.H - 1);
+    const int cbase = max(min((int)floorf(__fmul_rn(a.scale_x, (float)tx0)) - 1, a.w - 1), 0);
+    const int cend = max(min((int)floorf(__fmul_rn(a.scale_x, (float)xlast)) + 2, a.w - 1), 0);
+    const int rbase = max(min((int)floorf(__fmul_rn(a.scale_y, (float)ty0)) - 1, a.h - 1), 0);
+    const int rend = max(min((int)floorf(__fmul_rn(a.scale_y, (float)ylast)) + 2, a.h - 1), 0);
+    const int nrows = rend - rbase + 1, ncols = cend - cbase + 1;          // <= rmax, cmax (host)
+
+    // columns x0, x0+1: coefficients and tap columns relative to cbase (INTERIOR: taps are ix[c][0] + k)
+    float cx[2][4];
+    int ix[2][INTERIOR ? 1 : 4];
+    bool xin[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const int x = x0 + c;
+        xin[c] = x < a.W;
+        const float rx = __fmul_rn(a.scale_x, (float)min(x, a.W - 1));
+        const int fx = (int)floorf(rx);
+        Cubic<CONTRACT>::coeffs(rx - (float)fx, cx[c]);
+#pragma unroll
+        for (int k = 0; k < (INTERIOR ? 1 : 4); ++k) ix[c][k] = max(min(fx - 1 + k, a.w - 1), 0) - cbase;
+    }
+    // rows ty0 + warp, ty0 + warp + 8: coefficients and R offsets (INTERIOR: iy[j][0] + 64 k)
+    float cy[2][4];
+    int iy[2][INTERIOR ? 1 : 4];
+    bool yin[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int y = ty0 + warp + 8 * j;
+        yin[j] = y < a.H;
+        const float ry = __fmul_rn(a.scale_y, (float)min(y, a.H - 1));
+        const int fy = (int)floorf(ry);
+        Cubic<CONTRACT>::coeffs(ry - (float)fy, cy[j]);
+#pragma unroll
+        for (int k = 0; k < (INTERIOR ? 1 : 4); ++k) iy[j][k] = (max(min(fy - 1 + k, a.h - 1), 0) - rbase) * kLrTileW + 2 * lane;
+    }
+    // my (at most two) elements of the input tile
+    int e_src[2], e_dst[2];
+    bool e_on[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int e = threadIdx.x + 256 * q;
+        e_on[q] = e < nrows * ncols;
+        const int r = e_on[q] ? e / ncols : 0, col = e_on[q] ? e - r * ncols : 0;
+        e_src[q] = (rbase + r) * a.w + cbase + col;
+        e_dst[q] = r * cmax + col;
+    }
+    const bool pair_ok = xin[0] && xin[1];
+    auto pix = [&](int j) { return (size_t)(ty0 + warp + 8 * j) * a.W + x0; };
+    auto ld2 = [&](const __half *p, size_t i) -> float2 {
+        if (pair_ok) return __half22float2(*reinterpret_cast<const __half2 *>(p + i));
+        return make_float2(__half2float(p[i]), 0.f);
+    };
+    auto st2 = [&](__half *p, size_t i, __half2 v) {
+        if (pair_ok) *reinterpret_cast<__half2 *>(p + i) = v;
+        else p[i] = __low2half(v);
+    };
+    // raw depth of t-1 / t-2 at my 2 x 2 pixels, as floats (exact fp16 values)
+    float2 p1[2], p2[2];
+    p1[0] = p1[1] = p2[0] = p2[1] = make_float2(0.f, 0.f);
+    const bool on[2] = {yin[0] && xin[0], yin[1] && xin[0]};
+    if (!a.first) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+            if (on[j]) { p1[j] = ld2(a.hist1, pix(j)); p2[j] = ld2(a.hist2, pix(j)); }
+    }
+    const float w0 = a.sw.w_now, w1 = a.sw.w_prev1, w2 = a.sw.w_prev2;
+    const bool scale = a.scaler != 1.0f;
+    bool init = a.first != 0;
+    __half *outp[2] = {a.out + pix(0), a.out + pix(1)};
+
+    __half nxt[2];                                                          // tile of frame t, loaded one frame ahead
+#pragma unroll
+    for (int q = 0; q < 2; ++q) nxt[q] = e_on[q] ? __ldg(a.lowres + e_src[q]) : __float2half(0.f);
+    const __half *src = a.lowres;
+
+    for (int t = 0; t < a.B; ++t) {
+        float *Tb = Tin + (t & 1) * rmax * cmax;
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+            if (e_on[q]) Tb[e_dst[q]] = h2f(nxt[q]);
+        src += (size_t)a.h * a.w;
+        if (t + 1 < a.B) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+                if (e_on[q]) nxt[q] = __ldg(src + e_src[q]);
+        }
+        __syncthreads();
+        // phase A: row interpolations of the tile's input rows at my two columns
+        for (int r = warp; r < nrows; r += 8) {
+            const float *row = Tb + r * cmax;
+            float2 v;
+            if (INTERIOR) {
+                const float *q0 = row + ix[0][0], *q1 = row + ix[1][0];
+                v.x = Cubic<CONTRACT>::dot4(q0[0], q0[1], q0[2], q0[3], cx[0]);
+                v.y = Cubic<CONTRACT>::dot4(q1[0], q1[1], q1[2], q1[3], cx[1]);
+            } else {
+                v.x = Cubic<CONTRACT>::dot4(row[ix[0][0]], row[ix[0][INTERIOR ? 0 : 1]], row[ix[0][INTERIOR ? 0 : 2]], row[ix[0][INTERIOR ? 0 : 3]], cx[0]);
+                v.y = Cubic<CONTRACT>::dot4(row[ix[1][0]], row[ix[1][INTERIOR ? 0 : 1]], row[ix[1][INTERIOR ? 0 : 2]], row[ix[1][INTERIOR ? 0 : 3]], cx[1]);
+            }
+            *reinterpret_cast<float2 *>(R + r * kLrTileW + 2 * lane) = v;
+        }
+        __syncthreads();
+        // phase B: column interpolation, scaler, smoothing, max, store
+        __half2 res[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            float2 r0, r1, r2, r3;
+            if (INTERIOR) {
+                const float *q = R + iy[j][0];
+                r0 = *reinterpret_cast<const float2 *>(q);                  r1 = *reinterpret_cast<const float2 *>(q + kLrTileW);
+                r2 = *reinterpret_cast<const float2 *>(q + 2 * kLrTileW);   r3 = *reinterpret_cast<const float2 *>(q + 3 * kLrTileW);
+            } else {
+                r0 = *reinterpret_cast<const float2 *>(R + iy[j][0]);                  r1 = *reinterpret_cast<const float2 *>(R + iy[j][INTERIOR ? 0 : 1]);
+                r2 = *reinterpret_cast<const float2 *>(R + iy[j][INTERIOR ? 0 : 2]);   r3 = *reinterpret_cast<const float2 *>(R + iy[j][INTERIOR ? 0 : 3]);
+            }
+            __half2 curh = __floats2half2_rn(Cubic<CONTRACT>::dot4(r0.x, r1.x, r2.x, r3.x, cy[j]), Cubic<CONTRACT>::dot4(r0.y, r1.y, r2.y, r3.y, cy[j]));
+            float2 cur = __half22float2(curh);
+            if (scale) {                                                    // `* scaler` in fp16 (PredictAndGenerate.py:55)
+                curh = __floats2half2_rn(__fmul_rn(cur.x, a.scaler), __fmul_rn(cur.y, a.scaler));
+                cur = __half22float2(curh);
+            }
+            if (init) { p1[j] = cur; p2[j] = cur; }
+            __half2 d = __hadd2(__floats2half2_rn(__fmul_rn(cur.x, w0), __fmul_rn(cur.y, w0)),
+                                __floats2half2_rn(__fmul_rn(p1[j].x, w1), __fmul_rn(p1[j].y, w1)));
+            d = __hadd2(d, __floats2half2_rn(__fmul_rn(p2[j].x, w2), __fmul_rn(p2[j].y, w2)));
+            res[j] = d;
+            if (on[j]) st2(outp[j], 0, d);
+            outp[j] += n;
+            p2[j] = p1[j];
+            p1[j] = cur;
+        }
+        init = false;
+        // per-frame max of my pixels as an order-preserving 17-bit key (NaN on top)
+        uint32_t key = 0;
+        {
+            if (!pair_ok) { res[0] = __low2half2(res[0]); res[1] = __low2half2(res[1]); }
+            __half2 m = on[0] ? res[0] : res[1];
+            if (on[0] && on[1]) m = __hmax2_nan(res[0], res[1]);
+            m = __hmax2_nan(m, __lowhigh2highlow(m));
+            if (on[0] || on[1]) key = h16_key((uint32_t)__half_as_ushort(__low2half(m)));
+        }
+        key = __reduce_max_sync(0xffffffffu, key);
+        if (lane == 0 && key) atomicMax(&s_key[t], key);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+        if (on[j]) {
+            st2(a.hist1, pix(j), __floats2half2_rn(p1[j].x, p1[j].y));
+            st2(a.hist2, pix(j), __floats2half2_rn(p2[j].x, p2[j].y));
+        }
+}
+
+template <bool CONTRACT>
+__global__ void __launch_bounds__(256, 3) k_depth_lowres_tiled(DepthArgs a, int rmax, int cmax) {
+    extern __shared__ __align__(16) uint8_t lr_smem[];
+    uint32_t *s_key = reinterpret_cast<uint32_t *>(reinterpret_cast<float *>(lr_smem) + rmax * kLrTileW + 2 * rmax * cmax);
+    for (int i = threadIdx.x; i < a.B; i += blockDim.x) s_key[i] = 0;
+    __syncthreads();
+    // a tile is interior when none of its taps is clamped at the image border: the four taps are then consecutive
+    const int tx0 = blockIdx.x * kLrTileW, ty0 = blockIdx.y * kLrTileH;
+    const int xlast = min(tx0 + kLrTileW - 1, a.W - 1), ylast = min(ty0 + kLrTileH - 1, a.H - 1);
+    const bool interior = (int)floorf(__fmul_rn(a.scale_x, (float)tx0)) >= 1 && (int)floorf(__fmul_rn(a.scale_x, (float)xlast)) + 2 <= a.w - 1 &&
+                          (int)floorf(__fmul_rn(a.scale_y, (float)ty0)) >= 1 && (int)floorf(__fmul_rn(a.scale_y, (float)ylast)) + 2 <= a.h - 1;
+    if (interior) depth_lowres_tile<CONTRACT, true>(a, rmax, cmax, lr_smem);
+    else depth_lowres_tile<CONTRACT, false>(a, rmax, cmax, lr_smem);
+    __syncthreads();
+    for (int t = threadIdx.x; t < a.B; t += blockDim.x) {
+        const uint32_t key = s_key[t];
+        if (key == 0x1ffffu) atomicOr(&a.frame_nan[t], 1u);
+        else if (key) {
+            const uint32_t u = (key & 0x8000u) ? (key & 0x7fffu) : (~key & 0xffffu);
+            atomicMax(&a.frame_max[t], f2ord(__half2float(__ushort_as_half((unsigned short)u))));
+        }
+    }
+}
+
 }  // namespace vrsbs

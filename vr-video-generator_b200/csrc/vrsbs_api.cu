@@ -181,6 +181,7 @@ struct vrsbs_ctx {
     int key_pad = 0;                     // fast path: bound on |signed layer offset| in pixels (multiple of 32)
     int fused = 1;                       // option: use the fused route in vrsbs_process_batch when possible
     int fast_tables = 1;                 // option (tests): 0 forces the slow membership path of k_warp_fused
+    int lowres_tiled = 1;                // option: 0 = one-pixel-per-thread bicubic kernel (tests)
     int smooth_in_warp = 0;              // option: 1 = smoothing recomputed inside the warp kernel (no smoothed depth in HBM);
                                          // measured slower than materialising it, so off by default
     // host pipeline
@@ -338,9 +339,19 @@ int launch_depth(vrsbs_ctx *c, Scratch &s, const __half *raw, const __half *lowr
             k_depth_full<1><<<(unsigned)((n + 255) / 256), 256, smem, st>>>(a);
         }
     } else {
-        dim3 grid((W + 31) / 32, (H + 7) / 8);
-        if (c->bicubic_contract) k_depth_lowres<true><<<grid, 256, smem, st>>>(a);
-        else k_depth_lowres<false><<<grid, 256, smem, st>>>(a);
+        // tiled kernel: input rows a 16-row output tile can touch; very strong downscaling keeps the simple kernel
+        const int rmax = (int)ceilf(a.scale_y * (kLrTileH - 1)) + 5, cmax = (int)ceilf(a.scale_x * (kLrTileW - 1)) + 5;
+        const bool tiled = c->lowres_tiled && rmax * cmax <= 512 && (W % 2 == 0) && ((uintptr_t)out % 4 == 0);
+        if (tiled) {
+            dim3 grid((W + kLrTileW - 1) / kLrTileW, (H + kLrTileH - 1) / kLrTileH);
+            const size_t tsmem = sizeof(float) * ((size_t)rmax * kLrTileW + 2 * (size_t)rmax * cmax) + smem;
+            if (c->bicubic_contract) k_depth_lowres_tiled<true><<<grid, 256, tsmem, st>>>(a, rmax, cmax);
+            else k_depth_lowres_tiled<false><<<grid, 256, tsmem, st>>>(a, rmax, cmax);
+        } else {
+            dim3 grid((W + 31) / 32, (H + 7) / 8);
+            if (c->bicubic_contract) k_depth_lowres<true><<<grid, 256, smem, st>>>(a);
+            else k_depth_lowres<false><<<grid, 256, smem, st>>>(a);
+        }
     }
     CU_TRY(c, cudaGetLastError());
     c->launches++;
@@ -1081,6 +1092,7 @@ int vrsbs_set_option(vrsbs_ctx *c, const char *name, int value) {
     else if (!strcmp(name, "fused")) c->fused = value != 0;
     else if (!strcmp(name, "fast_tables")) c->fast_tables = value != 0;
     else if (!strcmp(name, "smooth_in_warp")) c->smooth_in_warp = value != 0;
+    else if (!strcmp(name, "lowres_tiled")) c->lowres_tiled = value != 0;
     else return fail(c, VRSBS_E_INVALID, "unknown option %s", name);
     return VRSBS_OK;
 }
