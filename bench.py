@@ -289,7 +289,7 @@ def run_ours(args, wl, name):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8 pixels / fp16 depth compares / f64 table+blur accumulate", "data": "synthetic",
+            "dtype": "u8 pixels / fp16 depth compares / integer-exact blur / f64 layer tables", "data": "synthetic",
             "config": {"workload": f"{name}: {W}x{H}, {B}-frame batch per GPU, fg={wl['fg']} bg={wl['bg']} step={wl['step']}, "
                                    f"D-{wl['depth']} depth (limit_step {infos[0].limit_step}, {infos[0].layers} layers, "
                                    f"{100.0 * infos[0].holes / (H * W):.2f}% holes)",
