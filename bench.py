@@ -208,6 +208,11 @@ def run_ours(args, wl, name):
     proc = pkg.SbsProcessor(None, 0, ns, device=dev, max_batch=16)
     if args.host_chunk:
         proc._context(H, W).set_option("host_chunk", args.host_chunk)
+    # the host copy threads of all ranks share the box's cores
+    proc._context(H, W).set_option("copy_threads", max(2, min(8, (os.cpu_count() or 8) // world)))
+    for kv in args.host_opt:
+        k, v = kv.split("=")
+        proc._context(H, W).set_option(k, int(v))
     f_pin = torch.from_numpy(frames_h).pin_memory()
     d_pin = torch.from_numpy(raw_h).pin_memory()
     o_pin = torch.empty((B, H, 2 * W, 3), dtype=torch.uint8).pin_memory()
@@ -396,6 +401,7 @@ def main():
     ap.add_argument("--host-chunk", type=int, default=0)
     ap.add_argument("--video-frames", type=int, default=0,
                     help="also stream an N-frame synthetic video (e.g. 18000 = 10 min of 1080p30), sharded by clip range over the ranks")
+    ap.add_argument("--host-opt", action="append", default=[], help="library option name=value for the host-API context")
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (vrsbs_set_option)")
     ap.add_argument("--pageable", action="store_true", help="also time the host API with pageable numpy buffers")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
