@@ -566,6 +566,10 @@ FusedArgs make_fused_args(vrsbs_ctx *c, Scratch &s, const uint8_t *frames, const
     a.first = 0;
     a.blob_bytes = blob_bytes(c->ent_cap, c->lut_cap); a.ent_bytes = blob_ent_bytes(c->ent_cap); a.key_pad = c->key_pad;
     a.w0 = c->sw.w_now; a.w1 = c->sw.w_prev1; a.w2 = c->sw.w_prev2;
+    const FusedSmem L = fused_smem_layout(W, a.blob_bytes);
+    a.lay.img = (uint32_t)L.img; a.lay.img_stride = (uint32_t)L.img_stride; a.lay.dep = (uint32_t)L.dep; a.lay.dep_stride = (uint32_t)L.dep_stride;
+    a.lay.out = (uint32_t)L.out; a.lay.keys = (uint32_t)L.keys; a.lay.blob = (uint32_t)L.blob; a.lay.blob_stride = (uint32_t)L.blob_stride;
+    a.lay.mask = (uint32_t)L.mask; a.lay.bars = (uint32_t)L.bars;
     return a;
 }
 

@@ -29,6 +29,11 @@
 
 namespace vrsbs {
 
+// shared-memory layout as 32-bit kernel parameters (constant bank: no per-row re-derivation); see fused_smem_layout
+struct FusedLay {
+    uint32_t img, img_stride, dep, dep_stride, out, keys, blob, blob_stride, mask, bars;
+};
+
 struct FusedArgs {
     const uint8_t *frames;     // [B,H,W,3]
     const __half *depth;       // [B,H,W] RAW depth (SMOOTH) or already smoothed depth (!SMOOTH)
@@ -48,11 +53,13 @@ struct FusedArgs {
     int key_pad;               // fast path: |signed offset| <= key_pad pixels (multiple of 32); only segments closer than
                                // that to a row end can wrap
     float w0, w1, w2;          // smoothing weights (fp32 narrowing of the python doubles)
+    FusedLay lay;              // shared-memory layout, filled on the host from fused_smem_layout()
 };
 
 struct FusedSmem {
     size_t img, img_stride, dep, dep_stride, out, keys, blob, blob_stride, mask, bars, total;
 };
+
 constexpr int kImgSlots = 3, kDepSlots = 4, kBlobSlots = 2, kBars = 3;
 
 __host__ __device__ inline FusedSmem fused_smem_layout(int W, uint32_t blob_b) {
@@ -79,11 +86,9 @@ __device__ __forceinline__ uint32_t fetch_rgb(const uint8_t *row, int x) {
 template <bool SMOOTH, int NT>
 __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_fused(FusedArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const FusedSmem lay = fused_smem_layout(a.W, a.blob_bytes);
-    uint32_t *keys = reinterpret_cast<uint32_t *>(smem + lay.keys);
-    uint8_t *out_row = smem + lay.out;
-    uint32_t *s_mask = reinterpret_cast<uint32_t *>(smem + lay.mask);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + lay.bars);
+    const uint32_t sb = smem_u32(smem);                              // every shared access below is sb + constant-bank offset
+    const uint32_t sa_keys = sb + a.lay.keys, sa_out = sb + a.lay.out, sa_mask = sb + a.lay.mask, sa_bars = sb + a.lay.bars;
+    uint32_t *keys = reinterpret_cast<uint32_t *>(smem + a.lay.keys);   // generic pointer: slow path only
 
     constexpr int NW = NT / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -97,12 +102,11 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_fused(FusedArgs a) {
     if (N <= 0) return;
 
     {   // zero the key row and the mask row once; later rows are re-zeroed by the destination pass
-        uint4 z = make_uint4(0, 0, 0, 0);
-        for (int i = tid; i < nquad; i += NT) reinterpret_cast<uint4 *>(keys)[i] = z;
-        for (int i = tid; i < Wwords; i += NT) s_mask[i] = 0;
+        for (int i = tid; i < nquad; i += NT) sts_zero128(sa_keys + 16u * i);
+        for (int i = tid; i < Wwords; i += NT) sts_u32(sa_mask + 4u * i, 0u);
     }
     if (tid == 0) {
-        for (int i = 0; i < kBars; ++i) mbar_init(&bars[i], 1);
+        for (int i = 0; i < kBars; ++i) mbar_init(reinterpret_cast<uint64_t *>(smem + a.lay.bars) + i, 1);
         fence_mbar_init();
     }
     __syncthreads();
@@ -114,16 +118,16 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_fused(FusedArgs a) {
     };
     // thread 0: stage image row + current depth row + table blob of iteration k
     auto issue_main = [&](int k, int y, int t, int dslot, bool bnd) {
-        uint64_t *bar = &bars[k % kBars];
-        mbar_expect_tx(bar, img_bytes + dep_bytes + a.blob_bytes + ((SMOOTH && bnd) ? 2 * dep_bytes : 0u));
-        bulk_g2s(smem + lay.img + (k % kImgSlots) * lay.img_stride, a.frames + ((size_t)t * H + y) * img_bytes, img_bytes, bar);
-        bulk_g2s(smem + lay.dep + dslot * lay.dep_stride, depth_row(y, t), dep_bytes, bar);
-        bulk_g2s(smem + lay.blob + (k & 1) * lay.blob_stride, a.blobs + (size_t)t * a.blob_bytes, a.blob_bytes, bar);
+        const uint32_t bar = sa_bars + 8u * (uint32_t)(k % kBars);
+        mbar_expect_tx_a(bar, img_bytes + dep_bytes + a.blob_bytes + ((SMOOTH && bnd) ? 2 * dep_bytes : 0u));
+        bulk_g2s_a(sb + a.lay.img + (uint32_t)(k % kImgSlots) * a.lay.img_stride, a.frames + ((size_t)t * H + y) * img_bytes, img_bytes, bar);
+        bulk_g2s_a(sb + a.lay.dep + (uint32_t)dslot * a.lay.dep_stride, depth_row(y, t), dep_bytes, bar);
+        bulk_g2s_a(sb + a.lay.blob + (uint32_t)(k & 1) * a.lay.blob_stride, a.blobs + (size_t)t * a.blob_bytes, a.blob_bytes, bar);
     };
     auto issue_hist = [&](int k, int y, int t, int s_h1, int s_h2) {
-        uint64_t *bar = &bars[k % kBars];
-        bulk_g2s(smem + lay.dep + s_h2 * lay.dep_stride, depth_row(y, t - 2), dep_bytes, bar);
-        bulk_g2s(smem + lay.dep + s_h1 * lay.dep_stride, depth_row(y, t - 1), dep_bytes, bar);
+        const uint32_t bar = sa_bars + 8u * (uint32_t)(k % kBars);
+        bulk_g2s_a(sb + a.lay.dep + (uint32_t)s_h2 * a.lay.dep_stride, depth_row(y, t - 2), dep_bytes, bar);
+        bulk_g2s_a(sb + a.lay.dep + (uint32_t)s_h1 * a.lay.dep_stride, depth_row(y, t - 1), dep_bytes, bar);
     };
 
     // (y,t) of iterations n, n+1, n+2 and the depth-ring slots of n and n+1 (uniform state)
@@ -166,20 +170,17 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_fused(FusedArgs a) {
         else if (bnd1) { h2_1 = (c1 + 1) & 3; h1_1 = (c1 + 2) & 3; c2 = (c1 + 3) & 3; }
         else      { h1_1 = c0; h2_1 = h1_0; c2 = c1 ^ c0 ^ h1_0; }
 
-        const uint8_t *img_row = smem + lay.img + i3 * lay.img_stride;
-        const uint8_t *blob = smem + lay.blob + (n & 1) * lay.blob_stride;
-        const uint16_t *dcur = reinterpret_cast<const uint16_t *>(smem + lay.dep + c0 * lay.dep_stride);
-        const uint16_t *dp1 = reinterpret_cast<const uint16_t *>(smem + lay.dep + h1_0 * lay.dep_stride);
-        const uint16_t *dp2 = reinterpret_cast<const uint16_t *>(smem + lay.dep + h2_0 * lay.dep_stride);
+        const uint32_t sa_imgrow = sb + a.lay.img + (uint32_t)i3 * a.lay.img_stride;
+        const uint32_t sa_blob = sb + a.lay.blob + (uint32_t)(n & 1) * a.lay.blob_stride;
+        const uint32_t sa_cur = sb + a.lay.dep + (uint32_t)c0 * a.lay.dep_stride;
+        const uint32_t sa_p1 = sb + a.lay.dep + (uint32_t)h1_0 * a.lay.dep_stride, sa_p2 = sb + a.lay.dep + (uint32_t)h2_0 * a.lay.dep_stride;
 
-        mbar_wait(&bars[i3], par);
+        mbar_wait_a(sa_bars + 8u * (uint32_t)i3, par);
 
-        const BlobHdr hdr = *reinterpret_cast<const BlobHdr *>(blob);
-        const bool fast = hdr.flags & 1u;
-        const int fill = hdr.fill_off;
-
-        const uint32_t sa_cur = smem_u32(dcur), sa_p1 = smem_u32(dp1), sa_p2 = smem_u32(dp2);
-        const uint32_t sa_img = smem_u32(img_row) + 4u * (uint32_t)wofs, sa_keys = smem_u32(keys);
+        const uint4 hdrw = lds_u128(sa_blob);                       // BlobHdr: fill_off, shift, ncells, flags
+        const bool fast = hdrw.w & 1u;
+        const int fill = (int)hdrw.x;
+        const uint32_t sa_img = sa_imgrow + 4u * (uint32_t)wofs;
 
         // smoothed depth of pixel x (both halves of the result hold it), from raw halves
         auto smooth_px = [&](uint32_t c, uint32_t p1, uint32_t p2) -> uint32_t {
@@ -197,10 +198,10 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_fused(FusedArgs a) {
 
         // ---- scatter ------------------------------------------------------------------------------------
         if (fast) {
-            const uint32_t sa_ent = smem_u32(blob) + 16u, sa_lut = sa_ent + a.ent_bytes;
+            const uint32_t sa_ent = sa_blob + 16u, sa_lut = sa_ent + a.ent_bytes;
             // LUT address = sa_lut + min(bits >> shift, ncells); dd holds the fp16 bits twice, so dd >> (16 + shift)
             // = umulhi(dd, 2^(16 - shift)) folds the shift and the base add into one IMAD.HI
-            const uint32_t lut_mul = 1u << (16u - hdr.shift), lut_last = sa_lut + hdr.ncells;
+            const uint32_t lut_mul = 1u << (16u - hdrw.y), lut_last = sa_lut + hdrw.z;
             const uint32_t sa_keys_lo = sa_keys - 4u * (uint32_t)a.key_pad;
             // U segments of 32 pixels per step, all loads of a step issued before their uses
             // w_last: warp index used for the LAST segment of the batch (differs from `warp` only for the left-over segment)
@@ -308,14 +309,14 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_fused(FusedArgs a) {
             }
         } else {
             // slow path (L > 255, non-monotone bounds, LUT too coarse): brute-force membership, layer-only keys
-            const int L = (int)(hdr.flags >> 8);
+            const int L = (int)(hdrw.w >> 8);
             const int frame = t0;
             const float2 *gb = a.bounds + (size_t)frame * a.Lcap;
             const int *go = a.offm + (size_t)frame * (a.Lcap + 1);
             for (int seg = warp; seg < nseg; seg += NW) {
                 const int x = (seg << 5) + lane;
                 if (x < W) {
-                    const uint32_t du = smooth_px(dcur[x], SMOOTH ? dp1[x] : 0, SMOOTH ? dp2[x] : 0);
+                    const uint32_t du = smooth_px(lds_u16(sa_cur + 2u * x), SMOOTH ? lds_u16(sa_p1 + 2u * x) : 0u, SMOOTH ? lds_u16(sa_p2 + 2u * x) : 0u);
                     const float d = __half2float(__ushort_as_half((unsigned short)(du & 0xffffu)));
                     for (int k = 0; k < L; ++k) {
                         const float2 b = __ldg(gb + k);
@@ -333,13 +334,13 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_fused(FusedArgs a) {
 
         // ---- destination pass: 4 pixels per thread --------------------------------------------------------
         {
-            uint4 *keys4 = reinterpret_cast<uint4 *>(keys);
-            uint32_t *out32 = reinterpret_cast<uint32_t *>(out_row);
-            const uint4 z = make_uint4(0, 0, 0, 0);
-            const int *go = a.offm + (size_t)t0 * (a.Lcap + 1);
+            auto fetch = [&](int xs) {                          // 3 bytes at byte offset 3*xs of the staged image row
+                const uint32_t ab = 3u * (uint32_t)xs, wa = sa_imgrow + (ab & ~3u);
+                return __funnelshift_r(lds_u32(wa), lds_u32(wa + 4u), (ab & 3u) * 8u) & 0x00ffffffu;
+            };
             for (int j = tid; j < nquad; j += NT) {
-                uint4 k = keys4[j];
-                keys4[j] = z;
+                const uint4 k = lds_u128(sa_keys + 16u * j);
+                sts_zero128(sa_keys + 16u * j);
                 uint32_t kk[4] = {k.x, k.y, k.z, k.w};
                 if (fast) {
                     const uint32_t mn = min(min(k.x, k.y), min(k.z, k.w));
@@ -350,36 +351,38 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_fused(FusedArgs a) {
                             if (kk[i] < 0x01000000u) {
                                 int xs = 4 * j + i - fill;
                                 xs += (xs < 0) ? W : 0;
-                                kk[i] = fetch_rgb(img_row, xs);
+                                kk[i] = fetch(xs);
                                 hm |= 1u << i;
                             }
                         }
-                        atomicOr(&s_mask[j >> 3], hm << ((j & 7) * 4));
+                        reds_or(sa_mask + 4u * (uint32_t)(j >> 3), hm << ((j & 7) * 4));
                     }
                 } else {
+                    const int *go = a.offm + (size_t)t0 * (a.Lcap + 1);
                     uint32_t hm = 0;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         int xs = 4 * j + i - (kk[i] ? __ldg(go + kk[i]) : fill);
                         xs += (xs < 0) ? W : 0;
                         hm |= (kk[i] ? 0u : 1u) << i;
-                        kk[i] = fetch_rgb(img_row, xs);
+                        kk[i] = fetch(xs);
                     }
-                    if (hm) atomicOr(&s_mask[j >> 3], hm << ((j & 7) * 4));
+                    if (hm) reds_or(sa_mask + 4u * (uint32_t)(j >> 3), hm << ((j & 7) * 4));
                 }
-                out32[3 * j + 0] = __byte_perm(kk[0], kk[1], 0x4210);
-                out32[3 * j + 1] = __byte_perm(kk[1], kk[2], 0x5421);
-                out32[3 * j + 2] = __byte_perm(kk[2], kk[3], 0x6542);
+                const uint32_t oa = sa_out + 12u * j;
+                sts_u32(oa, __byte_perm(kk[0], kk[1], 0x4210));
+                sts_u32(oa + 4u, __byte_perm(kk[1], kk[2], 0x5421));
+                sts_u32(oa + 8u, __byte_perm(kk[2], kk[3], 0x6542));
             }
         }
         fence_async_smem();
         __syncthreads();
 
-        const long long row = (long long)t0 * H + y0;             // global row index of this iteration
+        const uint32_t row = (uint32_t)t0 * (uint32_t)H + (uint32_t)y0;        // global row index of this iteration (< 2^24)
         if (tid == 0) {
             uint8_t *go = a.sbs + (size_t)row * img_bytes * 2;
-            bulk_s2g(go, out_row, img_bytes);
-            bulk_s2g(go + img_bytes, img_row, img_bytes);
+            bulk_s2g_a(go, sa_out, img_bytes);
+            bulk_s2g_a(go + img_bytes, sa_imgrow, img_bytes);
             bulk_commit();
             if (n + 2 < N) issue_main(n + 2, y2, t2, c2, t2 == 0);
             if (SMOOTH && bnd1 && n + 1 < N) issue_hist(n + 1, y1, t1, h1_1, h2_1);
@@ -389,8 +392,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_fused(FusedArgs a) {
             const int w = tid;
             uint32_t v = 0;
             if (w < Wwords) {
-                v = s_mask[w];
-                s_mask[w] = 0;
+                v = lds_u32(sa_mask + 4u * w);
+                sts_u32(sa_mask + 4u * w, 0u);
                 a.hole_mask[(size_t)row * Wwords + w] = v;
             }
             const unsigned nz = __ballot_sync(0xffffffffu, v != 0u);
@@ -402,7 +405,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_fused(FusedArgs a) {
                     atomicAdd(&a.tabs[t0].holes, (unsigned long long)holes);
                 }
                 base = __shfl_sync(0xffffffffu, base, 0);
-                if (v) a.hole_list[base + __popc(nz & ((1u << lane) - 1u))] = ((uint32_t)row << 8) | (uint32_t)w;
+                if (v) a.hole_list[base + __popc(nz & ((1u << lane) - 1u))] = (row << 8) | (uint32_t)w;
             }
         }
         // advance the uniform state
