@@ -500,3 +500,26 @@ def test_repeated_warp_batch_is_idempotent():
     assert np.array_equal(outs[0][:, :, :W], ref_left)
     assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
     ctx.close()
+
+
+def test_out_of_budget_frames_fall_back(oracle_lib):
+    """The fast-path tables are sized on the host for limit_step <= 32.  Frames beyond that budget (more layers,
+    larger offsets than the key-row bound, a bigger LUT) must take the slow membership path inside the same
+    kernel and stay bit-exact; frames inside the budget in the same batch keep the fast path."""
+    rng = np.random.default_rng(21)
+    H, W = 270, 480
+    frames = rng.integers(0, 256, size=(4, H, W, 3), dtype=np.uint8)
+    raw = (rng.random((4, H, W)) * 13).astype(np.float16)
+    raw[1] = (rng.random((H, W)) * 90).astype(np.float16)          # limit_step 90: far outside the budget
+    raw[2, :40] = np.float16(47.0)                                  # limit_step 47
+    p = dict(fg=0.05, bg=-0.03, step=1)
+    w = O.gaussian_weights(*O.blur_kernel_shape(H))
+    for mode in (0, 4):
+        ctx = _ctx(H, W, p["fg"], p["bg"], p["step"], w, mode=mode, max_layers=1024)
+        sbs, _, infos, masks = _run_device(ctx, frames, raw)
+        want, stages = _oracle_run(oracle_lib, p, frames, raw, w)
+        assert infos[1].limit_step > 40 and infos[0].limit_step <= 13
+        for t in range(4):
+            assert np.array_equal(masks[t], stages[t]["holes"]), (mode, t)
+            assert np.array_equal(sbs[t], want[t]), (mode, t, int((sbs[t] != want[t]).sum()))
+        ctx.close()
