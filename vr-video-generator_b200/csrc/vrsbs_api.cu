@@ -19,6 +19,7 @@
 #include "depth_kernels.cuh"
 #include "table_kernel.cuh"
 #include "warp_fused.cuh"
+#include "warp_ws.cuh"
 #include "warp_kernel.cuh"
 
 using namespace vrsbs;
@@ -181,6 +182,7 @@ struct vrsbs_ctx {
     int key_pad = 0;                     // fast path: bound on |signed layer offset| in pixels (multiple of 32)
     int fused = 1;                       // option: use the fused route in vrsbs_process_batch when possible
     int fast_tables = 1;                 // option (tests): 0 forces the slow membership path of k_warp_fused
+    int warp_ws = 1;                     // option: 1 = warp-specialised warp kernel (k_warp_ws) when it fits, 0 = k_warp_fused
     int lowres_tiled = 1;                // option: 0 = one-pixel-per-thread bicubic kernel (tests)
     int smooth_in_warp = 0;              // option: 1 = smoothing recomputed inside the warp kernel (no smoothed depth in HBM);
                                          // measured slower than materialising it, so off by default
@@ -472,6 +474,33 @@ int launch_fused_inst(vrsbs_ctx *c, const FusedArgs &a, cudaStream_t st) {
     return VRSBS_OK;
 }
 
+// warp-specialised variant: 5 scatter + 3 destination warps; used when it reaches the same residency as k_warp_fused
+// (4 CTAs per SM), the mask row fits the destination warps and the key-row bound fits the scatter warps
+int launch_ws(vrsbs_ctx *c, const FusedArgs &a, cudaStream_t st, bool *launched) {
+    constexpr int NT = 256, NS = 5;
+    *launched = false;
+    const int wwords32 = ((a.W + 31) / 32 + 31) / 32 * 32;
+    if (a.W % 32 != 0 || a.W > 2048 || a.key_pad > 32 * NS || wwords32 > (NT / 32 - NS) * 32) return VRSBS_OK;
+    WsArgs w{};
+    w.f = a;
+    w.lay = ws_smem_layout(a.W, a.blob_bytes);
+    auto kern = k_warp_ws<NT, NS>;
+    if (w.lay.total > 200 * 1024) return VRSBS_OK;
+    CU_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.lay.total));
+    int occ = 0;
+    CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, w.lay.total));
+    if (occ < 4) return VRSBS_OK;
+    if (c->blocks_per_sm > 0 && c->blocks_per_sm < occ) occ = c->blocks_per_sm;
+    long long iters = (long long)a.B * a.H, grid = (long long)c->sm_count * occ;
+    if (grid > iters) grid = iters;
+    StageTimer timer(c, st, 2);
+    kern<<<(unsigned)grid, NT, w.lay.total, st>>>(w);
+    CU_TRY(c, cudaGetLastError());
+    c->launches++;
+    *launched = true;
+    return VRSBS_OK;
+}
+
 bool fused_capable(const vrsbs_ctx *c, const void *frames, const void *depth, const void *sbs, int W) {
     const size_t smem = fused_smem_layout(W, blob_bytes(c->ent_cap, c->lut_cap)).total;
     return (W % 16 == 0) && W * 4 <= 65535 && ((uintptr_t)frames % 16 == 0) && ((uintptr_t)depth % 16 == 0) &&
@@ -581,7 +610,9 @@ int launch_warp(vrsbs_ctx *c, Scratch &s, const uint8_t *frames, const __half *d
     if ((rc = fresh_hole_list(c, s, st))) return rc;
     if (c->fused && fused_capable(c, frames, depth, sbs, W)) {
         FusedArgs a = make_fused_args(c, s, frames, depth, B, H, W, sbs);
-        rc = W <= 2048 ? launch_fused_inst<false, 256>(c, a, st) : launch_fused_inst<false, 512>(c, a, st);
+        bool done = false;
+        if (c->warp_ws) rc = launch_ws(c, a, st, &done);
+        if (!rc && !done) rc = W <= 2048 ? launch_fused_inst<false, 256>(c, a, st) : launch_fused_inst<false, 512>(c, a, st);
     } else {
         WarpArgs a{};
         a.frames = frames; a.depth = depth; a.sbs = sbs; a.tabs = s.tabs; a.bounds = s.bounds; a.offm = s.offm;
@@ -1097,6 +1128,7 @@ int vrsbs_set_option(vrsbs_ctx *c, const char *name, int value) {
     else if (!strcmp(name, "fast_tables")) c->fast_tables = value != 0;
     else if (!strcmp(name, "smooth_in_warp")) c->smooth_in_warp = value != 0;
     else if (!strcmp(name, "lowres_tiled")) c->lowres_tiled = value != 0;
+    else if (!strcmp(name, "warp_ws")) c->warp_ws = value != 0;
     else return fail(c, VRSBS_E_INVALID, "unknown option %s", name);
     return VRSBS_OK;
 }
