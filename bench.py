@@ -304,7 +304,7 @@ def run_ours(args, wl, name):
                        "sharding": "independent clip range per GPU, no collective", "depth_input": args.depth_input,
                        "route": f"rows(scatter_mode={args.scatter_mode})" if args.scatter_mode else "fused"},
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_warp_rows" if args.scatter_mode else "k_warp_fused", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_warp_rows" if args.scatter_mode else ("k_warp_ws" if W % 32 == 0 and W <= 2048 else "k_warp_fused"), "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": abytes, "launch_ms": warp_ms / max(warp_n, 1)},
             "stage_ms_per_step": {k: v[0] / args.steps for k, v in stage.items()},

@@ -182,6 +182,7 @@ struct vrsbs_ctx {
     int key_pad = 0;                     // fast path: bound on |signed layer offset| in pixels (multiple of 32)
     int fused = 1;                       // option: use the fused route in vrsbs_process_batch when possible
     int fast_tables = 1;                 // option (tests): 0 forces the slow membership path of k_warp_fused
+    int ws_scatter_warps = 4;            // option: scatter warps of k_warp_ws (3, 4 or 5 of 8 warps; 6 = 6 of 9, 7 = 6 of 10); 4 measured best
     int warp_ws = 1;                     // option: 1 = warp-specialised warp kernel (k_warp_ws) when it fits, 0 = k_warp_fused
     int lowres_tiled = 1;                // option: 0 = one-pixel-per-thread bicubic kernel (tests)
     int smooth_in_warp = 0;              // option: 1 = smoothing recomputed inside the warp kernel (no smoothed depth in HBM);
@@ -476,8 +477,8 @@ int launch_fused_inst(vrsbs_ctx *c, const FusedArgs &a, cudaStream_t st) {
 
 // warp-specialised variant: 5 scatter + 3 destination warps; used when it reaches the same residency as k_warp_fused
 // (4 CTAs per SM), the mask row fits the destination warps and the key-row bound fits the scatter warps
-int launch_ws(vrsbs_ctx *c, const FusedArgs &a, cudaStream_t st, bool *launched) {
-    constexpr int NT = 256, NS = 5;
+template <int NT, int NS>
+int launch_ws_inst(vrsbs_ctx *c, const FusedArgs &a, cudaStream_t st, bool *launched) {
     *launched = false;
     const int wwords32 = ((a.W + 31) / 32 + 31) / 32 * 32;
     if (a.W % 32 != 0 || a.W > 2048 || a.key_pad > 32 * NS || wwords32 > (NT / 32 - NS) * 32) return VRSBS_OK;
@@ -499,6 +500,16 @@ int launch_ws(vrsbs_ctx *c, const FusedArgs &a, cudaStream_t st, bool *launched)
     c->launches++;
     *launched = true;
     return VRSBS_OK;
+}
+int launch_ws(vrsbs_ctx *c, const FusedArgs &a, cudaStream_t st, bool *launched) {
+    switch (c->ws_scatter_warps) {
+        case 3: return launch_ws_inst<256, 3>(c, a, st, launched);
+        case 4: return launch_ws_inst<256, 4>(c, a, st, launched);
+        case 6: return launch_ws_inst<288, 6>(c, a, st, launched);      // 9 warps: 6 scatter + 3 destination
+        case 7: return launch_ws_inst<320, 6>(c, a, st, launched);      // 10 warps: 6 + 4
+        case 5: return launch_ws_inst<256, 5>(c, a, st, launched);
+        default: return launch_ws_inst<256, 4>(c, a, st, launched);
+    }
 }
 
 bool fused_capable(const vrsbs_ctx *c, const void *frames, const void *depth, const void *sbs, int W) {
@@ -1129,6 +1140,7 @@ int vrsbs_set_option(vrsbs_ctx *c, const char *name, int value) {
     else if (!strcmp(name, "smooth_in_warp")) c->smooth_in_warp = value != 0;
     else if (!strcmp(name, "lowres_tiled")) c->lowres_tiled = value != 0;
     else if (!strcmp(name, "warp_ws")) c->warp_ws = value != 0;
+    else if (!strcmp(name, "ws_scatter_warps")) c->ws_scatter_warps = value;
     else return fail(c, VRSBS_E_INVALID, "unknown option %s", name);
     return VRSBS_OK;
 }

@@ -48,12 +48,25 @@ struct WsArgs {
 __device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// mbarrier wait that sleeps between polls: in k_warp_ws a waiting group would otherwise spend issue slots the
+// working group needs (profiles/r01l: 14 % of all executed instructions were try_wait polls)
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "WAIT_%=:\n\t"
+        "nanosleep.u32 %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity), "r"(40u) : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 template <int NT, int NS>
-__global__ void __launch_bounds__(NT, 1024 / NT) k_warp_ws(WsArgs wa) {
+__global__ void __launch_bounds__(NT, 4) k_warp_ws(WsArgs wa) {
     const FusedArgs &a = wa.f;
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int NW = NT / 32, ND = NW - NS, NDT = ND * 32;
@@ -102,8 +115,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_ws(WsArgs wa) {
             const uint32_t sa_blob = sb + wa.lay.blob + b * wa.lay.blob_stride;
             const uint32_t sa_cur = sb + wa.lay.dep + (uint32_t)i3 * wa.lay.dep_stride;
             const uint32_t sa_img = sb + wa.lay.img + (uint32_t)i3 * wa.lay.img_stride + 4u * (uint32_t)wofs;
-            mbar_wait_a(bar_in + 8u * (uint32_t)i3, par3);
-            mbar_wait_a(bar_kempty + 8u * b, (((uint32_t)n >> 1) & 1u) ^ 1u);
+            mbar_wait_sleep(bar_in + 8u * (uint32_t)i3, par3);
+            mbar_wait_sleep(bar_kempty + 8u * b, (((uint32_t)n >> 1) & 1u) ^ 1u);
             const uint4 hdrw = lds_u128(sa_blob);
             if (hdrw.w & 1u) {
                 const uint32_t sa_ent = sa_blob + 16u, sa_lut = sa_ent + a.ent_bytes;
@@ -216,12 +229,18 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_ws(WsArgs wa) {
             const uint32_t sa_keys = sb + wa.lay.keys + b * wa.lay.keys_stride;
             const uint32_t sa_blob = sb + wa.lay.blob + b * wa.lay.blob_stride;
             const uint32_t sa_imgrow = sb + wa.lay.img + (uint32_t)i3 * wa.lay.img_stride;
-            mbar_wait_a(bar_in + 8u * (uint32_t)i3, par3);
+            mbar_wait_sleep(bar_in + 8u * (uint32_t)i3, par3);
             const uint4 hdrw = lds_u128(sa_blob);
             const bool fast = hdrw.w & 1u;
             const int fill = (int)hdrw.x;
-            mbar_wait_a(bar_kfull + 8u * b, ((uint32_t)n >> 1) & 1u);
-            if (elect) bulk_wait_read0();                 // the previous row's bulk stores have finished reading out / img slots
+            mbar_wait_sleep(bar_kfull + 8u * b, ((uint32_t)n >> 1) & 1u);
+            if (elect) {
+                bulk_wait_read0();                        // the previous row's bulk stores have finished reading out / img slots
+                // row n+2 goes into the slots of row n-1 (scattered, packed and stored) and into blob slot b, whose header
+                // is already in registers and whose tables only scatter(n) - complete, k_full seen - needed: issue it
+                // now, a whole destination pass earlier than after the stores
+                if (n + 2 < N) issue(n + 2, y2, t2);
+            }
             named_bar_sync(1, NDT);
             auto fetch = [&](int xs) {
                 const uint32_t ab = 3u * (uint32_t)xs, wadr = sa_imgrow + (ab & ~3u);
@@ -272,7 +291,6 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_ws(WsArgs wa) {
                 bulk_s2g_a(go + img_bytes, sa_imgrow, img_bytes);
                 bulk_commit();
                 mbar_arrive_a(bar_kempty + 8u * b);       // keys[b] is zero again
-                if (n + 2 < N) issue(n + 2, y2, t2);
             }
             // hole mask row -> global bitmask + blur work list (first ceil(Wwords/32) destination warps)
             if (dt < ((Wwords + 31) & ~31)) {
