@@ -208,7 +208,8 @@ __global__ void __launch_bounds__(NT, 4) k_warp_ws(WsArgs wa) {
     } else {
         // =============================== destination warps ===========================================
         const int dt = tid - NS * 32;                                     // 0 .. NDT-1
-        const bool elect = dt == 0;
+        const bool elect = dt == 0;                                       // issues the bulk stores, arrives on k_empty
+        const bool loader = dt == NDT - 32;                               // lane 0 of the last destination warp: TMA loads
         int y1 = y0, t1 = t0; next_yt(y1, t1);
         int y2 = y1, t2 = t1; next_yt(y2, t2);
         auto issue = [&](int k, int y, int t) {                           // elected thread: TMA loads of iteration k
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(NT, 4) k_warp_ws(WsArgs wa) {
             bulk_g2s_a(sb + wa.lay.dep + s3 * wa.lay.dep_stride, a.depth + ((size_t)t * H + y) * W, dep_bytes, bar);
             bulk_g2s_a(sb + wa.lay.blob + (uint32_t)(k & 1) * wa.lay.blob_stride, a.blobs + (size_t)t * a.blob_bytes, a.blob_bytes, bar);
         };
-        if (elect) {
+        if (loader) {
             issue(0, y0, t0);
             if (N > 1) issue(1, y1, t1);
         }
@@ -234,14 +235,12 @@ __global__ void __launch_bounds__(NT, 4) k_warp_ws(WsArgs wa) {
             const bool fast = hdrw.w & 1u;
             const int fill = (int)hdrw.x;
             mbar_wait_sleep(bar_kfull + 8u * b, ((uint32_t)n >> 1) & 1u);
-            if (elect) {
-                bulk_wait_read0();                        // the previous row's bulk stores have finished reading out / img slots
-                // row n+2 goes into the slots of row n-1 (scattered, packed and stored) and into blob slot b, whose header
-                // is already in registers and whose tables only scatter(n) - complete, k_full seen - needed: issue it
-                // now, a whole destination pass earlier than after the stores
-                if (n + 2 < N) issue(n + 2, y2, t2);
-            }
+            if (elect) bulk_wait_read0();                 // the previous row's bulk stores have finished reading out / img slots
             named_bar_sync(1, NDT);
+            // row n+2 goes into the slots of row n-1 (scattered, packed, and - the barrier above - read by its stores) and into
+            // blob slot b, whose header every destination thread holds in registers and whose tables only scatter(n) -
+            // complete, k_full seen - needed.  A different thread than the storer issues it, off the storer's critical path.
+            if (loader && n + 2 < N) issue(n + 2, y2, t2);
             auto fetch = [&](int xs) {
                 const uint32_t ab = 3u * (uint32_t)xs, wadr = sa_imgrow + (ab & ~3u);
                 return __funnelshift_r(lds_u32(wadr), lds_u32(wadr + 4u), (ab & 3u) * 8u) & 0x00ffffffu;
