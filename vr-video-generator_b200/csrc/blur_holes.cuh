@@ -281,7 +281,7 @@ __host__ __device__ constexpr size_t blur_fixed_warp_smem() {
 // and strip (one round of dependent loads for 32 entries), then the warp walks the entries, lane = pixel.
 __global__ void __launch_bounds__(256) k_blur_commit(BlurArgs a, int do_commit) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const uint32_t count = do_commit ? *a.hole_count : 0u;
+    const uint32_t count = (do_commit & 1) ? *a.hole_count : 0u;      // do_commit: bit 0 = hole values, bit 1 = skip the strip (experiments)
     constexpr int E = 4;                                   // entries per warp step: four independent load chains in flight
     for (uint32_t e0 = (blockIdx.x * nwarps + warp) * E; e0 < count; e0 += gridDim.x * nwarps * E) {
         uint32_t gw = 0, m = 0, strip = 0;
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(256) k_blur_commit(BlurArgs a, int do_commit) 
     }
     // strip restore: 4 threads per image row, 64 bytes each per round (16-byte copies when the rows are aligned)
     const long long nthreads = (long long)gridDim.x * blockDim.x;
-    const long long rows = (long long)a.B * a.H;
+    const long long rows = (do_commit & 2) ? 0 : (long long)a.B * a.H;
     const bool vec = (a.W % 16 == 0) && ((reinterpret_cast<uintptr_t>(a.frames) | reinterpret_cast<uintptr_t>(a.sbs)) % 16 == 0);
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < rows * 4; idx += nthreads) {
         const long long r = idx >> 2;

@@ -183,6 +183,7 @@ struct vrsbs_ctx {
     int fused = 1;                       // option: use the fused route in vrsbs_process_batch when possible
     int fast_tables = 1;                 // option (tests): 0 forces the slow membership path of k_warp_fused
     int ws_scatter_warps = 4;            // option: scatter warps of k_warp_ws (3, 4 or 5 of 8 warps; 6 = 6 of 9, 7 = 6 of 10); 4 measured best
+    int commit_mode = 1;                 // experiments: 1 = commit + strip, 0 = strip only, 3 = commit only, 2 = neither
     int warp_ws = 1;                     // option: 1 = warp-specialised warp kernel (k_warp_ws) when it fits, 0 = k_warp_fused
     int lowres_tiled = 1;                // option: 0 = one-pixel-per-thread bicubic kernel (tests)
     int smooth_in_warp = 0;              // option: 1 = smoothing recomputed inside the warp kernel (no smoothed depth in HBM);
@@ -586,7 +587,7 @@ int launch_blur(vrsbs_ctx *c, Scratch &s, const uint8_t *frames, int B, int H, i
         CU_TRY(c, cudaGetLastError());
         c->launches++;
     }
-    return launch_commit(c, b, 1, st);
+    return launch_commit(c, b, c->commit_mode, st);
 }
 
 int check_blur_ready(vrsbs_ctx *c, int H, int W) {
@@ -1140,6 +1141,7 @@ int vrsbs_set_option(vrsbs_ctx *c, const char *name, int value) {
     else if (!strcmp(name, "smooth_in_warp")) c->smooth_in_warp = value != 0;
     else if (!strcmp(name, "lowres_tiled")) c->lowres_tiled = value != 0;
     else if (!strcmp(name, "warp_ws")) c->warp_ws = value != 0;
+    else if (!strcmp(name, "commit_mode")) c->commit_mode = value;
     else if (!strcmp(name, "ws_scatter_warps")) c->ws_scatter_warps = value;
     else return fail(c, VRSBS_E_INVALID, "unknown option %s", name);
     return VRSBS_OK;
