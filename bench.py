@@ -37,6 +37,7 @@ WORKLOADS = {
     # scatter / blur stress (19 % holes)
     "1080p_stress_b64": dict(H=1080, W=1920, B=64, fg=0.025, bg=-0.015, step=1, depth="stress"),
 }
+ranks = None
 METRIC = "sbs_frames_per_sec_warp_stage"
 UNIT = "frames/s"
 
@@ -110,6 +111,8 @@ def dist_setup():
     if cuda:
         torch.cuda.set_device(local)
     r = shard.Ranks(backend="nccl" if cuda else "gloo", device=f"cuda:{local}" if cuda else "cpu")
+    global ranks
+    ranks = r
     return r.rank, r.world, r.barrier, r.max
 
 
@@ -317,6 +320,7 @@ def run_ours(args, wl, name):
         print(json.dumps(line))
     ctx.close()
     proc.close()
+    ranks.close()
 
 
 # ---------------------------------------------------------------------------------------------------------

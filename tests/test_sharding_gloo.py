@@ -48,10 +48,13 @@ def test_shard_and_flush_bookkeeping():
     assert shard.shard_for_rank(0, 10 ** 14, 100, 8, 7) == (91, 104)
     assert shard.shard_for_rank(0, 10 ** 14, 3, 8, 5) is None
     # nibba_woka: flush every Max_Frame_Count frames and at the end; names are {first}_{last}.mp4
-    assert shard.flush_ranges(0, 25, 100, 15) == [(0, 14), (15, 24)]
-    assert shard.flush_ranges(91, 104, 100, 15) == [(91, 99)]
-    assert shard.subclip_name(15, 24) == "15_24.mp4"
-    # Check_Clips' rule: count == end + 1 - begin, neighbours continuous
+    # names and frame counts exactly as nibba_woka's loop produces them (PredictAndGenerate.py:221-250): frame i-1 is
+    # appended at iteration i, so "0_15" holds the 15 frames 0..14 and the next clip is named from 16
+    assert shard.flush_ranges(0, 25, 100, 15) == [(0, 15, 15), (16, 24, 10)]
+    assert shard.flush_ranges(91, 104, 100, 15) == [(91, 99, 9)]
+    assert shard.subclip_name(16, 24) == "16_24.mp4"
+    # same names as the worker loop writes, every frame of every range exactly once
+    from vr_video_generator_b200 import worker
     clips = [c for b, e in tables.clip_ranges(0, 10 ** 14, 100, 4) for c in shard.flush_ranges(b, e, 100, 15)]
-    assert clips[0][0] == 0 and clips[-1][1] == 99
-    assert all(clips[i][1] + 1 == clips[i + 1][0] for i in range(len(clips) - 1))
+    assert sum(c[2] for c in clips) == 100 and clips[0][0] == 0 and clips[-1][1] == 99
+    assert worker.order_subclips([shard.subclip_name(a, b) for a, b, _ in reversed(clips)]) == [shard.subclip_name(a, b) for a, b, _ in clips]

@@ -25,16 +25,20 @@ def shard_for_rank(start_frame, end_frame, video_length, world, rank):
 
 
 def flush_ranges(begin, end, video_length, max_frame_count):
-    """The sub-clips one worker writes: [(first, last_inclusive)], named f"{first}_{last}.mp4"
-    (nibba_woka's flush rule, PredictAndGenerate.py:236-247)."""
+    """The sub-clips one worker writes, exactly as nibba_woka's loop names them (PredictAndGenerate.py:221-250):
+    [(last_i, i, frames)] -> file f"{last_i}_{i}.mp4" holding `frames` frames.  Frame i-1 is appended at iteration i
+    (one-frame look-ahead) and the final frame at the last iteration, so a full sub-clip "0_15" holds frames 0..14
+    and the next one is named from 16."""
     stop = min(end, video_length)
-    out, first = [], begin
-    count = 0
+    out, pending, last_i = [], 0, begin
     for i in range(begin, stop):
-        count += 1
-        if count == max_frame_count or i == stop - 1:
-            out.append((first, i))
-            first, count = i + 1, 0
+        if i != begin:
+            pending += 1
+        if i == stop - 1:
+            pending += 1
+        if pending == max_frame_count or i == min(end - 1, video_length - 1):
+            out.append((last_i, i, pending))
+            last_i, pending = i + 1, 0
     return out
 
 
