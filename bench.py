@@ -305,7 +305,7 @@ def run_ours(args, wl, name):
                        "l2": f"inputs per step {int((frames_h.nbytes + raw_h.nbytes) / 2**20)} MiB + outputs "
                              f"{int(o_np.nbytes / 2**20)} MiB per GPU > 126 MB L2 (no flush needed)",
                        "sharding": "independent clip range per GPU, no collective", "depth_input": args.depth_input,
-                       "route": f"rows(scatter_mode={args.scatter_mode})" if args.scatter_mode else "fused"},
+                       "route": f"general row kernel (scatter_mode={args.scatter_mode})" if args.scatter_mode else "default (k_depth_pass, k_build_tables, k_warp_ws, k_blur_holes_fixed, k_blur_commit)"},
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_warp_rows" if args.scatter_mode else ("k_warp_ws" if W % 32 == 0 and W <= 2048 else "k_warp_fused"), "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
