@@ -525,3 +525,17 @@ def test_out_of_budget_frames_fall_back(oracle_lib):
             assert np.array_equal(masks[t], stages[t]["holes"]), (mode, t)
             assert np.array_equal(sbs[t], want[t]), (mode, t, int((sbs[t] != want[t]).sum()))
         ctx.close()
+
+
+@pytest.mark.parametrize("split", [3, 4, 5, 6, 7])
+def test_warp_specialised_splits(split, oracle_lib):
+    """k_warp_ws with every scatter/destination warp split (3+5, 4+4, 5+3 of 8 warps, 6+3 of 9, 6+4 of 10)."""
+    for name in ("small_a", "medium"):
+        meta, frames, raw, ref_left = load_case(name)
+        p = meta["params"]
+        ctx = _ctx(p["H"], p["W"], p["fg"], p["bg"], p["step"], golden_weights(meta))
+        ctx.set_option("ws_scatter_warps", split)
+        sbs, _, infos, masks = _run_device(ctx, frames, raw)
+        assert np.array_equal(sbs[:, :, :p["W"]], ref_left), (name, split)
+        assert np.array_equal(sbs[:, :, p["W"]:], frames)
+        ctx.close()
