@@ -482,7 +482,7 @@ template <int NT, int NS>
 int launch_ws_inst(vrsbs_ctx *c, const FusedArgs &a, cudaStream_t st, bool *launched) {
     *launched = false;
     const int wwords32 = ((a.W + 31) / 32 + 31) / 32 * 32;
-    if (a.W % 32 != 0 || a.W > 2048 || a.key_pad > 32 * NS || wwords32 > (NT / 32 - NS) * 32) return VRSBS_OK;
+    if (a.W % 32 != 0 || a.key_pad > 32 * NS || wwords32 > (NT / 32 - NS) * 32) return VRSBS_OK;
     WsArgs w{};
     w.f = a;
     w.lay = ws_smem_layout(a.W, a.blob_bytes);
@@ -491,7 +491,7 @@ int launch_ws_inst(vrsbs_ctx *c, const FusedArgs &a, cudaStream_t st, bool *laun
     CU_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.lay.total));
     int occ = 0;
     CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, w.lay.total));
-    if (occ < 4) return VRSBS_OK;
+    if (occ * NT < 1024) return VRSBS_OK;             // fewer than 32 resident warps per SM: k_warp_fused does better
     if (c->blocks_per_sm > 0 && c->blocks_per_sm < occ) occ = c->blocks_per_sm;
     long long iters = (long long)a.B * a.H, grid = (long long)c->sm_count * occ;
     if (grid > iters) grid = iters;
@@ -503,6 +503,13 @@ int launch_ws_inst(vrsbs_ctx *c, const FusedArgs &a, cudaStream_t st, bool *laun
     return VRSBS_OK;
 }
 int launch_ws(vrsbs_ctx *c, const FusedArgs &a, cudaStream_t st, bool *launched) {
+    if (a.W > 2048) {                                  // 4K rows: 2 CTAs of 16 warps per SM (shared memory bound)
+        switch (c->ws_scatter_warps) {
+            case 3: return launch_ws_inst<512, 6>(c, a, st, launched);
+            case 5: return launch_ws_inst<512, 10>(c, a, st, launched);
+            default: return launch_ws_inst<512, 8>(c, a, st, launched);
+        }
+    }
     switch (c->ws_scatter_warps) {
         case 3: return launch_ws_inst<256, 3>(c, a, st, launched);
         case 4: return launch_ws_inst<256, 4>(c, a, st, launched);

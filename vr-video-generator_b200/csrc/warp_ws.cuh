@@ -66,7 +66,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 
 template <int NT, int NS>
-__global__ void __launch_bounds__(NT, 4) k_warp_ws(WsArgs wa) {
+__global__ void __launch_bounds__(NT, 1024 / NT) k_warp_ws(WsArgs wa) {
     const FusedArgs &a = wa.f;
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int NW = NT / 32, ND = NW - NS, NDT = ND * 32;
