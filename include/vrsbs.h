@@ -165,10 +165,14 @@ uint64_t vrsbs_launch_count(const vrsbs_ctx *ctx);
 #define VRSBS_NUM_STAGES 5
 int  vrsbs_get_stage_times(vrsbs_ctx *ctx, double ms[VRSBS_NUM_STAGES], uint64_t count[VRSBS_NUM_STAGES]);
 
-/* Tuning knobs: "fused" (1 = TMA warp kernel k_warp_fused when the shape allows, 0 = general row kernel),
- * "smooth_in_warp" (see vrsbs_process_batch), "fast_tables" (0 forces the slow membership path, tests), "scatter_mode" of the general row kernel (2 = atomicMax for every key, 1 = plain store +
- * verify), "bicubic_contract", "blocks_per_sm", "host_chunk", "copy_threads", "pageable_direct", "host_right_half",
- * "stage_timing". */
+/* Tuning knobs (defaults are the measured best; the others stay for tests and experiments):
+ *   "fused" (1 = TMA warp kernels when the shape allows, 0 = general row kernel), "warp_ws" (1 = warp-specialised
+ *   k_warp_ws, 0 = barrier-synchronised k_warp_fused), "ws_scatter_warps" (scatter/destination split of k_warp_ws),
+ *   "smooth_in_warp" (see vrsbs_process_batch), "fast_tables" (0 forces the slow membership path),
+ *   "scatter_mode" of the general row kernel (2 = atomicMax for every key, 1 = plain store + verify),
+ *   "blur_screen" (1 = one-multiply screening sum before the exact integer blur, 0 = exact sum for every hole),
+ *   "commit_mode", "lowres_tiled", "bicubic_contract", "blocks_per_sm", "host_chunk", "copy_threads",
+ *   "pageable_direct", "host_right_half", "stage_timing". */
 int  vrsbs_set_option(vrsbs_ctx *ctx, const char *name, int value);
 
 #ifdef __cplusplus

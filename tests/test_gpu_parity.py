@@ -539,3 +539,25 @@ def test_warp_specialised_splits(split, oracle_lib):
         assert np.array_equal(sbs[:, :, :p["W"]], ref_left), (name, split)
         assert np.array_equal(sbs[:, :, p["W"]:], frames)
         ctx.close()
+
+
+@pytest.mark.parametrize("screen", [1, 0])
+def test_blur_screening_is_exact(screen, oracle_lib):
+    """Every pixel a hole (zero depth), so the blur evaluates ~390k values per frame: the one-multiply screening
+    sum followed by the exact sum for the undecided values (blur_screen=1) and the exact sum for every value
+    (blur_screen=0) both equal the oracle bit for bit, for the 1080p (11x9, 2 parts) and the 4K (19x17, 3 parts)
+    gaussians, on random bytes and on a two-level image (sums cluster, more near-ties)."""
+    rng = np.random.default_rng(23)
+    H, W = 270, 480
+    frames = rng.integers(0, 256, size=(2, H, W, 3), dtype=np.uint8)
+    frames[1] = np.where(rng.random((H, W, 3)) < 0.5, 0, 255).astype(np.uint8)
+    raw = np.zeros((2, H, W), dtype=np.float16)
+    for w in (O.gaussian_weights(11, 9), O.gaussian_weights(19, 17)):
+        ctx = _ctx(H, W, 0.025, -0.01, 1, w)
+        ctx.set_option("blur_screen", screen)
+        sbs, _, infos, masks = _run_device(ctx, frames, raw)
+        want, _ = _oracle_run(oracle_lib, dict(fg=0.025, bg=-0.01, step=1), frames, raw, w)
+        assert infos[0].holes == H * W
+        for t in range(2):
+            assert np.array_equal(sbs[t], want[t]), (w.shape, screen, t, int((sbs[t] != want[t]).sum()))
+        ctx.close()

@@ -1,8 +1,9 @@
 #!/bin/bash
-# launch list + one full-set capture of the main kernels of one bench step (1080p_b64)
+# launch list + one full-set capture of the main kernels of one bench step: gpu_prof.sh TAG [WORKLOAD]
 mkdir -p gpurun_out
 TAG=${1:-r1x}
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1"
+WL=${2:-1080p_b64}
+CMD="python bench.py --workload $WL --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1"
 K='k_depth_pass|k_build_tables|k_warp_fused|k_warp_ws|k_blur_holes|k_blur_commit'
 timeout -k 10 600 $CMD > gpurun_out/plain.log 2>&1 &&
 timeout -k 10 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"$K" -s 15 -c 10 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launches.log 2>&1

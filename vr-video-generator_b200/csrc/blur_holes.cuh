@@ -137,15 +137,20 @@ __global__ void __launch_bounds__(256) k_blur_holes(BlurArgs a) {
 //   * interior words stage their footprint with aligned 32-bit loads (one or two per lane per row) and build the
 //     vertical pair sums on packed bytes (2 x 16-bit lanes per register);
 //   * hole positions come from a rank table instead of __fns.
+//   * screening: every hole is first evaluated with ONE multiply per tap, using h = floor(w * 2^S1) (S1 <= 24 so the
+//     sum fits 32 bits).  The exact total is that sum plus a remainder in [0, rmax] (rmax = 255 * sum of the dropped
+//     weight bits, computed on the host), so unless the fractional part lies within rmax below one half - or
+//     exactly on it, a possible tie - the rounded value is already decided.  Only the undecided lanes (0.1-0.3 %
+//     of the holes) run the exact PARTS-way sum.
 template <int PARTS, int CX, int CY>
-struct BlurWeights { uint32_t q[PARTS][(CY + 1) * (CX + 1)]; };
+struct BlurWeights { uint32_t q[PARTS][(CY + 1) * (CX + 1)]; uint32_t h[(CY + 1) * (CX + 1)]; uint32_t s1, rmax; };
 
 // list entries staged per warp before their holes are evaluated together (fewer for the large 4K footprint, whose
 // staging buffers would otherwise cost occupancy)
 template <int CX> __host__ __device__ constexpr int blur_group() { return CX <= 6 ? 4 : 2; }
 
 template <int PARTS, int CX, int CY>
-__global__ void __launch_bounds__(256) k_blur_holes_fixed(BlurArgs a, const __grid_constant__ BlurWeights<PARTS, CX, CY> wts) {
+__global__ void __launch_bounds__(256, 4) k_blur_holes_fixed(BlurArgs a, const __grid_constant__ BlurWeights<PARTS, CX, CY> wts) {
     constexpr int PBITS = PARTS == 2 ? 15 : 13;
     constexpr int KX = 2 * CX + 1, NPX = 32 + KX - 1;
     constexpr int PHASE = ((-3 * CX) % 4 + 4) % 4;                    // (96 w - 3 CX) mod 4: the same for every word
@@ -153,7 +158,9 @@ __global__ void __launch_bounds__(256) k_blur_holes_fixed(BlurArgs a, const __gr
     constexpr int COLS = (NWORDS * 4 + 7) / 8 * 8;                    // u16 columns per T row (16-byte multiple)
     constexpr int TSZ = (CY + 1) * COLS + 32;                         // u16 per staged entry: T rows + rank->bit table
     constexpr int G = blur_group<CX>();
+    constexpr bool PAIR = CY <= 5;                                    // row loads of two entries in flight (registers allow it)
     static_assert(NWORDS <= 64, "footprint wider than two words per lane");
+    static_assert(blur_group<CX>() % 2 == 0, "entries are staged in pairs");
     extern __shared__ __align__(16) uint8_t blur_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int W = a.W, H = a.H;
@@ -161,71 +168,111 @@ __global__ void __launch_bounds__(256) k_blur_holes_fixed(BlurArgs a, const __gr
     const uint32_t count = *a.hole_count;
     const size_t pitch = (size_t)W * 6;
 
-    for (uint32_t e0 = (blockIdx.x * nwarps + warp) * G; e0 < count; e0 += gridDim.x * nwarps * G) {
+    // entry metadata, one group ahead: lane g (< G) holds (list entry, mask with the strip columns removed) of entry
+    // e0 + g, so the list -> mask / strip load chain of the next group overlaps this group's staging and evaluation
+    auto fetch_meta = [&](uint32_t e0, uint32_t &ent, uint32_t &m) {
+        ent = 0u; m = 0u;
+        if (lane < G && e0 < count && e0 + lane < count) {
+            ent = a.hole_list[e0 + lane];
+            const uint32_t row = ent >> 8;
+            const int xw = (int)(ent & 0xffu) * 32;
+            const int strip = a.tabs[(int)(((unsigned long long)row * a.magic_h) >> 40)].strip;
+            m = a.hole_mask[(size_t)row * a.Wwords + (ent & 0xffu)];
+            if (strip > xw) m = (strip - xw >= 32) ? 0u : (m & ~((1u << (strip - xw)) - 1u));
+        }
+    };
+    const uint32_t stride = gridDim.x * nwarps * G;
+    uint32_t ent_n, m_n;
+    fetch_meta((blockIdx.x * nwarps + warp) * G, ent_n, m_n);
+    for (uint32_t e0 = (blockIdx.x * nwarps + warp) * G; e0 < count; e0 += stride) {
+        const uint32_t ent_c = ent_n, m_c = m_n;
+        fetch_meta(e0 + stride, ent_n, m_n);
         __syncwarp();
         // ---- stage up to G entries; remember (row, first pixel, phase) and the running task count of each ----
         uint32_t g_row[G], g_xw[G], g_phase[G], g_end[G];
         uint32_t tasks = 0;
+        // interior entries, two at a time: all row loads of both in flight before the pair sums are built
+        auto stage_interior_load = [&](const uint8_t *left, int y, int s0, uint32_t (&v)[2 * CY + 1]) {
+            const uint8_t *colp = left + (s0 - PHASE) + 4 * lane;
+            if ((y - CY >= 0) && (y + CY < H)) {
+                const uint8_t *p0 = colp + (size_t)(y - CY) * pitch;
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-            g_row[g] = 0; g_xw[g] = 0; g_phase[g] = 0; g_end[g] = tasks;
-            if (e0 + g >= count) continue;
-            const uint32_t ent = a.hole_list[e0 + g];
-            const uint32_t row = ent >> 8, w = ent & 0xffu;
-            const int b = (int)(((unsigned long long)row * a.magic_h) >> 40), y = (int)row - b * H;
-            const int strip = a.tabs[b].strip;
-            uint32_t m = a.hole_mask[(size_t)row * a.Wwords + w];
-            const int xw = (int)w * 32;
-            if (strip > xw) m = (strip - xw >= 32) ? 0u : (m & ~((1u << (strip - xw)) - 1u));
-            if (m == 0u) continue;
-            uint16_t *T = Tw + g * TSZ;
-            uint16_t *pos = T + (CY + 1) * COLS;
-            if ((m >> lane) & 1u) pos[__popc(m & ((1u << lane) - 1u))] = (uint16_t)lane;
-            const uint8_t *left = a.sbs + (size_t)b * H * pitch;
-            const int s0 = 3 * (xw - CX);                             // byte offset of the footprint in its row
-            if (xw - CX >= 0 && xw + 31 + CX < W) {
-                // interior columns: aligned words, packed vertical pair sums
-                g_phase[g] = PHASE;
-                const bool rows_in = (y - CY >= 0) && (y + CY < H);
+                for (int i = 0; i <= 2 * CY; ++i) v[i] = __ldg(reinterpret_cast<const uint32_t *>(p0 + (size_t)i * pitch));
+            } else {
 #pragma unroll
-                for (int half = 0; half < (NWORDS + 31) / 32; ++half) {
-                    const int k = lane + 32 * half;
-                    if (k < NWORDS) {
-                        const uint8_t *colp = left + (s0 - PHASE) + 4 * k;
-                        uint32_t v[2 * CY + 1];
-                        if (rows_in) {
-                            const uint8_t *p0 = colp + (size_t)(y - CY) * pitch;
+                for (int i = 0; i <= 2 * CY; ++i)
+                    v[i] = __ldg(reinterpret_cast<const uint32_t *>(colp + (size_t)reflect_idx(y + i - CY, H) * pitch));
+            }
+        };
+        auto stage_interior_store = [&](uint16_t *T, int k, const uint32_t (&v)[2 * CY + 1]) {
 #pragma unroll
-                            for (int i = 0; i <= 2 * CY; ++i) v[i] = __ldg(reinterpret_cast<const uint32_t *>(p0 + (size_t)i * pitch));
-                        } else {
+            for (int i = 0; i <= CY; ++i) {
+                const uint32_t p = v[CY - i], q = v[CY + i];
+                uint32_t lo = p & 0x00ff00ffu, hi = (p >> 8) & 0x00ff00ffu;
+                if (i) { lo += q & 0x00ff00ffu; hi += (q >> 8) & 0x00ff00ffu; }
+                *reinterpret_cast<uint2 *>(T + i * COLS + 4 * k) = make_uint2(__byte_perm(lo, hi, 0x5410), __byte_perm(lo, hi, 0x7632));
+            }
+        };
 #pragma unroll
-                            for (int i = 0; i <= 2 * CY; ++i)
-                                v[i] = __ldg(reinterpret_cast<const uint32_t *>(colp + (size_t)reflect_idx(y + i - CY, H) * pitch));
+        for (int g2 = 0; g2 < G; g2 += 2) {
+            uint32_t v0[2 * CY + 1], v1[2 * CY + 1];
+            bool inner[2] = {false, false};
+            int yy[2] = {0, 0}, ss[2] = {0, 0};
+            const uint8_t *lf[2] = {nullptr, nullptr};
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int g = g2 + h;
+                g_row[g] = 0; g_xw[g] = 0; g_phase[g] = 0; g_end[g] = tasks;
+                const uint32_t ent = __shfl_sync(0xffffffffu, ent_c, g), m = __shfl_sync(0xffffffffu, m_c, g);
+                if (m == 0u) continue;
+                const uint32_t row = ent >> 8, w = ent & 0xffu;
+                const int b = (int)(((unsigned long long)row * a.magic_h) >> 40), y = (int)row - b * H;
+                const int xw = (int)w * 32;
+                uint16_t *T = Tw + g * TSZ;
+                uint16_t *pos = T + (CY + 1) * COLS;
+                if ((m >> lane) & 1u) pos[__popc(m & ((1u << lane) - 1u))] = (uint16_t)lane;
+                const uint8_t *left = a.sbs + (size_t)b * H * pitch;
+                const int s0 = 3 * (xw - CX);                             // byte offset of the footprint in its row
+                if (xw - CX >= 0 && xw + 31 + CX < W) {
+                    g_phase[g] = PHASE;
+                    inner[h] = true; yy[h] = y; ss[h] = s0; lf[h] = left;
+                    if (h == 0) stage_interior_load(left, y, s0, v0); else stage_interior_load(left, y, s0, v1);
+                    if (!PAIR) {                                          // large footprint: one entry's rows in registers at a time
+                        stage_interior_store(T, lane, h == 0 ? v0 : v1);
+                        if (NWORDS > 32 && lane < NWORDS - 32) {
+                            uint32_t v2[2 * CY + 1];
+                            stage_interior_load(left + 128, y, s0, v2);
+                            stage_interior_store(T, lane + 32, v2);
                         }
+                        inner[h] = false;
+                    }
+                } else {
+                    // border words: byte by byte with reflect padding
+                    for (int c = lane; c < 3 * NPX; c += 32) {
+                        const int px = c / 3, ch = c - px * 3;
+                        const int X = min(max(reflect_idx(xw - CX + px, W), 0), W - 1);
+                        const uint8_t *colp = left + (size_t)X * 3 + ch;
+                        T[c] = colp[(size_t)y * pitch];
 #pragma unroll
-                        for (int i = 0; i <= CY; ++i) {
-                            const uint32_t p = v[CY - i], q = v[CY + i];
-                            uint32_t lo = p & 0x00ff00ffu, hi = (p >> 8) & 0x00ff00ffu;
-                            if (i) { lo += q & 0x00ff00ffu; hi += (q >> 8) & 0x00ff00ffu; }
-                            *reinterpret_cast<uint2 *>(T + i * COLS + 4 * k) = make_uint2(__byte_perm(lo, hi, 0x5410), __byte_perm(lo, hi, 0x7632));
-                        }
+                        for (int i = 1; i <= CY; ++i)
+                            T[i * COLS + c] = (uint16_t)colp[(size_t)reflect_idx(y - i, H) * pitch] + (uint16_t)colp[(size_t)reflect_idx(y + i, H) * pitch];
                     }
                 }
-            } else {
-                // border words: byte by byte with reflect padding
-                for (int c = lane; c < 3 * NPX; c += 32) {
-                    const int px = c / 3, ch = c - px * 3;
-                    const int X = min(max(reflect_idx(xw - CX + px, W), 0), W - 1);
-                    const uint8_t *colp = left + (size_t)X * 3 + ch;
-                    T[c] = colp[(size_t)y * pitch];
+                g_row[g] = row; g_xw[g] = (uint32_t)xw;
+                tasks += 3u * (uint32_t)__popc(m);
+                g_end[g] = tasks;
+            }
 #pragma unroll
-                    for (int i = 1; i <= CY; ++i)
-                        T[i * COLS + c] = (uint16_t)colp[(size_t)reflect_idx(y - i, H) * pitch] + (uint16_t)colp[(size_t)reflect_idx(y + i, H) * pitch];
+            for (int h = 0; h < 2; ++h) {
+                if (!inner[h]) continue;
+                uint16_t *T = Tw + (g2 + h) * TSZ;
+                if (h == 0) stage_interior_store(T, lane, v0); else stage_interior_store(T, lane, v1);
+                if (NWORDS > 32 && lane < NWORDS - 32) {                 // the few words past the 32nd: same lanes again
+                    uint32_t v2[2 * CY + 1];
+                    stage_interior_load(lf[h] + 128, yy[h], ss[h], v2);
+                    stage_interior_store(T, lane + 32, v2);
                 }
             }
-            g_row[g] = row; g_xw[g] = (uint32_t)xw;
-            tasks += 3u * (uint32_t)__popc(m);
-            g_end[g] = tasks;
         }
         __syncwarp();
         // ---- evaluate: task = (entry, hole rank, channel), 32 tasks per pass ----
@@ -245,25 +292,40 @@ __global__ void __launch_bounds__(256) k_blur_holes_fixed(BlurArgs a, const __gr
                 const uint16_t *T = Tw + g * TSZ;
                 const int xo = T[(CY + 1) * COLS + rank];
                 const uint16_t *Tc = T + phase + 3 * (xo + CX) + ch;
-                uint32_t acc[PARTS];
-#pragma unroll
-                for (int p = 0; p < PARTS; ++p) acc[p] = 0u;
+                uint32_t a1 = 0u;
 #pragma unroll
                 for (int i = 0; i <= CY; ++i) {
 #pragma unroll
                     for (int j = 0; j <= CX; ++j) {
                         const uint32_t v = j ? (uint32_t)Tc[i * COLS - 3 * j] + (uint32_t)Tc[i * COLS + 3 * j] : (uint32_t)Tc[i * COLS];
-#pragma unroll
-                        for (int p = 0; p < PARTS; ++p) acc[p] += v * wts.q[p][i * (CX + 1) + j];
+                        a1 += v * wts.h[i * (CX + 1) + j];
                     }
                 }
-                unsigned long long total = 0ull;
+                const uint32_t half1 = 1u << (wts.s1 - 1u), r1 = a1 & (2u * half1 - 1u);
+                uint32_t q = (a1 >> wts.s1) + (r1 > half1 ? 1u : 0u);
+                if (!(r1 > half1 || r1 + wts.rmax < half1)) {
+                    // undecided by the screening sum: exact total in PARTS 32-bit accumulators
+                    uint32_t acc[PARTS];
 #pragma unroll
-                for (int p = PARTS - 1; p >= 0; --p) total = (total << PBITS) + acc[p];
-                const int S = a.wshift;
-                unsigned long long q = total >> S;
-                const unsigned long long r = total & ((1ull << S) - 1ull), half = 1ull << (S - 1);
-                q += (r > half || (r == half && (q & 1ull))) ? 1ull : 0ull;
+                    for (int p = 0; p < PARTS; ++p) acc[p] = 0u;
+#pragma unroll 1
+                    for (int i = 0; i <= CY; ++i) {
+#pragma unroll
+                        for (int j = 0; j <= CX; ++j) {
+                            const uint32_t v = j ? (uint32_t)Tc[i * COLS - 3 * j] + (uint32_t)Tc[i * COLS + 3 * j] : (uint32_t)Tc[i * COLS];
+#pragma unroll
+                            for (int p = 0; p < PARTS; ++p) acc[p] += v * wts.q[p][i * (CX + 1) + j];
+                        }
+                    }
+                    unsigned long long total = 0ull;
+#pragma unroll
+                    for (int p = PARTS - 1; p >= 0; --p) total = (total << PBITS) + acc[p];
+                    const int S = a.wshift;
+                    unsigned long long qq = total >> S;
+                    const unsigned long long r = total & ((1ull << S) - 1ull), half = 1ull << (S - 1);
+                    qq += (r > half || (r == half && (qq & 1ull))) ? 1ull : 0ull;
+                    q = (uint32_t)qq;
+                }
                 a.plane[((size_t)row * W + xw + xo) * 3 + ch] = (uint8_t)q;
             }
         }

@@ -176,7 +176,9 @@ struct vrsbs_ctx {
     cudaStream_t st_in = nullptr, st_k = nullptr, st_out = nullptr;   // H2D / kernels / D2H of the host pipeline
     float *weights = nullptr;
     uint32_t *wq = nullptr;              // integer blur weights [parts][(ky/2+1)*(kx/2+1)]
-    std::vector<uint32_t> wq_host;
+    std::vector<uint32_t> wq_host, wh_host;   // exact parts / screening weights floor(w * 2^s1) of the integer blur
+    uint32_t ws1 = 1, wrmax = 2;
+    int blur_screen = 1;
     int kx = 0, ky = 0, wparts = 0, wshift = 0;
     int ent_cap = 0, lut_cap = 0;        // fast-path table capacities of the last vrsbs_build_tables
     int key_pad = 0;                     // fast path: bound on |signed layer offset| in pixels (multiple of 32)
@@ -539,6 +541,13 @@ template <int PARTS, int CX, int CY>
 int launch_blur_fixed(vrsbs_ctx *c, const BlurArgs &b, cudaStream_t st) {
     BlurWeights<PARTS, CX, CY> wts;
     memcpy(wts.q, c->wq_host.data(), sizeof(wts.q));
+    if (c->blur_screen) {
+        memcpy(wts.h, c->wh_host.data(), sizeof(wts.h));
+        wts.s1 = c->ws1; wts.rmax = c->wrmax;
+    } else {                                           // screening sum 0 is never decisive: every hole takes the exact path
+        memset(wts.h, 0, sizeof(wts.h));
+        wts.s1 = 1; wts.rmax = 2;
+    }
     auto kern = k_blur_holes_fixed<PARTS, CX, CY>;
     const size_t per_warp = blur_fixed_warp_smem<CX, CY>();
     const int warps = 8;
@@ -897,6 +906,26 @@ int vrsbs_set_blur_weights(vrsbs_ctx *c, const float *w, int kx, int ky) {
                     for (int p = 0; p < parts; ++p) { q[(size_t)p * nu + i * (cx + 1) + j] = (uint32_t)(v & ((1ull << pbits) - 1ull)); v >>= pbits; }
                 }
             c->wq_host = q;
+            // screening weights (blur_holes.cuh): h = floor(w * 2^s1) with 255 * sum(h) < 2^32, and the bound
+            // rmax >= (exact total - screening total) in units of 2^-s1
+            std::vector<uint32_t> hq(nu, 0u);
+            uint32_t s1 = 1, rmax = 2;
+            for (int t = S < 24 ? S : 24; t >= 2; --t) {
+                unsigned long long sum_h = 0, sum_r = 0;
+                const int drop = S - t;
+                for (int i = 0; i <= cy; ++i)
+                    for (int j = 0; j <= cx; ++j) {
+                        const unsigned long long v = (unsigned long long)ldexp((double)w[(cy - i) * kx + (cx - j)], S);
+                        const unsigned long long mult = (i ? 2ull : 1ull) * (j ? 2ull : 1ull);
+                        hq[i * (cx + 1) + j] = (uint32_t)(v >> drop);
+                        sum_h += mult * (v >> drop);
+                        sum_r += mult * (v & ((1ull << drop) - 1ull));
+                    }
+                const unsigned long long rm = ((255ull * sum_r) >> drop) + 1ull;
+                if (255ull * sum_h < (1ull << 32) && rm < (1ull << (t - 2))) { s1 = (uint32_t)t; rmax = (uint32_t)rm; break; }
+            }
+            if (s1 == 1) std::fill(hq.begin(), hq.end(), 0u);
+            c->wh_host = hq; c->ws1 = s1; c->wrmax = rmax;
             CU_TRY(c, dmalloc(&c->wq, q.size()));
             CU_TRY(c, cudaMemcpy(c->wq, q.data(), sizeof(uint32_t) * q.size(), cudaMemcpyHostToDevice));
             c->wparts = parts; c->wshift = S;
@@ -1149,6 +1178,7 @@ int vrsbs_set_option(vrsbs_ctx *c, const char *name, int value) {
     else if (!strcmp(name, "lowres_tiled")) c->lowres_tiled = value != 0;
     else if (!strcmp(name, "warp_ws")) c->warp_ws = value != 0;
     else if (!strcmp(name, "commit_mode")) c->commit_mode = value;
+    else if (!strcmp(name, "blur_screen")) c->blur_screen = value ? 1 : 0;
     else if (!strcmp(name, "ws_scatter_warps")) c->ws_scatter_warps = value;
     else return fail(c, VRSBS_E_INVALID, "unknown option %s", name);
     return VRSBS_OK;
