@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(256, 4) k_blur_holes_fixed(BlurArgs a, const _
     constexpr int COLS = (NWORDS * 4 + 7) / 8 * 8;                    // u16 columns per T row (16-byte multiple)
     constexpr int TSZ = (CY + 1) * COLS + 32;                         // u16 per staged entry: T rows + rank->bit table
     constexpr int G = blur_group<CX>();
+    constexpr int NP = CX > 6 ? 2 : 1;                                // pixels per evaluation lane (see "pair slots" below)
     constexpr bool PAIR = CY <= 5;                                    // row loads of two entries in flight (registers allow it)
     static_assert(NWORDS <= 64, "footprint wider than two words per lane");
     static_assert(blur_group<CX>() % 2 == 0, "entries are staged in pairs");
@@ -230,7 +231,11 @@ __global__ void __launch_bounds__(256, 4) k_blur_holes_fixed(BlurArgs a, const _
                 const int xw = (int)w * 32;
                 uint16_t *T = Tw + g * TSZ;
                 uint16_t *pos = T + (CY + 1) * COLS;
-                if ((m >> lane) & 1u) pos[__popc(m & ((1u << lane) - 1u))] = (uint16_t)lane;
+                // NP == 2, pair slots: pixels (2s, 2s+1) of the word are evaluated by one lane per channel (they share all
+                // but two of their taps); a slot is listed when either pixel is a hole.  NP == 1: one hole per lane.
+                const uint32_t pm = NP == 2 ? ((m | (m >> 1)) & 0x55555555u) : m;
+                if ((pm >> lane) & 1u) pos[__popc(pm & ((1u << lane) - 1u))] = (uint16_t)lane;
+                if (NP == 2 && lane == 0) { pos[16] = (uint16_t)(m & 0xffffu); pos[17] = (uint16_t)(m >> 16); }
                 const uint8_t *left = a.sbs + (size_t)b * H * pitch;
                 const int s0 = 3 * (xw - CX);                             // byte offset of the footprint in its row
                 if (xw - CX >= 0 && xw + 31 + CX < W) {
@@ -259,7 +264,7 @@ __global__ void __launch_bounds__(256, 4) k_blur_holes_fixed(BlurArgs a, const _
                     }
                 }
                 g_row[g] = row; g_xw[g] = (uint32_t)xw;
-                tasks += 3u * (uint32_t)__popc(m);
+                tasks += 3u * (uint32_t)__popc(pm);
                 g_end[g] = tasks;
             }
 #pragma unroll
@@ -290,21 +295,35 @@ __global__ void __launch_bounds__(256, 4) k_blur_holes_fixed(BlurArgs a, const _
                     if (g == k) { row = g_row[k]; xw = g_xw[k]; phase = g_phase[k]; }
                 const uint32_t rel = task - start, rank = rel / 3u, ch = rel - rank * 3u;
                 const uint16_t *T = Tw + g * TSZ;
-                const int xo = T[(CY + 1) * COLS + rank];
+                const uint16_t *pos = T + (CY + 1) * COLS;
+                const int xo = pos[rank];                                     // NP == 2: even, first pixel of the pair
+                const uint32_t mk = NP == 2 ? ((uint32_t)pos[16] | ((uint32_t)pos[17] << 16)) >> xo : 1u;   // bit o: pixel xo+o is a hole
                 const uint16_t *Tc = T + phase + 3 * (xo + CX) + ch;
-                uint32_t a1 = 0u;
+                // screening sums of the NP pixels: columns xo-CX .. xo+NP-1+CX of row i are read once
+                uint32_t a1[2] = {0u, 0u};
 #pragma unroll
                 for (int i = 0; i <= CY; ++i) {
+                    uint32_t u[2 * CX + NP];
+#pragma unroll
+                    for (int k = 0; k < 2 * CX + NP; ++k) u[k] = Tc[i * COLS + 3 * (k - CX)];
 #pragma unroll
                     for (int j = 0; j <= CX; ++j) {
-                        const uint32_t v = j ? (uint32_t)Tc[i * COLS - 3 * j] + (uint32_t)Tc[i * COLS + 3 * j] : (uint32_t)Tc[i * COLS];
-                        a1 += v * wts.h[i * (CX + 1) + j];
+                        const uint32_t hw = wts.h[i * (CX + 1) + j];
+#pragma unroll
+                        for (int o = 0; o < NP; ++o) a1[o] += (j ? u[CX + o - j] + u[CX + o + j] : u[CX + o]) * hw;
                     }
                 }
-                const uint32_t half1 = 1u << (wts.s1 - 1u), r1 = a1 & (2u * half1 - 1u);
-                uint32_t q = (a1 >> wts.s1) + (r1 > half1 ? 1u : 0u);
-                if (!(r1 > half1 || r1 + wts.rmax < half1)) {
-                    // undecided by the screening sum: exact total in PARTS 32-bit accumulators
+                const uint32_t half1 = 1u << (wts.s1 - 1u);
+                uint32_t q[2] = {0u, 0u};
+                bool open[2] = {false, false};
+#pragma unroll
+                for (int o = 0; o < NP; ++o) {
+                    const uint32_t r1 = a1[o] & (2u * half1 - 1u);
+                    q[o] = (a1[o] >> wts.s1) + (r1 > half1 ? 1u : 0u);
+                    open[o] = ((mk >> o) & 1u) && !(r1 > half1 || r1 + wts.rmax < half1);
+                }
+                // undecided by the screening sum: exact total in PARTS 32-bit accumulators
+                auto exact = [&](const uint16_t *To) {
                     uint32_t acc[PARTS];
 #pragma unroll
                     for (int p = 0; p < PARTS; ++p) acc[p] = 0u;
@@ -312,7 +331,7 @@ __global__ void __launch_bounds__(256, 4) k_blur_holes_fixed(BlurArgs a, const _
                     for (int i = 0; i <= CY; ++i) {
 #pragma unroll
                         for (int j = 0; j <= CX; ++j) {
-                            const uint32_t v = j ? (uint32_t)Tc[i * COLS - 3 * j] + (uint32_t)Tc[i * COLS + 3 * j] : (uint32_t)Tc[i * COLS];
+                            const uint32_t v = j ? (uint32_t)To[i * COLS - 3 * j] + (uint32_t)To[i * COLS + 3 * j] : (uint32_t)To[i * COLS];
 #pragma unroll
                             for (int p = 0; p < PARTS; ++p) acc[p] += v * wts.q[p][i * (CX + 1) + j];
                         }
@@ -324,9 +343,41 @@ __global__ void __launch_bounds__(256, 4) k_blur_holes_fixed(BlurArgs a, const _
                     unsigned long long qq = total >> S;
                     const unsigned long long r = total & ((1ull << S) - 1ull), half = 1ull << (S - 1);
                     qq += (r > half || (r == half && (qq & 1ull))) ? 1ull : 0ull;
-                    q = (uint32_t)qq;
+                    return (uint32_t)qq;
+                };
+                if (NP == 2) {
+                    // (written out rather than calling `exact`: ptxas keeps everything in registers this way)
+#pragma unroll 1
+                    for (int o = 0; o < 2; ++o) {
+                        if (!(o ? open[1] : open[0])) continue;
+                        const uint16_t *To = Tc + 3 * o;
+                        uint32_t acc[PARTS];
+#pragma unroll
+                        for (int p = 0; p < PARTS; ++p) acc[p] = 0u;
+#pragma unroll 1
+                        for (int i = 0; i <= CY; ++i) {
+#pragma unroll
+                            for (int j = 0; j <= CX; ++j) {
+                                const uint32_t v = j ? (uint32_t)To[i * COLS - 3 * j] + (uint32_t)To[i * COLS + 3 * j] : (uint32_t)To[i * COLS];
+#pragma unroll
+                                for (int p = 0; p < PARTS; ++p) acc[p] += v * wts.q[p][i * (CX + 1) + j];
+                            }
+                        }
+                        unsigned long long total = 0ull;
+#pragma unroll
+                        for (int p = PARTS - 1; p >= 0; --p) total = (total << PBITS) + acc[p];
+                        const int S = a.wshift;
+                        unsigned long long qq = total >> S;
+                        const unsigned long long r = total & ((1ull << S) - 1ull), half = 1ull << (S - 1);
+                        qq += (r > half || (r == half && (qq & 1ull))) ? 1ull : 0ull;
+                        if (o) q[1] = (uint32_t)qq; else q[0] = (uint32_t)qq;
+                    }
+                } else if (open[0]) {
+                    q[0] = exact(Tc);
                 }
-                a.plane[((size_t)row * W + xw + xo) * 3 + ch] = (uint8_t)q;
+                uint8_t *dst = a.plane + ((size_t)row * W + xw + xo) * 3 + ch;
+                if (mk & 1u) dst[0] = (uint8_t)q[0];
+                if (NP == 2 && (mk & 2u)) dst[3] = (uint8_t)q[1];
             }
         }
     }
