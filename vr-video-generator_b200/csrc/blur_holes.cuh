@@ -207,11 +207,35 @@ __global__ void __launch_bounds__(256, 4) k_blur_holes_fixed(BlurArgs a, const _
         };
         auto stage_interior_store = [&](uint16_t *T, int k, const uint32_t (&v)[2 * CY + 1]) {
 #pragma unroll
-            for (int i = 0; i <= CY; ++i) {
+            for (int i = 0; i <= CY; ++i) {                              // bytes -> u16 lanes, pair sums on two packed u16 each
                 const uint32_t p = v[CY - i], q = v[CY + i];
-                uint32_t lo = p & 0x00ff00ffu, hi = (p >> 8) & 0x00ff00ffu;
-                if (i) { lo += q & 0x00ff00ffu; hi += (q >> 8) & 0x00ff00ffu; }
-                *reinterpret_cast<uint2 *>(T + i * COLS + 4 * k) = make_uint2(__byte_perm(lo, hi, 0x5410), __byte_perm(lo, hi, 0x7632));
+                if (PAIR) {                                              // measured: PRMT expansion wins at 1080p, mask/shift at 4K
+                    uint32_t lo = __byte_perm(p, 0u, 0x4140), hi = __byte_perm(p, 0u, 0x4342);
+                    if (i) { lo += __byte_perm(q, 0u, 0x4140); hi += __byte_perm(q, 0u, 0x4342); }
+                    *reinterpret_cast<uint2 *>(T + i * COLS + 4 * k) = make_uint2(lo, hi);
+                } else {
+                    uint32_t lo = p & 0x00ff00ffu, hi = (p >> 8) & 0x00ff00ffu;
+                    if (i) { lo += q & 0x00ff00ffu; hi += (q >> 8) & 0x00ff00ffu; }
+                    *reinterpret_cast<uint2 *>(T + i * COLS + 4 * k) = make_uint2(__byte_perm(lo, hi, 0x5410), __byte_perm(lo, hi, 0x7632));
+                }
+            }
+        };
+        // the few words past the 32nd (wide footprints): (word, row pair) tasks spread over the lanes
+        auto stage_interior_tail = [&](uint16_t *T, const uint8_t *left, int y, int s0) {
+            constexpr int TAILN = (NWORDS > 32 ? NWORDS - 32 : 0) * (CY + 1);
+#pragma unroll
+            for (int tt = 0; tt < (TAILN + 31) / 32; ++tt) {
+                const int t = lane + 32 * tt;
+                if (t >= TAILN) continue;
+                const int wd = t / (CY + 1), i = t - wd * (CY + 1);
+                const uint8_t *colp = left + (s0 - PHASE) + 4 * (32 + wd);
+                const uint32_t p = __ldg(reinterpret_cast<const uint32_t *>(colp + (size_t)reflect_idx(y - i, H) * pitch));
+                uint32_t lo = __byte_perm(p, 0u, 0x4140), hi = __byte_perm(p, 0u, 0x4342);
+                if (i) {
+                    const uint32_t q = __ldg(reinterpret_cast<const uint32_t *>(colp + (size_t)reflect_idx(y + i, H) * pitch));
+                    lo += __byte_perm(q, 0u, 0x4140); hi += __byte_perm(q, 0u, 0x4342);
+                }
+                *reinterpret_cast<uint2 *>(T + i * COLS + 4 * (32 + wd)) = make_uint2(lo, hi);
             }
         };
 #pragma unroll
@@ -272,11 +296,7 @@ __global__ void __launch_bounds__(256, 4) k_blur_holes_fixed(BlurArgs a, const _
                 if (!inner[h]) continue;
                 uint16_t *T = Tw + (g2 + h) * TSZ;
                 if (h == 0) stage_interior_store(T, lane, v0); else stage_interior_store(T, lane, v1);
-                if (NWORDS > 32 && lane < NWORDS - 32) {                 // the few words past the 32nd: same lanes again
-                    uint32_t v2[2 * CY + 1];
-                    stage_interior_load(lf[h] + 128, yy[h], ss[h], v2);
-                    stage_interior_store(T, lane + 32, v2);
-                }
+                if (NWORDS > 32) stage_interior_tail(T, lf[h], yy[h], ss[h]);
             }
         }
         __syncwarp();
