@@ -2,12 +2,16 @@
 //
 // k_warp_fused runs scatter -> CTA barrier -> destination pass -> CTA barrier per row; ~40 % of its stall samples
 // are warps parked at those two barriers (profiles/r01k).  Here the CTA is split into NS scatter warps and ND
-// destination warps that meet only through mbarriers around a DOUBLE-BUFFERED key row:
+// destination warps that meet only through split arrive / sync barriers around a DOUBLE-BUFFERED key row:
 //
-//   scatter warps, row n:  wait in_full[n%3] (TMA data) and k_empty[n&1]  ->  atomicMax keys into keys[n&1]
+//   scatter warps, row n:  wait in_full[n%3] (TMA data, mbarrier) and k_empty[n&1]  ->  atomicMax keys into keys[n&1]
 //                          ->  arrive k_full[n&1]                     (and go straight on to row n+1)
 //   destination warps:     wait in_full[n%3] and k_full[n&1]  ->  read + re-zero keys[n&1], fill holes, pack the
 //                          row  ->  bulk stores  ->  arrive k_empty[n&1]  ->  mask flush, TMA loads of row n+2
+//
+// k_full / k_empty are hardware named barriers (bar.arrive by the producer group, bar.sync by the consumer group):
+// a parked consumer issues nothing, whereas mbarrier try_wait loops spent 23 % of the kernel's issue slots on
+// polling (profiles/r01q).
 //
 // so a slow warp delays only its own group, and the scatter of row n+1 overlaps the destination pass of row n.
 // Smoothed depth in (the depth pass materialises it); frames whose tables did not validate take the same
@@ -25,6 +29,7 @@ struct WsLay {               // shared-memory layout of k_warp_ws as kernel para
     uint32_t img, img_stride, dep, dep_stride, out, keys, keys_stride, blob, blob_stride, mask, bars, total;
 };
 constexpr int kWsImgSlots = 3, kWsDepSlots = 3;
+constexpr int kBarFull = 2, kBarEmpty = 4;      // named barriers 2,3: key row complete; 4,5: key row free again (1: destination group)
 
 __host__ inline WsLay ws_smem_layout(int W, uint32_t blob_b) {
     WsLay s{};
@@ -35,7 +40,7 @@ __host__ inline WsLay ws_smem_layout(int W, uint32_t blob_b) {
     s.keys = (uint32_t)o; s.keys_stride = (uint32_t)align_up((size_t)W * 4, 128);      o += 2 * s.keys_stride;
     s.blob = (uint32_t)o; s.blob_stride = (uint32_t)align_up((size_t)blob_b, 128);     o += 2 * s.blob_stride;
     s.mask = (uint32_t)o; o += align_up((size_t)((W + 31) / 32) * 4, 16);
-    s.bars = (uint32_t)o; o += 8 * 7;                    // in_full[3], k_full[2], k_empty[2]
+    s.bars = (uint32_t)o; o += 8 * 4;                    // in_full[3]
     s.total = (uint32_t)align_up(o, 16);
     return s;
 }
@@ -48,21 +53,25 @@ struct WsArgs {
 __device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// mbarrier wait that sleeps between polls: in k_warp_ws a waiting group would otherwise spend issue slots the
-// working group needs (profiles/r01l: 14 % of all executed instructions were try_wait polls)
+// mbarrier wait for a group that may be parked for a whole row time: a plain try_wait loop re-polls every few hundred
+// cycles and a waiting group then spends issue slots the working group needs (profiles/r01o: 19 % of all executed
+// warp-instructions were wait-loop polls).  try_wait's suspend-time hint lets the hardware park the thread until the
+// phase completes (or the hint expires), so a wait costs a handful of instructions.
+#ifndef VRSBS_WS_WAIT_HINT_NS
+#define VRSBS_WS_WAIT_HINT_NS 4000
+#endif
 __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
         "WAIT_%=:\n\t"
-        "nanosleep.u32 %2;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@!p bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity), "r"(40u) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@!p bra WAIT_%=;\n\t}" ::"r"(bar), "r"(parity), "r"((uint32_t)VRSBS_WS_WAIT_HINT_NS) : "memory");
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 template <int NT, int NS>
@@ -72,7 +81,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_ws(WsArgs wa) {
     constexpr int NW = NT / 32, ND = NW - NS, NDT = ND * 32;
     const uint32_t sb = smem_u32(smem);
     const uint32_t sa_out = sb + wa.lay.out, sa_mask = sb + wa.lay.mask, sa_bars = sb + wa.lay.bars;
-    const uint32_t bar_in = sa_bars, bar_kfull = sa_bars + 24u, bar_kempty = sa_bars + 40u;
+    const uint32_t bar_in = sa_bars;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = a.W, H = a.H, B = a.B;
@@ -89,8 +98,6 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_ws(WsArgs wa) {
     if (tid == 0) {
         uint64_t *bars = reinterpret_cast<uint64_t *>(smem + wa.lay.bars);
         for (int i = 0; i < 3; ++i) mbar_init(bars + i, 1);              // in_full: one expect_tx arrival + bytes
-        for (int i = 0; i < 2; ++i) mbar_init(bars + 3 + i, NS);         // k_full: one arrival per scatter warp
-        for (int i = 0; i < 2; ++i) mbar_init(bars + 5 + i, 1);          // k_empty: the destination group's elected thread
         fence_mbar_init();
     }
     __syncthreads();
@@ -116,7 +123,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_ws(WsArgs wa) {
             const uint32_t sa_cur = sb + wa.lay.dep + (uint32_t)i3 * wa.lay.dep_stride;
             const uint32_t sa_img = sb + wa.lay.img + (uint32_t)i3 * wa.lay.img_stride + 4u * (uint32_t)wofs;
             mbar_wait_sleep(bar_in + 8u * (uint32_t)i3, par3);
-            mbar_wait_sleep(bar_kempty + 8u * b, (((uint32_t)n >> 1) & 1u) ^ 1u);
+            if (n >= 2) named_bar_sync(kBarEmpty + (int)b, NS * 32 + 32);   // keys[b] re-zeroed by the destination pass of row n-2
             const uint4 hdrw = lds_u128(sa_blob);
             if (hdrw.w & 1u) {
                 const uint32_t sa_ent = sa_blob + 16u, sa_lut = sa_ent + a.ent_bytes;
@@ -201,7 +208,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_ws(WsArgs wa) {
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive_a(bar_kfull + 8u * b);
+            named_bar_arrive(kBarFull + (int)b, NT);                       // keys[b] complete (orders this warp's atomics)
             if (++i3 == 3) { i3 = 0; par3 ^= 1u; }
             next_yt(y0, t0);
         }
@@ -234,7 +241,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_ws(WsArgs wa) {
             const uint4 hdrw = lds_u128(sa_blob);
             const bool fast = hdrw.w & 1u;
             const int fill = (int)hdrw.x;
-            mbar_wait_sleep(bar_kfull + 8u * b, ((uint32_t)n >> 1) & 1u);
+            named_bar_sync(kBarFull + (int)b, NT);                         // parked in hardware until every scatter warp has arrived
             if (elect) bulk_wait_read0();                 // the previous row's bulk stores have finished reading out / img slots
             named_bar_sync(1, NDT);
             // row n+2 goes into the slots of row n-1 (scattered, packed, and - the barrier above - read by its stores) and into
@@ -289,8 +296,9 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_ws(WsArgs wa) {
                 bulk_s2g_a(go, sa_out, img_bytes);
                 bulk_s2g_a(go + img_bytes, sa_imgrow, img_bytes);
                 bulk_commit();
-                mbar_arrive_a(bar_kempty + 8u * b);       // keys[b] is zero again
             }
+            __syncwarp();
+            if (dt < 32 && n + 2 < N) named_bar_arrive(kBarEmpty + (int)b, NS * 32 + 32);   // keys[b] is zero again (scatter of row n+2 waits for it)
             // hole mask row -> global bitmask + blur work list (first ceil(Wwords/32) destination warps)
             if (dt < ((Wwords + 31) & ~31)) {
                 const int w = dt;
