@@ -390,6 +390,13 @@ def test_dropin_sbs_processor(oracle_lib):
         assert out.dtype == np.uint8 and out.shape == (p["H"], 2 * p["W"], 3)
         assert np.array_equal(out[:, :p["W"]], ref_left[t]) and np.array_equal(out[:, p["W"]:], frames[t])
         assert proc.last_offset_range == unhex(meta["frames"][t]["range"])
+    # the depth may also stay on the device (a producer in the same process)
+    proc3 = pkg.SbsProcessor(notify, 1, args)
+    for t in range(p["n"]):
+        res.put(torch.from_numpy(raw[t]).cuda())
+        out = proc3.left_side_sbs(frames[t], jobs, res)
+        assert np.array_equal(out[:, :p["W"]], ref_left[t]) and np.array_equal(out[:, p["W"]:], frames[t])
+    proc3.close()
     # get_depth / get_cutoff as separate calls, on a fresh processor
     proc2 = pkg.SbsProcessor(notify, 0, args)
     res.put(torch.from_numpy(raw[0]))
@@ -561,3 +568,51 @@ def test_blur_screening_is_exact(screen, oracle_lib):
         for t in range(2):
             assert np.array_equal(sbs[t], want[t]), (w.shape, screen, t, int((sbs[t] != want[t]).sum()))
         ctx.close()
+
+
+def test_full_batch_properties_1080p(oracle_lib):
+    """BASELINE.json configs[1] at its full size (64 frames of 1080p in one launch), checked through properties
+    that do not need the oracle at that size: the result does not depend on how the clip is cut into batches
+    (64 = 40 + 24 = 64 x 1), the right half and the strip are the input, hole counts equal the mask popcounts,
+    non-hole pixels of the view are source pixels of the same row; three sampled frames are compared with the
+    oracle byte for byte (the oracle needs the whole depth history, so it walks frames 0..5 and 0..2 only)."""
+    from vr_video_generator_b200 import synth
+    n, H, W = 64, 1080, 1920
+    fg, bg, step = 0.025, -0.01, 1
+    frames = synth.frames_noise(8, H, W, 3)
+    frames = np.ascontiguousarray(np.concatenate([frames] * (n // 8)))
+    ctx0 = _ctx(H, W, fg, bg, step, max_batch=n)
+    lo = torch.from_numpy(synth.depth_lowres("scene", n, seed=3)).cuda()
+    raw_t = torch.empty((n, H, W), dtype=torch.float16, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    ctx0.depth_from_lowres(lo.data_ptr(), n, synth.DPT_H, synth.DPT_W, 1.0, H, W, raw_t.data_ptr(), s)
+    torch.cuda.synchronize()
+    ctx0.close()
+    # depth_from_lowres smooths too; use its output as the RAW depth of this test (any fp16 field will do)
+    raw = raw_t.cpu().numpy()
+    del raw_t, lo
+    outs = []
+    for splits in ([n], [40, 24], [1] * n):
+        ctx = _ctx(H, W, fg, bg, step, max_batch=n)
+        sbs, _, infos, masks = _run_device(ctx, frames, raw, splits)
+        outs.append(sbs)
+        if len(outs) == 1:
+            info0, masks0 = infos, masks
+        ctx.close()
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    sbs = outs[0]
+    assert np.array_equal(sbs[:, :, W:], frames)
+    for t in range(n):
+        strip = info0[t].strip
+        assert strip > 0 and np.array_equal(sbs[t, :, :strip], frames[t, :, :strip])
+        assert int(masks0[t].sum()) == info0[t].holes
+    # painted pixels are source pixels of the same row: every non-hole byte triple of a row occurs in the input row
+    t, y = 17, 501
+    bits = masks0[t].astype(bool)
+    row_px = set(map(bytes, frames[t, y]))
+    assert all(bytes(px) in row_px for px in sbs[t, y, :W][~bits[y]])
+    # oracle on the first frames (full history available)
+    w = O.gaussian_weights(*O.blur_kernel_shape(H))
+    want, _ = _oracle_run(oracle_lib, dict(fg=fg, bg=bg, step=step), frames[:3], raw[:3], w)
+    for k in range(3):
+        assert np.array_equal(sbs[k], want[k]), (k, int((sbs[k] != want[k]).sum()))

@@ -98,12 +98,25 @@ class SbsProcessor:
         return out
 
     def left_side_sbs(self, raw_img, job_queue, result_queue):
-        """numpy [H,W,3] uint8 RGB -> numpy [H,2W,3] uint8 SBS frame (PredictAndGenerate.py:157-198)."""
+        """numpy [H,W,3] uint8 RGB -> numpy [H,2W,3] uint8 SBS frame (PredictAndGenerate.py:157-198).
+        The depth popped from `result_queue` is a CPU tensor in the reference (inference_worker does `.to('cpu')`,
+        :55-56): that case goes through the host pipeline (pinned staging, only the synthesised half crosses PCIe
+        on the way back).  A CUDA depth tensor is used where it is."""
         H, W, _ = raw_img.shape
         ctx = self._context(H, W)
+        raw = result_queue.get()
+        if not (isinstance(raw, torch.Tensor) and raw.is_cuda):
+            d = _as_numpy(raw)
+            if d.dtype != np.float16:
+                raise TypeError(f"depth must be float16 (the producer's autocast dtype), got {d.dtype}")
+            if d.shape != (H, W):
+                raise ValueError(f"depth {d.shape} does not match the frame {(H, W)}")
+            out = np.empty((H, 2 * W, 3), dtype=np.uint8)
+            f = np.ascontiguousarray(raw_img)
+            ctx.process_host(f.ctypes.data, d.ctypes.data, 1, H, W, 0, 0, 1.0, out.ctypes.data)
+            return out
         with torch.cuda.device(self.device):
             img = torch.from_numpy(np.ascontiguousarray(raw_img)).to(self.device, non_blocking=True)
-            raw = result_queue.get()
             depth = self._smooth(self._raw_to_device(raw))
             st = self._stream()
             ctx.build_tables(1, H, W, st)
