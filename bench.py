@@ -56,14 +56,38 @@ def measured_hbm_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons of this rank's GPU, sampled every 50 ms during the timed regions (the quantities of
+    the B200_PROFILING.md nvidia-smi recipe: clocks.sm, clocks.max.sm, clocks_event_reasons.*).  Read through NVML in
+    this process: one `nvidia-smi -lms` child per rank spends about a second attaching to every GPU of the box right
+    when the timed region starts, and on an 8-GPU box that showed up as 8 % longer steps at N > 1.  Falls back to the
+    nvidia-smi child when pynvml is missing."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self.handle = index, [], None, None, None
+        self.stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if visible:
+                ids = [v.strip() for v in visible.split(",") if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
     def __enter__(self):
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -74,12 +98,30 @@ class ClockSampler:
             self.proc = None
         return self
 
+    def _poll(self):
+        n = self.nvml
+        bits = [(getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8), "hw_slowdown"),
+                (getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40), "hw_thermal_slowdown"),
+                (getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), "sw_thermal_slowdown"),
+                (getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4), "sw_power_cap")]
+        while not self.stop.is_set():
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                self.rows.append([str(sm), str(self.max_sm)] + ["Active" if mask & b else "Not Active" for b, _ in bits])
+            except Exception:
+                pass
+            self.stop.wait(0.05)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def __exit__(self, *a):
-        if self.proc:
+        if self.nvml is not None:
+            self.stop.set()
+            self.thread.join(timeout=2)
+        elif self.proc:
             time.sleep(0.15)
             self.proc.terminate()
             self.thread.join(timeout=2)
@@ -87,10 +129,9 @@ class ClockSampler:
     def summary(self):
         sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i] == "Active" for r in self.rows)]
+        reasons = [n for i, n in enumerate(self.NAMES) if any(len(r) >= 6 and r[2 + i] == "Active" for r in self.rows)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def make_inputs(wl, seed):
@@ -128,7 +169,10 @@ def run_ours(args, wl, name):
     dev = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(dev)
     H, W, B = wl["H"], wl["W"], wl["B"]
-    frames_h, lowres_h = make_inputs(wl, seed=100 + rank)        # every rank = its own clip range
+    # every rank = its own clip range with its own state; the CONTENT is the same seeded clip on every rank, so that
+    # the work per GPU is fixed as N grows (weak scaling) - hole counts, and with them the blur time, vary by ~10 %
+    # between seeds and the job time is the max over ranks
+    frames_h, lowres_h = make_inputs(wl, seed=100)
 
     ctx = _native.Context(dev, H, W, B, 512)
     ctx.reset(wl["fg"], wl["bg"], wl["step"], True)
@@ -178,18 +222,22 @@ def run_ours(args, wl, name):
     ctx.set_option("stage_timing", 1)
     launches0 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clocks = ClockSampler(dev)               # NVML attach happens here, outside the timed region
     barrier()
     torch.cuda.synchronize()
-    clocks = ClockSampler(dev)
     clocks.__enter__()                       # sampled over the device-timed region AND the e2e region
     time.sleep(0.25)
     e0.record()
+    t_host = time.perf_counter()
     for _ in range(args.steps):
         step()
     e1.record()
+    host_issue_ms = (time.perf_counter() - t_host) * 1e3 / args.steps      # CPU time to issue one step (launch bound if ~ ms_per_step)
     torch.cuda.synchronize()
     barrier()
-    ms_total = reduce_max(e0.elapsed_time(e1))
+    ms_rank = e0.elapsed_time(e1)
+    ms_total = reduce_max(ms_rank)
+    per_rank = ranks.gather({"rank": rank, "ms_per_step": ms_rank / args.steps, "host_issue_ms_per_step": host_issue_ms})
     stage = ctx.stage_times()
     ctx.set_option("stage_timing", 0)
     launches = ctx.launch_count() - launches0
@@ -304,9 +352,9 @@ def run_ours(args, wl, name):
                        "timed_region": "depth smoothing+max pass, device tables, warp+fill+pack, hole blur, commit+strip; inputs/outputs in HBM",
                        "l2": f"inputs per step {int((frames_h.nbytes + raw_h.nbytes) / 2**20)} MiB + outputs "
                              f"{int(o_np.nbytes / 2**20)} MiB per GPU > 126 MB L2 (no flush needed)",
-                       "sharding": "independent clip range per GPU, no collective", "depth_input": args.depth_input,
+                       "sharding": "independent clip range per GPU (same seeded content on every rank: fixed work per GPU), no collective", "depth_input": args.depth_input,
                        "route": f"general row kernel (scatter_mode={args.scatter_mode})" if args.scatter_mode else "default (k_depth_pass, k_build_tables, k_warp_ws, k_blur_holes_fixed, k_blur_commit)"},
-            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "per_rank": per_rank,
             "roofline": {"bound": "hbm", "kernel": "k_warp_rows" if args.scatter_mode else ("k_warp_ws" if W % 32 == 0 and W <= 2048 else "k_warp_fused"), "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": abytes, "launch_ms": warp_ms / max(warp_n, 1)},
