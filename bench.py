@@ -243,7 +243,7 @@ def run_ours(args, wl, name):
     launches = ctx.launch_count() - launches0
     value = world * B * args.steps / (ms_total * 1e-3)
 
-    # roofline of the dominant kernel (k_warp_rows): algorithmic bytes per launch / mean launch duration
+    # roofline of the dominant kernel (the warp stage): algorithmic bytes per launch / mean launch duration
     warp_ms, warp_n = stage["warp"]
     peak, peak_src = measured_hbm_peak()
     abytes = algorithmic_bytes(H, W) * B
@@ -355,7 +355,7 @@ def run_ours(args, wl, name):
                        "sharding": "independent clip range per GPU (same seeded content on every rank: fixed work per GPU), no collective", "depth_input": args.depth_input,
                        "route": f"general row kernel (scatter_mode={args.scatter_mode})" if args.scatter_mode else "default (k_depth_pass, k_build_tables, k_warp_ws, k_blur_holes_fixed, k_blur_commit)"},
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "per_rank": per_rank,
-            "roofline": {"bound": "hbm", "kernel": "k_warp_rows" if args.scatter_mode else ("k_warp_ws" if W % 32 == 0 and W <= 2048 else "k_warp_fused"), "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_warp_rows" if args.scatter_mode else ("k_warp_ws" if W % 32 == 0 else "k_warp_fused"), "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": abytes, "launch_ms": warp_ms / max(warp_n, 1)},
             "stage_ms_per_step": {k: v[0] / args.steps for k, v in stage.items()},
