@@ -173,6 +173,13 @@ def run_ours(args, wl, name):
     # the work per GPU is fixed as N grows (weak scaling) - hole counts, and with them the blur time, vary by ~10 %
     # between seeds and the job time is the max over ranks
     frames_h, lowres_h = make_inputs(wl, seed=100)
+    binding = None
+    if not args.no_bind:
+        from vr_video_generator_b200 import shard
+        pr = torch.cuda.get_device_properties(dev)
+        bdf = "%04x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), getattr(pr, "pci_bus_id", 0), getattr(pr, "pci_device_id", 0))
+        cpus = shard.bind_near_gpu(bdf)
+        binding = f"{bdf}: {len(cpus)} local cpus" if cpus else f"{bdf}: unchanged ({len(os.sched_getaffinity(0))} cpus)"
 
     ctx = _native.Context(dev, H, W, B, 512)
     ctx.reset(wl["fg"], wl["bg"], wl["step"], True)
@@ -352,7 +359,7 @@ def run_ours(args, wl, name):
                        "timed_region": "depth smoothing+max pass, device tables, warp+fill+pack, hole blur, commit+strip; inputs/outputs in HBM",
                        "l2": f"inputs per step {int((frames_h.nbytes + raw_h.nbytes) / 2**20)} MiB + outputs "
                              f"{int(o_np.nbytes / 2**20)} MiB per GPU > 126 MB L2 (no flush needed)",
-                       "sharding": "independent clip range per GPU (same seeded content on every rank: fixed work per GPU), no collective", "depth_input": args.depth_input,
+                       "sharding": "independent clip range per GPU (same seeded content on every rank: fixed work per GPU), no collective", "depth_input": args.depth_input, "cpu_binding": binding,
                        "route": f"general row kernel (scatter_mode={args.scatter_mode})" if args.scatter_mode else "default (k_depth_pass, k_build_tables, k_warp_ws, k_blur_holes_fixed, k_blur_commit)"},
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "per_rank": per_rank,
             "roofline": {"bound": "hbm", "kernel": "k_warp_rows" if args.scatter_mode else ("k_warp_ws" if W % 32 == 0 else "k_warp_fused"), "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -451,6 +458,7 @@ def main():
     ap.add_argument("--depth-input", default="full", choices=["full", "lowres"],
                     help="full: raw full-resolution fp16 depth (the metric's config); lowres: DPT-resolution map, bicubic on the device")
     ap.add_argument("--host-chunk", type=int, default=0)
+    ap.add_argument("--no-bind", action="store_true", help="do not bind the process to the CPUs local to its GPU")
     ap.add_argument("--video-frames", type=int, default=0,
                     help="also stream an N-frame synthetic video (e.g. 18000 = 10 min of 1080p30), sharded by clip range over the ranks")
     ap.add_argument("--host-opt", action="append", default=[], help="library option name=value for the host-API context")

@@ -95,3 +95,27 @@ def test_worker_control_flow_matches_reference(begin, end, length, max_count, mi
             # RGB order after the [2,1,0] swap: R=9, G=7, B=index (black frame where the read failed)
             exp = (0, 0, 0) if i < 0 else (9, 7, i % 251)
             assert tuple(sbs[k, 0, 0]) == exp and tuple(sbs[k, 0, W]) == exp
+
+
+def test_bind_near_gpu_uses_sysfs_local_cpulist(tmp_path):
+    """NUMA placement helper: parses the sysfs cpulist, intersects it with the CPUs this process may use, and leaves
+    the affinity alone when sysfs has no entry or too few local CPUs are available."""
+    import os
+    from vr_video_generator_b200 import shard
+    assert shard.parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert shard.parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    try:
+        assert shard.bind_near_gpu("0000:ff:00.0", sysfs=str(tmp_path)) is None          # no such device
+        dev = tmp_path / "0000:1b:00.0"
+        dev.mkdir()
+        (dev / "local_cpulist").write_text("100000-100003\n")                            # CPUs we do not have
+        assert shard.bind_near_gpu("0000:1B:00.0", sysfs=str(tmp_path)) is None
+        assert os.sched_getaffinity(0) == before
+        if len(before) >= 3:
+            keep = sorted(before)[:2]
+            (dev / "local_cpulist").write_text(",".join(map(str, keep)) + "\n")
+            assert shard.bind_near_gpu("0000:1b:00.0", min_cpus=2, sysfs=str(tmp_path)) == set(keep)
+            assert os.sched_getaffinity(0) == set(keep)
+    finally:
+        os.sched_setaffinity(0, before)

@@ -18,6 +18,41 @@ def world_from_env():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
+def parse_cpulist(text):
+    """'0-3,8,10-11' -> {0,1,2,3,8,10,11} (the sysfs cpulist format)."""
+    cpus = set()
+    for part in text.strip().split(","):
+        part = part.strip()
+        if not part:
+            continue
+        if "-" in part:
+            a, b = part.split("-", 1)
+            cpus.update(range(int(a), int(b) + 1))
+        else:
+            cpus.add(int(part))
+    return cpus
+
+
+def bind_near_gpu(pci_bus_id, min_cpus=4, sysfs="/sys/bus/pci/devices"):
+    """Restrict this process (and the threads it starts later: the library's copy pool) to the CPUs of the NUMA node
+    the GPU hangs off, so that pinned staging buffers are first-touched next to the GPU's PCIe root.  One process
+    per GPU is the reference's own layout (main_func spawns a worker per clip range); the end-to-end path at 4-8
+    GPUs is host-memory bound, which is where placement matters.  `pci_bus_id` as CUDA prints it
+    ("0000:1b:00.0").  Returns the CPU set applied, or None when sysfs has no answer or fewer than `min_cpus` of the
+    node's CPUs are available to this process (nothing is changed then)."""
+    try:
+        with open(os.path.join(sysfs, pci_bus_id.lower(), "local_cpulist")) as f:
+            local = parse_cpulist(f.read())
+        allowed = os.sched_getaffinity(0)
+        target = local & allowed
+        if len(target) < min_cpus or target == allowed:
+            return None
+        os.sched_setaffinity(0, target)
+        return target
+    except (OSError, ValueError, AttributeError):
+        return None
+
+
 def shard_for_rank(start_frame, end_frame, video_length, world, rank):
     """(begin, end) of this rank's clip range, or None when there are more ranks than ranges."""
     ranges = tables.clip_ranges(start_frame, end_frame, video_length, world)
