@@ -246,6 +246,7 @@ def test_edge_cases_vs_oracle(oracle_lib):
         dict(H=300, W=96, fg=0.3, bg=-0.2, step=30),       # steps 1 px next to 30 px: non-monotone bounds
         dict(H=40, W=2048, fg=0.5, bg=-0.4, step=1),       # widest single-CTA-row configuration of NT=256
         dict(H=24, W=2064, fg=0.05, bg=-0.05, step=1),     # NT=512 instantiation
+        dict(H=40, W=2560, fg=0.5, bg=-0.4, step=1),       # k_warp_ws<512,8> (wide rows) with offsets that wrap at the row ends
     ]
     for i, c in enumerate(cases):
         H, W = c["H"], c["W"]
