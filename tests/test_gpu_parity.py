@@ -23,7 +23,7 @@ def _sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
-# 0 default route (depth pass stores the smoothed depth, k_warp_fused<false>, LUT membership); 1/2 general row kernel
+# 0 default route (depth pass stores the smoothed depth, warp-specialised k_warp_ws, LUT membership); 1/2 general row kernel
 # (store+verify / atomicMax); 3 default route with the slow membership path; 4 smoothing inside the warp kernel
 # (k_warp_fused<true>, no smoothed depth in HBM); 5 = 4 with the slow membership path; 6 = default route with the
 # barrier-synchronised k_warp_fused<false> instead of the warp-specialised k_warp_ws
