@@ -277,7 +277,10 @@ def test_blur_weight_paths(oracle_lib):
     raw[:, 30:70, 40:90] = np.float16(13.5)                     # a near plane: wide disocclusion holes
     asym = rng.random((5, 7)).astype(np.float32)
     asym /= asym.sum()
-    for w in (O.gaussian_weights(11, 9), O.gaussian_weights(19, 17), asym):
+    # 9x7 (720p) and 13x11 (1440p; its footprint is 34 words wide: the spread tail-word staging) are the other two
+    # specialised instantiations; 7x5 runs the generic integer kernel
+    for w in (O.gaussian_weights(11, 9), O.gaussian_weights(19, 17), O.gaussian_weights(9, 7), O.gaussian_weights(13, 11),
+              O.gaussian_weights(7, 5), asym):
         ctx = _ctx(H, W, 0.08, -0.05, 1, w)
         sbs, _, _, masks = _run_device(ctx, frames, raw)
         want, stages = _oracle_run(oracle_lib, dict(fg=0.08, bg=-0.05, step=1), frames, raw, w)
@@ -560,7 +563,7 @@ def test_blur_screening_is_exact(screen, oracle_lib):
     frames = rng.integers(0, 256, size=(2, H, W, 3), dtype=np.uint8)
     frames[1] = np.where(rng.random((H, W, 3)) < 0.5, 0, 255).astype(np.uint8)
     raw = np.zeros((2, H, W), dtype=np.float16)
-    for w in (O.gaussian_weights(11, 9), O.gaussian_weights(19, 17)):
+    for w in (O.gaussian_weights(11, 9), O.gaussian_weights(19, 17), O.gaussian_weights(9, 7), O.gaussian_weights(13, 11)):
         ctx = _ctx(H, W, 0.025, -0.01, 1, w)
         ctx.set_option("blur_screen", screen)
         sbs, _, infos, masks = _run_device(ctx, frames, raw)

@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(256, 4) k_blur_holes_fixed(BlurArgs a, const _
         uint32_t tasks = 0;
         // interior entries, two at a time: all row loads of both in flight before the pair sums are built
         auto stage_interior_load = [&](const uint8_t *left, int y, int s0, uint32_t (&v)[2 * CY + 1]) {
+            if (NWORDS < 32 && lane >= NWORDS) return;                   // narrow footprints (9 x 7): fewer words than lanes
             const uint8_t *colp = left + (s0 - PHASE) + 4 * lane;
             if ((y - CY >= 0) && (y + CY < H)) {
                 const uint8_t *p0 = colp + (size_t)(y - CY) * pitch;
@@ -206,6 +207,7 @@ __global__ void __launch_bounds__(256, 4) k_blur_holes_fixed(BlurArgs a, const _
             }
         };
         auto stage_interior_store = [&](uint16_t *T, int k, const uint32_t (&v)[2 * CY + 1]) {
+            if (k >= NWORDS) return;
 #pragma unroll
             for (int i = 0; i <= CY; ++i) {                              // bytes -> u16 lanes, pair sums on two packed u16 each
                 const uint32_t p = v[CY - i], q = v[CY + i];
