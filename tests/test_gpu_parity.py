@@ -620,3 +620,54 @@ def test_full_batch_properties_1080p(oracle_lib):
     want, _ = _oracle_run(oracle_lib, dict(fg=fg, bg=bg, step=step), frames[:3], raw[:3], w)
     for k in range(3):
         assert np.array_equal(sbs[k], want[k]), (k, int((sbs[k] != want[k]).sum()))
+
+
+@pytest.mark.parametrize("opts", [dict(host_right_half=0), dict(host_right_half=2), dict(pageable_direct=1),
+                                  dict(host_chunk=1, copy_threads=1), dict(host_chunk=3, copy_threads=5)])
+def test_host_pipeline_options(opts, oracle_lib):
+    """Every knob of vrsbs_process_host gives the same bytes: right halves over PCIe (0) or host-to-host (1, default;
+    2 skips them: bandwidth experiments), pageable buffers handed to the DMA directly, odd chunk sizes and copy-thread
+    counts."""
+    import vr_video_generator_b200 as pkg
+    meta, frames, raw, _ = load_case("medium")
+    p = meta["params"]
+    args = argparse.Namespace(offset_fg=p["fg"], offset_bg=p["bg"], offset_step_size=p["step"])
+    fr = np.concatenate([frames] * 3)[:11]
+    rw = np.concatenate([raw] * 3)[:11]
+    st = O.WarpState(p["fg"], p["bg"], p["step"])
+    w = golden_weights(meta)
+    want = np.stack([oracle_lib.process_frame(st, fr[t], rw[t], weights=w) for t in range(len(fr))])
+    for pinned in (False, True):
+        proc = pkg.SbsProcessor(None, 0, args, max_batch=4)
+        ctx = proc._context(p["H"], p["W"])
+        for k, v in opts.items():
+            ctx.set_option(k, v)
+        if pinned:
+            got = proc.left_side_sbs_batch(torch.from_numpy(fr).pin_memory(), torch.from_numpy(rw).pin_memory())
+        else:
+            got = proc.left_side_sbs_batch(fr, rw)
+        if opts.get("host_right_half") == 2:          # measurement mode: the right halves are not delivered at all
+            got, ref = got[:, :, :p["W"]], want[:, :, :p["W"]]
+        else:
+            ref = want
+        assert np.array_equal(got, ref), (opts, pinned, int((got != ref).sum()))
+        proc.close()
+
+
+@pytest.mark.parametrize("split", [3, 4, 5])
+def test_warp_specialised_splits_wide_rows(split, oracle_lib):
+    """k_warp_ws<512, 6 | 8 | 10>: the 16-warp instantiations used for rows wider than 2048 pixels."""
+    rng = np.random.default_rng(77)
+    H, W = 36, 2560
+    frames = rng.integers(0, 256, size=(2, H, W, 3), dtype=np.uint8)
+    raw = (rng.random((2, H, W)) * 15 - 0.5).astype(np.float16)
+    raw[:, :, 700:1500] = np.float16(6.0)
+    w = O.gaussian_weights(*O.blur_kernel_shape(H))
+    ctx = _ctx(H, W, 0.6, -0.5, 1, w, max_layers=1024)
+    ctx.set_option("ws_scatter_warps", split)
+    sbs, _, infos, masks = _run_device(ctx, frames, raw)
+    want, stages = _oracle_run(oracle_lib, dict(fg=0.6, bg=-0.5, step=1), frames, raw, w)
+    for t in range(2):
+        assert np.array_equal(masks[t], stages[t]["holes"])
+        assert np.array_equal(sbs[t], want[t]), (split, t, int((sbs[t] != want[t]).sum()))
+    ctx.close()
