@@ -365,6 +365,35 @@ def test_depth_tail_lowres():
         assert max(frac[0][0], frac[1][0]) > 0.9999, "neither variant reproduces torch's CUDA bicubic"
 
 
+def test_depth_tail_shapes_and_fallback_kernel():
+    """The tiled bicubic kernel and the one-pixel-per-thread kernel it falls back to (odd widths, tile footprints that do
+    not fit) agree bit for bit with each other and with the oracle's restatement, for up-scaling by 2.1 (the DPT case),
+    by 4.3, identity, down-scaling and a 1-pixel-high input, batches of 3 with the smoothing history carried."""
+    from vr_video_generator_b200 import _native, synth
+    shapes = [(74, 132, 156, 280), (37, 66, 160, 284), (60, 80, 60, 80), (96, 128, 40, 54), (50, 70, 75, 101), (1, 9, 16, 48)]
+    s = torch.cuda.current_stream().cuda_stream
+    for h, w, H, W in shapes:
+        lo = synth.depth_stress(3, h, w, seed=h + w)
+        want = _smooth_chain([O.bicubic_resize(lo[i], H, W, 1.618) for i in range(3)])
+        lo_t = torch.from_numpy(np.ascontiguousarray(lo)).cuda()
+        got = {}
+        for tiled in (1, 0):
+            ctx = _native.Context(0, H, W, 4, 64)
+            ctx.reset(0.025, -0.01, 1, False)
+            ctx.set_option("bicubic_contract", 0)
+            ctx.set_option("lowres_tiled", tiled)
+            out = torch.empty((3, H, W), dtype=torch.float16, device="cuda")
+            ctx.depth_from_lowres(lo_t.data_ptr(), 3, h, w, 1.618, H, W, out.data_ptr(), s)
+            ctx.build_tables(3, H, W, s)
+            infos = ctx.frame_info(3, s)
+            got[tiled] = out.cpu().numpy()
+            for t in range(3):
+                assert infos[t].depth_max == np.float32(want[t].max()), (h, w, H, W, tiled, t)
+            ctx.close()
+        assert np.array_equal(got[1].view(np.uint16), got[0].view(np.uint16)), (h, w, H, W)
+        assert np.array_equal(got[1].view(np.uint16), want.view(np.uint16)), (h, w, H, W)
+
+
 def test_lowres_batches_carry_history():
     """depth_from_lowres: history lives in registers inside a batch and in HBM between batches."""
     from vr_video_generator_b200 import synth
