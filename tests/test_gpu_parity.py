@@ -242,6 +242,8 @@ def test_edge_cases_vs_oracle(oracle_lib):
         dict(H=200, W=48, fg=0.3, bg=-0.2, step=1),        # offsets wrap several times
         dict(H=90, W=100, fg=0.2, bg=-0.1, step=2),        # W % 16 != 0 -> generic loads/stores
         dict(H=64, W=77, fg=0.1, bg=-0.1, step=3),         # odd width, partial last segment
+        dict(H=63, W=75, fg=0.1, bg=-0.1, step=1),         # odd pixel count: frames 1, 2 start at 2-byte-aligned depth / odd
+                                                           # image addresses (scalar depth pass, byte-wise row kernel and blur)
         dict(H=80, W=96, fg=-0.1, bg=0.08, step=1),        # bg > 0 > fg (the CLI leaves this alone): one layer
         dict(H=300, W=96, fg=0.3, bg=-0.2, step=30),       # steps 1 px next to 30 px: non-monotone bounds
         dict(H=40, W=2048, fg=0.5, bg=-0.4, step=1),       # widest single-CTA-row configuration of NT=256
