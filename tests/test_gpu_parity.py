@@ -702,3 +702,22 @@ def test_warp_specialised_splits_wide_rows(split, oracle_lib):
         assert np.array_equal(masks[t], stages[t]["holes"])
         assert np.array_equal(sbs[t], want[t]), (split, t, int((sbs[t] != want[t]).sum()))
     ctx.close()
+
+
+@pytest.mark.parametrize("H,W", [(720, 1280), (1440, 2560)])
+def test_other_resolutions(H, W, oracle_lib):
+    """720p (9x7 blur) and 1440p (13x11 blur, 16-warp warp kernel): scene depth from the DPT-resolution map, two frames,
+    byte-exact against the oracle."""
+    from vr_video_generator_b200 import synth
+    frames = synth.frames_noise(2, H, W, 9)
+    lo = synth.depth_lowres("scene", 2, seed=9)
+    raw = np.stack([O.bicubic_resize(lo[t], H, W, 1.0) for t in range(2)])
+    w = O.gaussian_weights(*O.blur_kernel_shape(H))
+    ctx = _ctx(H, W, 0.025, -0.015, 1, w, max_batch=2)
+    sbs, _, infos, masks = _run_device(ctx, frames, raw)
+    want, stages = _oracle_run(oracle_lib, dict(fg=0.025, bg=-0.015, step=1), frames, raw, w)
+    for t in range(2):
+        assert infos[t].holes > 1000
+        assert np.array_equal(masks[t], stages[t]["holes"])
+        assert np.array_equal(sbs[t], want[t]), (H, W, t, int((sbs[t] != want[t]).sum()))
+    ctx.close()
