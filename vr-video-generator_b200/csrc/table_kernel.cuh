@@ -56,6 +56,8 @@ __global__ void __launch_bounds__(256) k_build_tables(TableArgs a) {
     extern __shared__ double s_val[];          // [max(Lcap+2,B)] unsorted marks, then as many sorted
     const int sstride = max(a.Lcap + 2, a.B);
     double *s_sorted = s_val + sstride;
+    int *s_off = reinterpret_cast<int *>(s_val + 2 * sstride);       // [Lcap + 1] offset_x_list, kept for the later phases
+    float2 *s_bounds = reinterpret_cast<float2 *>(s_val);           // [Lcap] fp16 bounds as floats; s_val is free after the sort
     __shared__ double s_r0, s_r1, s_span, s_top;
     __shared__ int s_limit, s_start, s_nneg, s_E, s_bad;
     __shared__ float s_max;
@@ -148,32 +150,36 @@ __global__ void __launch_bounds__(256) k_build_tables(TableArgs a) {
         // python double -> float -> half (c10::Half has only a float constructor)
         __half lo = __float2half_rn(__double2float_rn(__dsub_rn(c, __dmul_rn(0.05, s))));
         __half hi = __float2half_rn(__double2float_rn(__dadd_rn(c, __dmul_rn(1.05, s))));
-        bounds[k] = make_float2(__half2float(lo), __half2float(hi));
+        const float2 bd = make_float2(__half2float(lo), __half2float(hi));
+        bounds[k] = bd;
+        s_bounds[k] = bd;                                      // (s_val region: every read of the marks is behind two barriers)
         a.lo16[(size_t)b * a.Lcap + k] = __half_as_ushort(lo);
         a.hi16[(size_t)b * a.Lcap + k] = __half_as_ushort(hi);
         offs[k] = off;
+        s_off[k] = off;
         offm[k + 1] = wrap_mod(off, a.W);
     }
-    __syncthreads();   // global writes by this CTA are visible to it after the barrier
+    __syncthreads();
     int mono = 1;
     for (int k = threadIdx.x; k + 1 < L; k += blockDim.x) {
-        float2 p = bounds[k], q = bounds[k + 1];
+        float2 p = s_bounds[k], q = s_bounds[k + 1];
         if (!(p.x <= q.x) || !(p.y <= q.y)) mono = 0;
     }
     mono = __syncthreads_and(mono);
+    const int fill_off = wrap_mod(s_off[(int)((double)(L * 3) / 5.0)], a.W);
     if (threadIdx.x == 0) {
         int fill = (int)((double)(L * 3) / 5.0);               // int(len(offset_img)*3/5)
-        offm[0] = offm[fill + 1];
-        double sn = py_round(__dmul_rn(__ddiv_rn((double)offs[L - 1], 3.0), 2.0));   // round(offset_x/3*2)
+        offm[0] = fill_off;
+        double sn = py_round(__dmul_rn(__ddiv_rn((double)s_off[L - 1], 3.0), 2.0));   // round(offset_x/3*2)
         int n = clamp_int(sn);
         int strip = n >= 0 ? min(n, a.W) : max(0, a.W + n);    // python slice 0:n
         float scale = 0.f, bias = 0.f;
         if (L >= 3) {
-            float lo1 = bounds[1].x, loN = bounds[L - 1].x;
+            float lo1 = s_bounds[1].x, loN = s_bounds[L - 1].x;
             if (loN > lo1) { scale = (float)(L - 2) / (loN - lo1); bias = 1.f - lo1 * scale; }
         }
         tab->layers = L;
-        tab->fill_off = offm[0];
+        tab->fill_off = fill_off;
         tab->strip = strip;
         tab->status = (a.frame_nan[b] ? VRSBS_FRAME_NAN : 0u) | (s_bad ? VRSBS_FRAME_OVERFLOW : 0u) |
                       (mono ? 0u : VRSBS_FRAME_GENERIC);
@@ -196,17 +202,12 @@ __global__ void __launch_bounds__(256) k_build_tables(TableArgs a) {
     uint8_t *lut = blob + 16 + ent_bytes;
     const float fmax = s_max;
     bool ok = mono && !s_bad && !a.frame_nan[b] && L <= a.ent_cap && L <= 255 && a.W * 4 <= 65535 && fmax < 60000.f;
-    // the LUT search binary-searches the bounds thousands of times: keep them in shared memory (the mark buffers
-    // are free again; 2 * sstride doubles >= Lcap float2)
-    float2 *s_bounds = reinterpret_cast<float2 *>(s_val);
-    __syncthreads();
-    if (ok) for (int k = threadIdx.x; k < L; k += blockDim.x) s_bounds[k] = bounds[k];
-    __syncthreads();
+    // (the LUT search binary-searches the bounds thousands of times: they are in shared memory already)
     const uint32_t maxbits = (fmax > 0.f) ? (uint32_t)__half_as_ushort(__float2half_rn(fmax)) : 0u;
     {
         int fits = 1;
         for (int k = threadIdx.x; k < L; k += blockDim.x) {
-            const int o = offm[k + 1], so = o * 2 < a.W ? o : o - a.W;
+            const int o = wrap_mod(s_off[k], a.W), so = o * 2 < a.W ? o : o - a.W;
             if (so > a.key_pad || so < -a.key_pad) fits = 0;
         }
         ok = __syncthreads_and(fits) && ok;
@@ -236,17 +237,17 @@ __global__ void __launch_bounds__(256) k_build_tables(TableArgs a) {
     ok = ok && shift >= 0;
     for (int e = threadIdx.x; e <= L && e <= a.ent_cap; e += blockDim.x) {
         LayerEnt le;
-        const uint32_t hi = e >= 1 ? a.hi16[(size_t)b * a.Lcap + e - 1] : 0xFC00u;        // -inf
-        const uint32_t lo = e <= L - 1 ? a.lo16[(size_t)b * a.Lcap + e] : 0x7C00u;        // +inf
+        const uint32_t hi = e >= 1 ? (uint32_t)__half_as_ushort(__float2half_rn(s_bounds[e - 1].y)) : 0xFC00u;   // -inf
+        const uint32_t lo = e <= L - 1 ? (uint32_t)__half_as_ushort(__float2half_rn(s_bounds[e].x)) : 0x7C00u;    // +inf
         auto biased4 = [&](int o) { return (uint32_t)(((o * 2 < a.W ? o : o - a.W) + a.key_pad) * 4) & 0xffffu; };
-        const uint32_t o0 = e >= 1 ? biased4(offm[e]) : 0u;
-        const uint32_t o1 = e <= L - 1 ? biased4(offm[e + 1]) : 0u;
+        const uint32_t o0 = e >= 1 ? biased4(wrap_mod(s_off[e - 1], a.W)) : 0u;
+        const uint32_t o1 = e <= L - 1 ? biased4(wrap_mod(s_off[e], a.W)) : 0u;
         le.hi_lo = hi | (lo << 16);
         le.off4 = (o0 & 0xffffu) | (o1 << 16);
         ent[e] = le;
     }
     if (threadIdx.x == 0) {
-        hdr->fill_off = offm[0];
+        hdr->fill_off = fill_off;
         hdr->shift = ok ? (uint32_t)shift : 0u;
         hdr->ncells = ok ? ncells : 0u;
         hdr->flags = (ok ? 1u : 0u) | ((uint32_t)L << 8);

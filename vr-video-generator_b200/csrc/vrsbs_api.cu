@@ -425,7 +425,8 @@ int launch_tables(vrsbs_ctx *c, Scratch &s, int B, int H, int W, cudaStream_t st
     a.B = B; a.H = H; a.W = W; a.Lcap = c->max_layers;
     fast_caps(c, H, W, &c->ent_cap, &c->lut_cap);
     a.blobs = s.blobs; a.ent_cap = c->ent_cap; a.lut_cap = c->lut_cap; a.key_pad = c->key_pad;
-    const size_t smem = sizeof(double) * 2 * (size_t)(c->max_layers + 2 > B ? c->max_layers + 2 : B);
+    const size_t smem = sizeof(double) * 2 * (size_t)(c->max_layers + 2 > B ? c->max_layers + 2 : B) +
+                        sizeof(int) * (size_t)(c->max_layers + 2);
     StageTimer timer(c, st, 1);
     k_build_tables<<<B, 256, smem, st>>>(a);
     CU_TRY(c, cudaGetLastError());
