@@ -102,3 +102,29 @@ def test_synth_is_deterministic_and_shaped():
     s = synth.depth_scene(2)
     assert s.shape == (2, synth.DPT_H, synth.DPT_W) and float(s.max()) == pytest.approx(13.9, abs=0.01)
     assert math.ceil(float(s.max())) == 14
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU port timed on the host cores) runs without a GPU and prints one JSON line
+    with the keys the driver reads; under a multi-rank launch only rank 0 works."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+           "--cpu-budget", "1", "--workload", "1080p_b16_cfg1"]
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "sbs_frames_per_sec_warp_stage" and d["unit"] == "frames/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "frames" in d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and d["gpu_launches"] == 0
+    # any other rank exits 0 without output
+    out1 = subprocess.run(cmd, capture_output=True, text=True, timeout=120, env=dict(env, RANK="1", WORLD_SIZE="2"), cwd=root)
+    assert out1.returncode == 0 and out1.stdout.strip() == ""
