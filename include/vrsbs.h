@@ -141,7 +141,9 @@ int  vrsbs_process_batch(vrsbs_ctx *ctx, const uint8_t *frames_dev, const void *
  * chunks overlap.  Only the synthesised (left) half of every SBS row crosses PCIe on the way back;
  * the right half is the caller's own frame and is copied host-to-host by the library's copy threads
  * (option "host_right_half", default 1).  Returns after sbs_host is complete (like the reference's
- * blocking D2H). */
+ * blocking D2H).  depth_host may also be a DEVICE pointer (a depth producer in the same process that keeps
+ * its output on the GPU, PredictAndGenerate.py:23-61 without the `.to('cpu')` at :55): it is then read where
+ * it is, and the caller guarantees that the work which produced it has completed. */
 int  vrsbs_process_host(vrsbs_ctx *ctx, const uint8_t *frames_host, const void *depth_host,
                         int B, int H, int W, int lowres_h, int lowres_w, float scaler,
                         uint8_t *sbs_host);

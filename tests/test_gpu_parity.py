@@ -721,3 +721,22 @@ def test_other_resolutions(H, W, oracle_lib):
         assert np.array_equal(masks[t], stages[t]["holes"])
         assert np.array_equal(sbs[t], want[t]), (H, W, t, int((sbs[t] != want[t]).sum()))
     ctx.close()
+
+
+def test_host_pipeline_with_depth_left_on_the_device():
+    """SURVEY 8 f2, the hand-off side: a producer in the same process leaves its depth on the GPU (full-res raw or the
+    DPT-resolution map); left_side_sbs_batch reads it where it is and gives the bytes of the all-host call."""
+    import vr_video_generator_b200 as pkg
+    from vr_video_generator_b200 import synth
+    H, W, B = 270, 480, 11
+    frames = synth.frames_noise(B, H, W, seed=6)
+    lo = synth.depth_scene(B, 74, 132, seed=6)
+    raw = np.stack([O.bicubic_resize(lo[t], H, W, 1.618) for t in range(B)])
+    args = argparse.Namespace(offset_fg=0.025, offset_bg=-0.015, offset_step_size=1)
+    for host_d, scaler in ((raw, 1.0), (lo, 1.618)):
+        p1 = pkg.SbsProcessor(None, 0, args, max_batch=4)
+        want = p1.left_side_sbs_batch(frames, host_d, scaler=scaler)
+        p2 = pkg.SbsProcessor(None, 0, args, max_batch=4)
+        got = p2.left_side_sbs_batch(frames, torch.from_numpy(host_d).cuda(), scaler=scaler)
+        assert np.array_equal(got, want), host_d.shape
+        p1.close(), p2.close()

@@ -696,6 +696,12 @@ bool is_pinned(const void *p) {
     return at.type == cudaMemoryTypeHost;
 }
 
+bool is_device(const void *p) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice;
+}
+
 int ensure_slot(vrsbs_ctx *c, HostSlot &s, size_t frames_b, size_t depth_in_b, size_t depth_b, size_t sbs_b, bool need_pin_in,
                 bool need_pin_out) {
     if (!c->st_in) {
@@ -1001,7 +1007,10 @@ int vrsbs_process_host(vrsbs_ctx *c, const uint8_t *frames, const void *depth, i
     const size_t dib = lowres ? (size_t)lh * lw * 2 : db;
     const size_t row3 = (size_t)W * 3;
     const bool direct = c->pageable_direct != 0;
-    const bool pin_f = direct || is_pinned(frames), pin_d = direct || is_pinned(depth), pin_s = direct || is_pinned(sbs);
+    // the depth may already live on the device (a depth producer in the same process): it is then used
+    // where it is - no staging, no H2D - and the caller has made sure the producer's stream is done with it
+    const bool dev_d = is_device(depth);
+    const bool pin_f = direct || is_pinned(frames), pin_d = direct || dev_d || is_pinned(depth), pin_s = direct || is_pinned(sbs);
     // the right half of every SBS row is the caller's own input row: copy it host to host and move only the
     // synthesised half across PCIe (halves the D2H traffic, which is the longer leg)
     const bool host_right = c->host_right_half != 0;
@@ -1015,7 +1024,7 @@ int vrsbs_process_host(vrsbs_ctx *c, const uint8_t *frames, const void *depth, i
     CopyPool *pool = c->pool;
     fast_caps(c, H, W, &c->ent_cap, &c->lut_cap);
     if ((rc = check_blur_ready(c, H, W))) return rc;
-    const bool use_fused = !lowres && c->fused && c->smooth_in_warp && ((size_t)H * W) % 8 == 0 &&
+    const bool use_fused = !dev_d && !lowres && c->fused && c->smooth_in_warp && ((size_t)H * W) % 8 == 0 &&
                            fused_capable(c, c->slot[0].dev_frames, c->slot[0].dev_depth_in, c->slot[0].dev_sbs, W);
 
     // Three streams: st_in copies chunk i+1 in while st_k runs the kernels of chunk i and st_out copies chunk i-1
@@ -1068,17 +1077,18 @@ int vrsbs_process_host(vrsbs_ctx *c, const uint8_t *frames, const void *depth, i
         if (!pin_f) hf = s.pin_frames;
         if (!pin_d) hd = s.pin_depth;
         CU_TRY(c, cudaMemcpyAsync(s.dev_frames, hf, fb * n, cudaMemcpyHostToDevice, c->st_in));
-        CU_TRY(c, cudaMemcpyAsync(s.dev_depth_in, hd, dib * n, cudaMemcpyHostToDevice, c->st_in));
+        if (!dev_d) CU_TRY(c, cudaMemcpyAsync(s.dev_depth_in, hd, dib * n, cudaMemcpyHostToDevice, c->st_in));
+        const __half *din = dev_d ? (const __half *)hd : (const __half *)s.dev_depth_in;
         CU_TRY(c, cudaEventRecord(s.in_done, c->st_in));
         if (host_right && c->host_right_half != 2)               // right halves: caller's frames -> caller's output, on the pool
             { pool->wait(tk_right[si]); tk_right[si] = pool->submit(sbs + (size_t)first * sb + row3, 2 * row3, frames + (size_t)first * fb, row3, row3, (size_t)n * H); }
         CU_TRY(c, cudaStreamWaitEvent(c->st_k, s.in_done, 0));
         Scratch &sc = c->scratch[si];
         if (use_fused) {
-            rc = launch_process_fused(c, sc, s.dev_frames, (const __half *)s.dev_depth_in, n, H, W, s.dev_sbs, c->st_k);
+            rc = launch_process_fused(c, sc, s.dev_frames, din, n, H, W, s.dev_sbs, c->st_k);
         } else {
-            if (lowres) rc = launch_depth(c, sc, nullptr, (const __half *)s.dev_depth_in, n, H, W, lh, lw, scaler, (__half *)s.dev_depth, c->st_k);
-            else rc = launch_depth(c, sc, (const __half *)s.dev_depth_in, nullptr, n, H, W, 0, 0, 1.f, (__half *)s.dev_depth, c->st_k);
+            if (lowres) rc = launch_depth(c, sc, nullptr, din, n, H, W, lh, lw, scaler, (__half *)s.dev_depth, c->st_k);
+            else rc = launch_depth(c, sc, din, nullptr, n, H, W, 0, 0, 1.f, (__half *)s.dev_depth, c->st_k);
             if (!rc) rc = launch_tables(c, sc, n, H, W, c->st_k);
             if (!rc) rc = launch_warp(c, sc, s.dev_frames, (const __half *)s.dev_depth, n, H, W, s.dev_sbs, c->st_k);
         }

@@ -130,18 +130,28 @@ class SbsProcessor:
     def left_side_sbs_batch(self, frames, depths, scaler=1.0, out=None):
         """Host-buffer batch: frames [B,H,W,3] uint8 and depths [B,H,W] fp16 (raw, full-res) or
         [B,h,w] fp16 (DPT low-res; bicubic + `scaler` applied on the device).  numpy arrays or CPU
-        tensors, pinned or pageable.  Returns numpy [B,H,2W,3].  Pipelined (pinned double buffering)."""
+        tensors, pinned or pageable; the depths may also be a CUDA tensor (the producer's output left on
+        the device).  Returns numpy [B,H,2W,3].  Pipelined (pinned double buffering)."""
         f = _as_numpy(frames)
-        d = _as_numpy(depths)
-        if d.dtype != np.float16:
-            raise TypeError(f"depth must be float16 (the producer's autocast dtype), got {d.dtype}")
         B, H, W, _ = f.shape
-        lowres = d.shape[1:] != (H, W)
+        if isinstance(depths, torch.Tensor) and depths.is_cuda:
+            # the depth producer's output is still on the device (same process): used where it is, no H2D of depth
+            _check_cuda(depths, torch.float16)
+            torch.cuda.current_stream(depths.device).synchronize()
+            dshape, dptr = tuple(depths.shape), depths.data_ptr()
+        else:
+            d = _as_numpy(depths)
+            if d.dtype != np.float16:
+                raise TypeError(f"depth must be float16 (the producer's autocast dtype), got {d.dtype}")
+            dshape, dptr = d.shape, d.ctypes.data
+        if len(dshape) != 3 or dshape[0] != B:
+            raise ValueError(f"depth {dshape} does not match {B} frames")
+        lowres = tuple(dshape[1:]) != (H, W)
         ctx = self._context(H, W)
         if out is None:
             out = np.empty((B, H, 2 * W, 3), dtype=np.uint8)
-        ctx.process_host(f.ctypes.data, d.ctypes.data, B, H, W, d.shape[1] if lowres else 0,
-                         d.shape[2] if lowres else 0, float(scaler), out.ctypes.data)
+        ctx.process_host(f.ctypes.data, dptr, B, H, W, dshape[1] if lowres else 0,
+                         dshape[2] if lowres else 0, float(scaler), out.ctypes.data)
         return out
 
     def warp_batch_device(self, frames, raw_depth, out=None, depth_scratch=None):
