@@ -174,7 +174,7 @@ def run_ours(args, wl, name):
     # between seeds and the job time is the max over ranks
     frames_h, lowres_h = make_inputs(wl, seed=100)
     binding = None
-    if not args.no_bind:
+    if args.bind:
         from vr_video_generator_b200 import shard
         pr = torch.cuda.get_device_properties(dev)
         bdf = "%04x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), getattr(pr, "pci_bus_id", 0), getattr(pr, "pci_device_id", 0))
@@ -465,7 +465,9 @@ def main():
     ap.add_argument("--depth-input", default="full", choices=["full", "lowres"],
                     help="full: raw full-resolution fp16 depth (the metric's config); lowres: DPT-resolution map, bicubic on the device")
     ap.add_argument("--host-chunk", type=int, default=0)
-    ap.add_argument("--no-bind", action="store_true", help="do not bind the process to the CPUs local to its GPU")
+    ap.add_argument("--bind", action="store_true",
+                    help="bind the process to the CPUs sysfs lists as local to its GPU (shard.bind_near_gpu); off by default: "
+                         "not yet measured on a multi-socket 8-GPU box")
     ap.add_argument("--video-frames", type=int, default=0,
                     help="also stream an N-frame synthetic video (e.g. 18000 = 10 min of 1080p30), sharded by clip range over the ranks")
     ap.add_argument("--host-opt", action="append", default=[], help="library option name=value for the host-API context")
