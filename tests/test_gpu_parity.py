@@ -740,3 +740,50 @@ def test_host_pipeline_with_depth_left_on_the_device():
         got = p2.left_side_sbs_batch(frames, torch.from_numpy(host_d).cuda(), scaler=scaler)
         assert np.array_equal(got, want), host_d.shape
         p1.close(), p2.close()
+
+
+class _ToyDepthModel:
+    """Stands in for DepthAnythingV2 in the hand-off test: same two methods (dpt.py:180-188, :204-228), toy arithmetic."""
+
+    def image2tensor(self, raw_image, input_size=518):
+        h, w = raw_image.shape[:2]
+        gh, gw = max(14, (h // 4) // 14 * 14), max(14, (w // 4) // 14 * 14)
+        ys, xs = np.arange(gh) * h // gh, np.arange(gw) * w // gw
+        img = raw_image[ys][:, xs].astype(np.float32) / 255.0
+        return torch.from_numpy(np.ascontiguousarray(img.transpose(2, 0, 1)))[None].cuda(), (h, w)
+
+    def forward(self, x):
+        k = torch.tensor([[1.0, 2.0, 1.0], [2.0, 4.0, 2.0], [1.0, 2.0, 1.0]], device=x.device)[None, None] / 16.0
+        g = torch.nn.functional.conv2d(x.mean(1, keepdim=True), k, padding=1)       # fp16 under autocast
+        return torch.relu(g * 9.0 - 0.5).squeeze(1)
+
+
+def test_producer_handoff_keeps_depth_on_the_device():
+    """f2 + f1 together: DepthProducer (one batched forward, DPT-resolution depth left on the GPU) feeding sbs_worker
+    gives the frames of the staged route fed with the same low-res maps from the host; and the fused bicubic + scaler
+    agrees with the reference's producer-side `interpolate(...) * scaler` within north_star's 1e-3."""
+    import vr_video_generator_b200 as pkg
+    from vr_video_generator_b200 import producer, worker
+    from vr_video_generator_b200 import synth
+    H, W, n = 270, 480, 9
+    frames_bgr = synth.frames_gradient(n, H, W, seed=2)
+    model = _ToyDepthModel()
+    prod = producer.DepthProducer(model, encoder="vits", max_forward_batch=4)
+    args, _ = worker.parse_args(["--Max_Frame_Count", "4"])
+    clips = {}
+    names = worker.sbs_worker(0, n, lambda i: frames_bgr[i], prod, lambda name, sbs: clips.__setitem__(name, sbs),
+                              args, n, H, W, scaler=prod.scaler)
+    got = np.concatenate([clips[k] for k in names])
+    assert got.shape == (n, H, 2 * W, 3)
+    rgb = np.ascontiguousarray(frames_bgr[:, :, :, ::-1])
+    lo = prod(rgb)
+    assert lo.is_cuda and lo.dtype == torch.float16 and lo.shape[0] == n
+    proc = pkg.SbsProcessor(None, 0, args, max_batch=5)
+    want = proc.left_side_sbs_batch(rgb, lo.cpu().numpy(), scaler=prod.scaler)
+    assert np.array_equal(got, want)
+    proc.close()
+    # producer-side reference arithmetic for one frame vs the fused depth tail (first frame of a clip: smoothing is
+    # 0.58 d + 0.30 d + 0.12 d of the same map, so compare before smoothing through the oracle's restatement)
+    ref = producer.reference_depth(model, rgb[0], prod.scaler).float().cpu().numpy()
+    mine = O.bicubic_resize(lo[0].cpu().numpy(), H, W, prod.scaler).astype(np.float32)
+    assert np.all(np.abs(mine - ref) <= 1e-3 * np.abs(ref) + 1e-3)
