@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(256) k_blur_holes(BlurArgs a) {
 
 // ---- specialised hole blur: kernel size known at compile time, integer weights in the kernel parameters ----
 // Same algorithm as k_blur_holes, three things tightened (the generic kernel was issue bound at ~980
-// warp-instructions per listed word, profiles/r01b):
+// warp-instructions per listed word in an early capture of this round):
 //   * weights live in the parameter constant bank and every (i,j) is unrolled, so a tap costs two LDS.U16, one
 //     add and PARTS IMADs with a constant operand - no weight loads, no loop counters;
 //   * interior words stage their footprint with aligned 32-bit loads (one or two per lane per row) and build the

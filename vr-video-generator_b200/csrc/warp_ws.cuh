@@ -1,7 +1,7 @@
 // Stage 3a, warp-specialised variant of k_warp_fused<false> (same arithmetic, same tables, same output).
 //
 // k_warp_fused runs scatter -> CTA barrier -> destination pass -> CTA barrier per row; ~40 % of its stall samples
-// are warps parked at those two barriers (profiles/r01k).  Here the CTA is split into NS scatter warps and ND
+// are warps parked at those two barriers (measured mid-round, see profiles/README.md).  Here the CTA is split into NS scatter warps and ND
 // destination warps that meet only through split arrive / sync barriers around a DOUBLE-BUFFERED key row:
 //
 //   scatter warps, row n:  wait in_full[n%3] (TMA data, mbarrier) and k_empty[n&1]  ->  atomicMax keys into keys[n&1]
@@ -11,7 +11,7 @@
 //
 // k_full / k_empty are hardware named barriers (bar.arrive by the producer group, bar.sync by the consumer group):
 // a parked consumer issues nothing, whereas mbarrier try_wait loops spent 23 % of the kernel's issue slots on
-// polling (profiles/r01q).
+// polling (profiles/README.md).
 //
 // so a slow warp delays only its own group, and the scatter of row n+1 overlaps the destination pass of row n.
 // Smoothed depth in (the depth pass materialises it); frames whose tables did not validate take the same
@@ -53,10 +53,10 @@ struct WsArgs {
 __device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// mbarrier wait for a group that may be parked for a whole row time: a plain try_wait loop re-polls every few hundred
-// cycles and a waiting group then spends issue slots the working group needs (profiles/r01o: 19 % of all executed
-// warp-instructions were wait-loop polls).  try_wait's suspend-time hint lets the hardware park the thread until the
-// phase completes (or the hint expires), so a wait costs a handful of instructions.
+// mbarrier wait with a suspend-time hint, used for the TMA arrival barriers (in_full).  The key-row hand-off used
+// the same loop at first; a group parked for most of a row time then re-polled about every 50 cycles - hint or
+// nanosleep made no difference - and 19-23 % of all executed warp-instructions were polls, which is why that hand-off
+// now goes through named barriers.
 #ifndef VRSBS_WS_WAIT_HINT_NS
 #define VRSBS_WS_WAIT_HINT_NS 4000
 #endif
