@@ -10,7 +10,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-SMALL_CASES = ["small_a", "small_b", "small_step3", "small_neg", "small_zero", "medium"]
+SMALL_CASES = ["small_a", "small_b", "small_step3", "small_neg", "small_zero", "small_pospos", "small_negneg", "medium"]
 FULL_CASES = ["full_1080p_cfg1", "full_1080p_step2", "full_4k_wide"]
 
 

@@ -57,6 +57,9 @@ CASES = {
     "small_step3": dict(H=96, W=128, n=2, fg=0.06, bg=-0.04, step=3, frames="noise", depth="stress", lo=(30, 40), seed=3),
     "small_neg":   dict(H=96, W=144, n=3, fg=0.05, bg=-0.03, step=1, frames="noise", depth="stress", lo=(30, 44), seed=4, shift=2.0),
     "small_zero":  dict(H=64, W=96, n=3, fg=0.05, bg=-0.03, step=1, frames="noise", depth="stress", lo=(20, 30), seed=5, zero=(0, 2)),
+    # same-sign offsets reach the warp as typed (the CLI's fix-up at PredictAndGenerate.py:387-393 never touches args_god)
+    "small_pospos": dict(H=96, W=160, n=3, fg=0.12, bg=0.04, step=1, frames="noise", depth="stress", lo=(30, 50), seed=12),
+    "small_negneg": dict(H=96, W=160, n=3, fg=-0.04, bg=-0.12, step=1, frames="noise", depth="scene", lo=(30, 50), seed=13),
     "medium":      dict(H=270, W=480, n=4, fg=0.025, bg=-0.015, step=1, frames="gradient", depth="scene", lo=(74, 132), seed=6),
     "full_1080p_cfg1":  dict(H=1080, W=1920, n=3, fg=0.025, bg=-0.015, step=1, frames="noise", depth="stress", lo=(518, 924), seed=7, full=True),
     "full_1080p_step2": dict(H=1080, W=1920, n=2, fg=0.025, bg=-0.01, step=2, frames="gradient", depth="scene", lo=(518, 924), seed=8, full=True),

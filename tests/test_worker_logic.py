@@ -8,7 +8,7 @@ import pytest
 from vr_video_generator_b200 import worker
 
 
-def test_cli_defaults_and_sign_fixup():
+def test_cli_defaults_and_offsets_pass_through():
     args, rest = worker.parse_args([])
     # PredictAndGenerate.py:328-357
     assert (args.DebugDir, args.SubClipDir, args.OutputDir) == ("./Debug/", "./Subclip/", "DeleteThis.mkv")
@@ -19,11 +19,12 @@ def test_cli_defaults_and_sign_fixup():
     # unknown flags are discarded, not an error (:365)
     args, rest = worker.parse_args(["--offset_fg", "0.05", "--bogus", "1"])
     assert args.offset_fg == 0.05 and rest == ["--bogus", "1"]
-    # same-sign offsets: one of them is flipped (:387-393)
+    # same-sign offsets reach the warp as typed: the reference's fix-up (:387-393) rebinds module-level names only,
+    # main_func(args) (:411) passes the untouched Namespace and SbsProcessor reads args_god.offset_* (:92-94)
     a, _ = worker.parse_args(["--offset_fg", "0.03", "--offset_bg", "0.01"])
-    assert (a.offset_fg, a.offset_bg) == (0.03, -0.01)
+    assert (a.offset_fg, a.offset_bg) == (0.03, 0.01)
     a, _ = worker.parse_args(["--offset_fg", "-0.03", "--offset_bg", "-0.01"])
-    assert (a.offset_fg, a.offset_bg) == (0.03, -0.01)
+    assert (a.offset_fg, a.offset_bg) == (-0.03, -0.01)
     assert worker.encoder_scaler("vits") == 1.618 and worker.encoder_scaler("vitg") == 1
 
 

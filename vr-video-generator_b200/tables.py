@@ -19,7 +19,9 @@ def smoothing_weights(count=2, initial=0.3, ratio=0.4):
 
 
 def fix_offset_signs(offset_fg, offset_bg):
-    """The CLI's same-sign fix-up (PredictAndGenerate.py:387-393)."""
+    """The CLI's same-sign fix-up (PredictAndGenerate.py:387-393), restated for documentation only: in the
+    reference it rebinds module-level names that no worker reads (SbsProcessor takes the offsets from the untouched
+    `args_god`, :92-94), so the product path never calls this."""
     if offset_bg * offset_fg > 0:
         if offset_bg >= 0:
             offset_bg = offset_bg * (-1)

@@ -2,7 +2,9 @@
 per-clip-range worker loop and the sub-clip bookkeeping.  Decode, encode and the depth model stay pluggable
 callables (OpenCV / ffmpeg / Depth-Anything-V2 in the reference); nothing here touches them.
 
-  * `parse_args`      - PredictAndGenerate.py:327-393 (same flags, same defaults, unknown flags ignored, sign fix-up)
+  * `parse_args`      - PredictAndGenerate.py:327-365 (same flags, same defaults, unknown flags ignored); the
+                        same-sign fix-up of :387-393 only rebinds module-level names there and never reaches the
+                        warp, so it is NOT applied to the namespace (see `parse_args`)
   * `sbs_worker`      - PredictAndGenerate.py:200-272 (`nibba_woka`), batched: one `left_side_sbs_batch` per sub-clip
   * `subclip_*`       - naming `{last_i}_{i}.mp4` (PredictAndGenerate.py:243), numeric order (Combine_Clips.py:9-10,
                         Check_Clips.py:17-18) and the length / continuity checks of Check_Clips.py:19-37
@@ -39,10 +41,13 @@ def make_arg_parser():
 
 
 def parse_args(argv=None):
-    """`args_god` as the reference builds it: parse_known_args (unknown flags are ignored, :365) followed by the
-    same-sign fix-up of the offsets (:387-393).  Returns (namespace, discarded)."""
+    """`args_god` exactly as the reference's workers receive it: the Namespace of parse_known_args (unknown flags
+    are ignored, :365), untouched.  The reference's same-sign fix-up (:387-393) rebinds the MODULE-LEVEL names
+    `offset_bg` / `offset_fg` only; `main_func(args)` (:411) hands the workers the original Namespace and
+    `SbsProcessor` reads `args_god.offset_fg` / `.offset_bg` (:92-94), so `--offset_fg 0.03 --offset_bg 0.01` warps
+    with both offsets positive.  `tables.fix_offset_signs` restates that dead fix-up for documentation; it is not
+    applied here.  Returns (namespace, discarded)."""
     args, discarded = make_arg_parser().parse_known_args(argv)
-    args.offset_fg, args.offset_bg = tables.fix_offset_signs(args.offset_fg, args.offset_bg)
     return args, discarded
 
 
