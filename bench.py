@@ -38,6 +38,7 @@ WORKLOADS = {
     "1080p_stress_b64": dict(H=1080, W=1920, B=64, fg=0.025, bg=-0.015, step=1, depth="stress"),
 }
 ranks = None
+ROUTE = "default (k_depth_pass, k_build_tables, k_warp_ws, k_blur_holes_fixed, k_blur_commit)"
 METRIC = "sbs_frames_per_sec_warp_stage"
 UNIT = "frames/s"
 
@@ -158,21 +159,233 @@ def dist_setup():
 
 
 # ---------------------------------------------------------------------------------------------------------
+class DeviceBench:
+    """Device-resident inputs of one workload + the timed step (vrsbs_process_batch, or the low-res depth route)."""
+
+    def __init__(self, args, wl, dev, seed=100):
+        import torch
+
+        from vr_video_generator_b200 import _native, tables
+        self.torch, self.wl, self.dev = torch, wl, dev
+        H, W, B = wl["H"], wl["W"], wl["B"]
+        # every rank = its own clip range with its own state; the CONTENT is the same seeded clip on every rank, so that
+        # the work per GPU is fixed as N grows (weak scaling) - hole counts, and with them the blur time, vary by ~10 %
+        # between seeds and the job time is the max over ranks
+        self.frames_h, self.lowres_h = make_inputs(wl, seed=seed)
+        ctx = _native.Context(dev, H, W, B, 512)
+        ctx.reset(wl["fg"], wl["bg"], wl["step"], True)
+        ctx.set_blur_weights(tables.gaussian_weights(*tables.blur_kernel_shape(H)))
+        if args.scatter_mode:                      # 1/2: the general row kernel instead of the fused route (A/B runs)
+            ctx.set_option("fused", 0)
+            ctx.set_option("scatter_mode", args.scatter_mode)
+        for kv in args.opt:                        # tuning experiments: --opt name=value
+            k, v = kv.split("=")
+            ctx.set_option(k, int(v))
+        self.ctx = ctx
+        stream = self.stream = torch.cuda.current_stream().cuda_stream
+        # device-resident inputs: frames + RAW full-res fp16 depth (what SbsProcessor.get_depth receives),
+        # produced once, untimed, by the library's own depth tail from the low-res synthetic DPT maps
+        self.frames_d = torch.from_numpy(self.frames_h).cuda()
+        self.lowres_d = torch.from_numpy(self.lowres_h).cuda()
+        self.raw_d = torch.empty((B, H, W), dtype=torch.float16, device="cuda")
+        prep = _native.Context(dev, H, W, 1, 64)
+        for t in range(B):                                            # B=1 with a fresh clip each: raw depth, not smoothed
+            prep.reset(wl["fg"], wl["bg"], wl["step"], False)
+            prep.depth_from_lowres(self.lowres_d[t].data_ptr(), 1, self.lowres_h.shape[1], self.lowres_h.shape[2], 1.0, H, W,
+                                   self.raw_d[t].data_ptr(), stream)
+            # first frame of a clip: smoothed = 0.58d + 0.3d + 0.12d != d in fp16; good enough as "raw" input
+        torch.cuda.synchronize()
+        prep.close()
+        self.raw_h = self.raw_d.cpu().numpy()
+        self.scratch_d = torch.empty_like(self.raw_d)
+        self.sbs_d = torch.empty((B, H, 2 * W, 3), dtype=torch.uint8, device="cuda")
+        self.lowres = args.depth_input == "lowres"
+
+    def step(self):
+        wl, ctx, s = self.wl, self.ctx, self.stream
+        H, W, B = wl["H"], wl["W"], wl["B"]
+        if self.lowres:
+            # the depth tail on the device: DPT-resolution map in, bicubic + smoothing + max fused (SURVEY section 8d, A_fused)
+            lh, lw = self.lowres_h.shape[1], self.lowres_h.shape[2]
+            ctx.depth_from_lowres(self.lowres_d.data_ptr(), B, lh, lw, 1.0, H, W, self.scratch_d.data_ptr(), s)
+            ctx.build_tables(B, H, W, s)
+            ctx.warp_batch(self.frames_d.data_ptr(), self.scratch_d.data_ptr(), B, H, W, self.sbs_d.data_ptr(), s)
+        else:
+            ctx.process_batch(self.frames_d.data_ptr(), self.raw_d.data_ptr(), B, H, W, self.scratch_d.data_ptr(),
+                              self.sbs_d.data_ptr(), s)
+
+    def timed(self, steps, warmup, barrier=lambda: None, on_start=lambda: None):
+        """(ms for `steps` steps on this rank, host issue ms per step, stage times, launches, frame infos)."""
+        torch, ctx = self.torch, self.ctx
+        for _ in range(warmup):
+            self.step()
+        torch.cuda.synchronize()
+        infos = ctx.frame_info(self.wl["B"], self.stream)
+        ctx.stage_times()
+        ctx.set_option("stage_timing", 1)
+        launches0 = ctx.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        torch.cuda.synchronize()
+        on_start()
+        e0.record()
+        t_host = time.perf_counter()
+        for _ in range(steps):
+            self.step()
+        e1.record()
+        host_issue_ms = (time.perf_counter() - t_host) * 1e3 / steps      # CPU time to issue one step (launch bound if ~ ms_per_step)
+        torch.cuda.synchronize()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        stage = ctx.stage_times()
+        ctx.set_option("stage_timing", 0)
+        # a second, untimed-by-events pass WITHOUT the per-kernel event pairs: the value the line reports
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        torch.cuda.synchronize()
+        e2.record()
+        for _ in range(steps):
+            self.step()
+        e3.record()
+        torch.cuda.synchronize()
+        barrier()
+        ms_clean = e2.elapsed_time(e3)
+        return ms, ms_clean, host_issue_ms, stage, (ctx.launch_count() - launches0) // 2, infos
+
+    def workload_text(self, name, infos):
+        wl = self.wl
+        return (f"{name}: {wl['W']}x{wl['H']}, {wl['B']}-frame batch per GPU, fg={wl['fg']} bg={wl['bg']} step={wl['step']}, "
+                f"D-{wl['depth']} depth (limit_step {infos[0].limit_step}, {infos[0].layers} layers, "
+                f"{100.0 * infos[0].holes / (wl['H'] * wl['W']):.2f}% holes)")
+
+    def close(self):
+        self.ctx.close()
+
+
+def stage_roofline(name, wl, ms_per_step, stage, steps, peak, peak_src, kernel):
+    """roofline of the dominant kernel (algorithmic bytes per launch / mean launch duration) AND of the whole warp stage
+    (`stage_frac` = frames/s x A_warp / peak: what north_star's >= 60 % target is about)."""
+    H, W, B = wl["H"], wl["W"], wl["B"]
+    warp_ms, warp_n = stage["warp"]
+    abytes = algorithmic_bytes(H, W) * B
+    achieved = abytes / (warp_ms / max(warp_n, 1) * 1e-3) / 1e9 if warp_n else None
+    traffic = stage_traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic, stage_traffic = tj.get(name), tj.get(name + "_stage")
+    stage_gbs = abytes / (ms_per_step * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": abytes, "launch_ms": warp_ms / max(warp_n, 1),
+            "stage_achieved": stage_gbs, "stage_frac": stage_gbs / peak, "stage_frac_vs_nominal_8TBs": stage_gbs / 8000.0,
+            "stage_traffic": stage_traffic,
+            "stage_note": "stage_* = all kernels of one step (depth pass, tables, warp, blur, commit): A_warp bytes x frames / step time"}
+
+
+def reference_cuda_fps(wl, frames, raw, n=6):
+    """The UNMODIFIED reference on this B200 as it ships (torch CUDA ops, cuDNN blur, pageable H2D, blocking D2H per
+    frame; PredictAndGenerate.py:157-198), fed through a plain queue: a second, more telling baseline."""
+    import torch
+
+    from oracle import ref_driver
+    if not ref_driver.reference_available():
+        return None
+    n = min(n, len(frames) - 1)
+    ref = ref_driver.ReferenceWarp(wl["fg"], wl["bg"], wl["step"], device="cuda")
+    ref.left_side_sbs(frames[0], torch.from_numpy(raw[0]))             # warm-up: cuDNN plan, allocator
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for t in range(1, 1 + n):
+        ref.left_side_sbs(frames[t], torch.from_numpy(raw[t]))
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    torch.cuda.empty_cache()
+    return {"value": n / dt, "unit": UNIT, "frames": n, "ms_per_frame": 1e3 * dt / n,
+            "what": "unmodified reference SbsProcessor.left_side_sbs on cuda:0 (host numpy frame + CPU fp16 depth in, host SBS frame out), "
+                    f"cudnn.allow_tf32={torch.backends.cudnn.allow_tf32}, torch {torch.__version__}"}
+
+
+def producer_timing(frames, encoders=("vits", "vitb", "vitl"), n=4):
+    """Depth producer, timed SEPARATELY (north_star; never part of the warp figure): the reference's Depth-Anything-V2
+    module with random-initialised weights (no checkpoints offline) under fp16 autocast.  `reference_per_frame` = what
+    inference_worker does per request (PredictAndGenerate.py:54-55): `infer_image_gpu(img) * scaler` (cv2 preprocessing
+    on the host, batch-1 forward, bicubic tail to frame size) plus the `.to('cpu')`.  `batched` = producer.DepthProducer:
+    one forward for n frames, DPT-resolution output left on the device (the bicubic tail and the scaler then run inside
+    the warp's depth pass)."""
+    import torch
+
+    from oracle import ref_driver
+    from vr_video_generator_b200.producer import DepthProducer
+    from vr_video_generator_b200.worker import encoder_scaler
+    if not ref_driver.reference_available():
+        return None
+    out = {}
+    dev = torch.device("cuda", torch.cuda.current_device())
+    for enc in encoders:
+        model = ref_driver.depth_model(enc, dev)
+        scaler = encoder_scaler(enc)
+        with torch.no_grad():
+            model.infer_image_gpu(frames[0])                                   # warm-up outside autocast, like :37
+            with torch.autocast(device_type="cuda", dtype=torch.float16):
+                (model.infer_image_gpu(frames[0]) * scaler).to("cpu")
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for t in range(n):
+                with torch.autocast(device_type="cuda", dtype=torch.float16):
+                    d = (model.infer_image_gpu(frames[t % len(frames)]) * scaler).to(torch.device("cpu"))
+            per_frame = (time.perf_counter() - t0) / n
+            x, _ = model.image2tensor(frames[0], 518)
+            with torch.autocast(device_type="cuda", dtype=torch.float16):
+                model.forward(x)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(n):
+                    model.forward(x)
+                e1.record()
+                torch.cuda.synchronize()
+            fwd1 = e0.elapsed_time(e1) / n
+        prod = DepthProducer(model, enc, max_forward_batch=n)
+        prod(frames[:n])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        lo = prod(frames[:n])
+        torch.cuda.synchronize()
+        batched = (time.perf_counter() - t0) / n
+        xb = torch.cat([x] * n)
+        with torch.no_grad(), torch.autocast(device_type="cuda", dtype=torch.float16):
+            model.forward(xb)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            model.forward(xb)
+            e1.record()
+            torch.cuda.synchronize()
+        out[enc] = {"reference_per_frame_ms": 1e3 * per_frame, "reference_per_frame_fps": 1.0 / per_frame,
+                    "forward_batch1_ms": fwd1, f"forward_batch{n}_ms_per_frame": e0.elapsed_time(e1) / n,
+                    "batched_producer_ms_per_frame": 1e3 * batched, "batched_producer_fps": 1.0 / batched,
+                    "out_dtype": str(d.dtype), "lowres_shape": list(lo.shape[1:]), "params_M": sum(p.numel() for p in model.parameters()) / 1e6}
+        del model, prod, lo, xb
+        torch.cuda.empty_cache()
+    out["note"] = ("random-init weights (timing only; random-init depth is degenerate for the warp, SURVEY 8d); 1080p frames; "
+                   "host preprocessing (cv2 INTER_AREA + float64 normalise, dpt.py:204-228) is inside reference_per_frame and "
+                   "batched_producer, not inside forward_*")
+    return out
+
+
 def run_ours(args, wl, name):
     import torch
 
     import vr_video_generator_b200 as pkg
-    from vr_video_generator_b200 import _native, tables
+    from vr_video_generator_b200 import tables
 
     rank, world, barrier, reduce_max = dist_setup()
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback in the product path)"
     dev = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(dev)
     H, W, B = wl["H"], wl["W"], wl["B"]
-    # every rank = its own clip range with its own state; the CONTENT is the same seeded clip on every rank, so that
-    # the work per GPU is fixed as N grows (weak scaling) - hole counts, and with them the blur time, vary by ~10 %
-    # between seeds and the job time is the max over ranks
-    frames_h, lowres_h = make_inputs(wl, seed=100)
     binding = None
     if args.bind:
         from vr_video_generator_b200 import shard
@@ -181,85 +394,20 @@ def run_ours(args, wl, name):
         cpus = shard.bind_near_gpu(bdf)
         binding = f"{bdf}: {len(cpus)} local cpus" if cpus else f"{bdf}: unchanged ({len(os.sched_getaffinity(0))} cpus)"
 
-    ctx = _native.Context(dev, H, W, B, 512)
-    ctx.reset(wl["fg"], wl["bg"], wl["step"], True)
-    ctx.set_blur_weights(tables.gaussian_weights(*tables.blur_kernel_shape(H)))
-    if args.scatter_mode:                      # 1/2: the general row kernel instead of the fused route (A/B runs)
-        ctx.set_option("fused", 0)
-        ctx.set_option("scatter_mode", args.scatter_mode)
-    for kv in args.opt:                        # tuning experiments: --opt name=value
-        k, v = kv.split("=")
-        ctx.set_option(k, int(v))
-    stream = torch.cuda.current_stream().cuda_stream
-
-    # device-resident inputs: frames + RAW full-res fp16 depth (what SbsProcessor.get_depth receives),
-    # produced once, untimed, by the library's own depth tail from the low-res synthetic DPT maps
-    frames_d = torch.from_numpy(frames_h).cuda()
-    lowres_d = torch.from_numpy(lowres_h).cuda()
-    raw_d = torch.empty((B, H, W), dtype=torch.float16, device="cuda")
-    prep = _native.Context(dev, H, W, 1, 64)
-    for t in range(B):                                            # B=1 with a fresh clip each: raw depth, not smoothed
-        prep.reset(wl["fg"], wl["bg"], wl["step"], False)
-        prep.depth_from_lowres(lowres_d[t].data_ptr(), 1, lowres_h.shape[1], lowres_h.shape[2], 1.0, H, W,
-                               raw_d[t].data_ptr(), stream)
-        # first frame of a clip: smoothed = 0.58d + 0.3d + 0.12d != d in fp16; good enough as "raw" input
-    torch.cuda.synchronize()
-    prep.close()
-    raw_h = raw_d.cpu().numpy()
-    scratch_d = torch.empty_like(raw_d)
-    sbs_d = torch.empty((B, H, 2 * W, 3), dtype=torch.uint8, device="cuda")
-
-    if args.depth_input == "lowres":
-        # the depth tail on the device: DPT-resolution map in, bicubic + smoothing + max fused (A_fused)
-        lh, lw = lowres_h.shape[1], lowres_h.shape[2]
-
-        def step():
-            ctx.depth_from_lowres(lowres_d.data_ptr(), B, lh, lw, 1.0, H, W, scratch_d.data_ptr(), stream)
-            ctx.build_tables(B, H, W, stream)
-            ctx.warp_batch(frames_d.data_ptr(), scratch_d.data_ptr(), B, H, W, sbs_d.data_ptr(), stream)
-    else:
-        def step():
-            ctx.process_batch(frames_d.data_ptr(), raw_d.data_ptr(), B, H, W, scratch_d.data_ptr(), sbs_d.data_ptr(), stream)
-
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
-    infos = ctx.frame_info(B, stream)
-    ctx.stage_times()
-    ctx.set_option("stage_timing", 1)
-    launches0 = ctx.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    db = DeviceBench(args, wl, dev)
+    frames_h, lowres_h, raw_h, lowres_d, sbs_d = db.frames_h, db.lowres_h, db.raw_h, db.lowres_d, db.sbs_d
     clocks = ClockSampler(dev)               # NVML attach happens here, outside the timed region
-    barrier()
-    torch.cuda.synchronize()
-    clocks.__enter__()                       # sampled over the device-timed region AND the e2e region
-    time.sleep(0.25)
-    e0.record()
-    t_host = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    host_issue_ms = (time.perf_counter() - t_host) * 1e3 / args.steps      # CPU time to issue one step (launch bound if ~ ms_per_step)
-    torch.cuda.synchronize()
-    barrier()
-    ms_rank = e0.elapsed_time(e1)
+
+    def start_clocks():
+        clocks.__enter__()                   # sampled over the device-timed region AND the e2e region
+        time.sleep(0.25)
+    ms_rank_staged, ms_rank, host_issue_ms, stage, launches, infos = db.timed(args.steps, args.warmup, barrier, start_clocks)
     ms_total = reduce_max(ms_rank)
     per_rank = ranks.gather({"rank": rank, "ms_per_step": ms_rank / args.steps, "host_issue_ms_per_step": host_issue_ms})
-    stage = ctx.stage_times()
-    ctx.set_option("stage_timing", 0)
-    launches = ctx.launch_count() - launches0
     value = world * B * args.steps / (ms_total * 1e-3)
-
-    # roofline of the dominant kernel (the warp stage): algorithmic bytes per launch / mean launch duration
-    warp_ms, warp_n = stage["warp"]
     peak, peak_src = measured_hbm_peak()
-    abytes = algorithmic_bytes(H, W) * B
-    achieved = abytes / (warp_ms / max(warp_n, 1) * 1e-3) / 1e9 if warp_n else None
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            traffic = json.load(f).get(name)
+    kernel = "k_warp_rows" if args.scatter_mode else ("k_warp_ws" if W % 32 == 0 else "k_warp_fused")
+    roof = stage_roofline(name, wl, ms_total / args.steps, stage, args.steps, peak, peak_src, kernel)
 
     # end to end: the public batch API with pinned host buffers (H2D + D2H inside the timed region)
     ns = argparse.Namespace(offset_fg=wl["fg"], offset_bg=wl["bg"], offset_step_size=wl["step"])
@@ -293,7 +441,19 @@ def run_ours(args, wl, name):
            "h2d_bytes_per_step": int(frames_h.nbytes + raw_h.nbytes), "d2h_bytes_per_step": int(o_np.nbytes // 2),
            "host_to_host_bytes_per_step": int(o_np.nbytes // 2),
            "steps": e2e_steps, "api": "SbsProcessor.left_side_sbs_batch (vrsbs_process_host), pinned buffers"}
-    same = bool(np.array_equal(o_np[0], sbs_d[0].cpu().numpy())) if e2e_steps else None
+    # the e2e output of the whole batch (every frame) against the device-resident output of the same clip.  The device
+    # context has run the clip several times over (warm-up + timed steps), the host context too: both carried the clip
+    # state from step to step the same way, so the last steps agree frame by frame only if their histories agree -
+    # re-run both from a clean state once, untimed.
+    db.ctx.reset(wl["fg"], wl["bg"], wl["step"], True)
+    db.step()
+    proc.reset_state()
+    proc.left_side_sbs_batch(f_pin, d_pin, out=o_np)
+    torch.cuda.synchronize()
+    dev_out = sbs_d.cpu().numpy()
+    same = bool(np.array_equal(o_np, dev_out))
+    same_frames = int(sum(np.array_equal(o_np[t], dev_out[t]) for t in range(B)))
+    del dev_out
     # the same call with ordinary (pageable) numpy arrays, as nibba_woka's FrameList holds them: one step, reported aside
     if args.pageable:
         o_pg = np.empty_like(o_np)
@@ -336,7 +496,6 @@ def run_ours(args, wl, name):
     # PredictAndGenerate.py:274-275), every rank streaming its range through the host API from a cycled pinned pool
     video = None
     if args.video_frames:
-        from vr_video_generator_b200 import shard
         ranges = tables.clip_ranges(0, args.video_frames, args.video_frames, world)
         begin, end = ranges[rank] if rank < len(ranges) else (0, 0)
         proc.reset_state()
@@ -349,43 +508,165 @@ def run_ours(args, wl, name):
         dt = reduce_max(time.perf_counter() - t0)
         barrier()
         video = {"frames": args.video_frames, "seconds": dt, "frames_per_sec": args.video_frames / dt,
-                 "ranges": [list(r) for r in ranges], "batch": B}
+                 "ranges": [list(r) for r in ranges], "batch": B,
+                 "what": "BASELINE.json configs[4] (bounded): synthetic 1080p video sharded by clip range over the ranks "
+                         "(main_func's split), host API with pinned buffers cycled from one batch"}
+    proc.close()
+    del f_pin, d_pin, o_pin, o_np, l_pin
 
-    cpu = None
+    # BASELINE.json's metric names 1080p AND 4K: configs[2] (4K, wide disparity) device-resident on the same box
+    extra = {}
+    if args.also_4k and name != "4k_wide_b16" and not args.scatter_mode:
+        wl4 = WORKLOADS["4k_wide_b16"]
+        frames_h = lowres_h = raw_h = None
+        db.close()
+        del db, sbs_d, lowres_d
+        torch.cuda.empty_cache()
+        db4 = DeviceBench(args, wl4, dev)
+        steps4 = max(3, min(args.steps, 10))
+        _ms_s, ms4, _hi, stage4, _l4, infos4 = db4.timed(steps4, 3, barrier)
+        ms4 = reduce_max(ms4)
+        roof4 = stage_roofline("4k_wide_b16", wl4, ms4 / steps4, stage4, steps4, peak, peak_src, "k_warp_ws")
+        extra["4k_wide_b16"] = {"workload": db4.workload_text("4k_wide_b16", infos4), "value": world * wl4["B"] * steps4 / (ms4 * 1e-3),
+                                "unit": UNIT, "steps": steps4, "ms_per_step": ms4 / steps4,
+                                "stage_ms_per_step": {k: v[0] / steps4 for k, v in stage4.items()},
+                                "roofline": {k: roof4[k] for k in ("achieved", "frac", "stage_achieved", "stage_frac", "launch_ms", "traffic", "stage_traffic")}}
+        db4.close()
+        del db4
+        torch.cuda.empty_cache()
+    else:
+        db.close()
+
+    cpu = ref_cuda = producer = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_port_fps(wl, frames_h, raw_h, budget_s=args.cpu_budget)
+        # the baseline legs sample the first frames of the headline workload (same seed, same generators)
+        from oracle import sbs_layered as O
+        nb = min(B, 16)
+        if frames_h is None:
+            frames_h, lo = make_inputs(dict(wl, B=nb), seed=100)
+            raw_h = np.stack([O.bicubic_resize(lo[t], H, W, 1.0) for t in range(nb)])
+        ref_cuda = reference_cuda_fps(wl, frames_h, raw_h)
+        if not args.no_producer:
+            producer = producer_timing(frames_h)
+        cpu = cpu_baseline(wl, frames_h, raw_h, budget_s=args.cpu_budget)
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8 pixels / fp16 depth compares / integer-exact blur / f64 layer tables", "data": "synthetic",
-            "config": {"workload": f"{name}: {W}x{H}, {B}-frame batch per GPU, fg={wl['fg']} bg={wl['bg']} step={wl['step']}, "
-                                   f"D-{wl['depth']} depth (limit_step {infos[0].limit_step}, {infos[0].layers} layers, "
-                                   f"{100.0 * infos[0].holes / (H * W):.2f}% holes)",
+            "config": {"workload": DeviceBench.workload_text(argparse.Namespace(wl=wl), name, infos),
                        "timed_region": "depth smoothing+max pass, device tables, warp+fill+pack, hole blur, commit+strip; inputs/outputs in HBM",
-                       "l2": f"inputs per step {int((frames_h.nbytes + raw_h.nbytes) / 2**20)} MiB + outputs "
-                             f"{int(o_np.nbytes / 2**20)} MiB per GPU > 126 MB L2 (no flush needed)",
+                       "l2": f"inputs per step {int((B * H * W * 5) / 2**20)} MiB + outputs "
+                             f"{int(B * H * W * 6 / 2**20)} MiB per GPU > 126 MB L2 (no flush needed)",
                        "sharding": "independent clip range per GPU (same seeded content on every rank: fixed work per GPU), no collective", "depth_input": args.depth_input, "cpu_binding": binding,
-                       "route": f"general row kernel (scatter_mode={args.scatter_mode})" if args.scatter_mode else "default (k_depth_pass, k_build_tables, k_warp_ws, k_blur_holes_fixed, k_blur_commit)"},
+                       "route": f"general row kernel (scatter_mode={args.scatter_mode})" if args.scatter_mode else ROUTE},
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "per_rank": per_rank,
-            "roofline": {"bound": "hbm", "kernel": "k_warp_rows" if args.scatter_mode else ("k_warp_ws" if W % 32 == 0 else "k_warp_fused"), "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": abytes, "launch_ms": warp_ms / max(warp_n, 1)},
+            "roofline": roof,
             "stage_ms_per_step": {k: v[0] / args.steps for k, v in stage.items()},
-            "e2e_equals_device_output": same,
+            "ms_per_step_with_stage_events": ms_rank_staged / args.steps,
+            "e2e_equals_device_output": same, "e2e_frames_equal": f"{same_frames}/{B}",
         }
+        if extra:
+            line["configs"] = extra
         if video:
             line["video"] = video
         if cpu:
             line["cpu_baseline"] = cpu
+        if ref_cuda:
+            line["reference_cuda"] = ref_cuda
+        if producer:
+            line["producer"] = producer
         print(json.dumps(line))
-    ctx.close()
-    proc.close()
     ranks.close()
 
 
 # ---------------------------------------------------------------------------------------------------------
+# CPU baselines.  "reference" = the UNMODIFIED reference class (oracle/_ref staged copy, or /root/reference in the
+# build container) behind the CPU device proxy of oracle/ref_driver.py, parallelised the way the reference itself
+# parallelises: Num_Workers processes, each owning a contiguous clip range with its own state (main_func,
+# PredictAndGenerate.py:274-275,300-306).  "port" = oracle/sbs_layered.py, used only when no reference copy exists.
+def _ref_cpu_worker(idx, path, lo, hi, wl, threads, barrier, out_q):
+    try:
+        import numpy as np
+        import torch
+        torch.set_num_threads(threads)
+        from oracle.ref_driver import ReferenceWarp
+        z = np.load(path, mmap_mode="r")
+        frames, raw = z["frames"], z["raw"]
+        warm = ReferenceWarp(wl["fg"], wl["bg"], wl["step"])
+        warm.left_side_sbs(np.ascontiguousarray(frames[lo]), torch.from_numpy(np.ascontiguousarray(raw[lo])))   # untimed: imports, allocator
+        ref = ReferenceWarp(wl["fg"], wl["bg"], wl["step"])          # fresh clip-range state, like a worker's SbsProcessor (:209)
+        barrier.wait()
+        t0 = time.perf_counter()
+        for t in range(lo, hi):
+            ref.left_side_sbs(np.ascontiguousarray(frames[t]), torch.from_numpy(np.ascontiguousarray(raw[t])))
+        out_q.put((idx, hi - lo, time.perf_counter() - t0, None))
+    except Exception as e:                                           # noqa: BLE001
+        try:
+            barrier.abort()
+        except Exception:
+            pass
+        out_q.put((idx, 0, 0.0, repr(e)))
+
+
+def reference_cpu_fps(wl, frames, raw, budget_s=20.0, workers=None, threads=None):
+    """frames/s of the unmodified reference warp on this box's host cores, on a bounded sample of the workload.
+    The worker processes start, import the reference and warm up OUTSIDE the timed region."""
+    import multiprocessing as mp
+    import tempfile
+
+    from oracle import ref_driver
+    if not ref_driver.reference_available():
+        return None
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    threads = threads or 1            # measured: one torch thread per worker and a worker per core beats 2x4 / 4x2 splits
+    workers = workers or max(1, cores // threads)
+    # ~0.4-1.5 s per 1080p frame per worker (4x that at 4K): size every worker's range to the budget
+    per_frame = 1.2 * (wl["H"] * wl["W"]) / (1080 * 1920) * (4.0 if wl["W"] > 2048 else 1.0)
+    per_worker = int(max(1, min(8, budget_s / per_frame)))
+    n = min(len(frames), workers * per_worker)
+    workers = min(workers, n)
+    bounds = [n * i // workers for i in range(workers + 1)]
+    tmp = tempfile.NamedTemporaryFile(suffix=".npz", dir="/dev/shm" if os.path.isdir("/dev/shm") else None, delete=False)
+    tmp.close()
+    try:
+        np.savez(tmp.name, frames=frames[:n], raw=raw[:n])
+        ctx = mp.get_context("spawn")
+        barrier, q = ctx.Barrier(workers + 1), ctx.Queue()
+        procs = [ctx.Process(target=_ref_cpu_worker, args=(i, tmp.name, bounds[i], bounds[i + 1], wl, threads, barrier, q))
+                 for i in range(workers)]
+        for p_ in procs:
+            p_.start()
+        try:
+            barrier.wait(timeout=600)
+        except Exception:
+            errs = []
+            while not q.empty():
+                errs.append(q.get()[3])
+            for p_ in procs:
+                p_.join(timeout=5)
+            raise RuntimeError(f"reference CPU workers failed to start: {errs}")
+        t0 = time.perf_counter()
+        res = [q.get(timeout=3600) for _ in procs]
+        dt = time.perf_counter() - t0
+        for p_ in procs:
+            p_.join()
+    finally:
+        os.unlink(tmp.name)
+    bad = [r[3] for r in res if r[3]]
+    if bad:
+        raise RuntimeError(f"reference CPU worker error: {bad[0]}")
+    import torch
+    return {"value": n / dt, "unit": UNIT, "cores": workers * threads, "kind": "reference",
+            "sample": f"{n} frames of the same workload ({wl['W']}x{wl['H']}) through the UNMODIFIED reference "
+                      f"SbsProcessor.left_side_sbs on the CPU (oracle/ref_driver.py device proxy; torch {torch.__version__}), "
+                      f"{workers} worker processes x {threads} torch threads on {cores} available host cores, one clip range "
+                      f"per worker like main_func's Num_Workers; start-up and one warm-up frame per worker untimed; "
+                      f"slowest worker {max(r[2] for r in res):.2f} s for {max(r[1] for r in res)} frames",
+            "workers": workers, "threads_per_worker": threads, "frames": n, "seconds": dt}
+
+
 def _cpu_worker(job):
     from oracle import sbs_layered as O
     img, depth, marks, steps, offsets, weights = job
@@ -393,9 +674,9 @@ def _cpu_worker(job):
 
 
 def cpu_port_fps(wl, frames, raw, budget_s=20.0, procs=None):
-    """The reference's algorithm on the host cores: oracle/sbs_layered.py (numpy layer loop, a port —
-    the Python reference itself cannot travel to the GPU box).  Smoothing + tables run serially (they
-    carry state), the per-frame warp — >99 % of the time — runs one frame per process."""
+    """Fallback when no copy of the reference exists: oracle/sbs_layered.py (numpy layer loop, a port).  Smoothing +
+    tables run serially (they carry state), the per-frame warp — >99 % of the time — runs one frame per process; the
+    pool is started before the timed region."""
     import multiprocessing as mp
 
     from oracle import sbs_layered as O
@@ -403,7 +684,6 @@ def cpu_port_fps(wl, frames, raw, budget_s=20.0, procs=None):
     procs = procs or cores
     st = O.WarpState(wl["fg"], wl["bg"], wl["step"])
     weights = O.gaussian_weights(*O.blur_kernel_shape(wl["H"]))
-    # calibrate on one frame, then size the sample to the budget
     d = O.smooth_depth(st, raw[0])
     tabs = O.layer_tables(st, d.max(), d.shape[0])
     t0 = time.perf_counter()
@@ -411,37 +691,46 @@ def cpu_port_fps(wl, frames, raw, budget_s=20.0, procs=None):
     one = time.perf_counter() - t0
     n = int(max(procs, min(len(frames) - 1, procs * max(1, int(budget_s / max(one, 1e-3))))))
     n = min(n, len(frames) - 1)
-    jobs = []
-    t0 = time.perf_counter()
-    for t in range(1, 1 + n):
-        d = O.smooth_depth(st, raw[t])
-        tabs = O.layer_tables(st, d.max(), d.shape[0])
-        jobs.append((frames[t], d, tabs[0], tabs[1], tabs[2], weights))
     with mp.get_context("fork").Pool(min(procs, n)) as pool:
+        pool.map(abs, range(procs))                                  # workers up before the clock starts
+        jobs = []
+        t0 = time.perf_counter()
+        for t in range(1, 1 + n):
+            d = O.smooth_depth(st, raw[t])
+            tabs = O.layer_tables(st, d.max(), d.shape[0])
+            jobs.append((frames[t], d, tabs[0], tabs[1], tabs[2], weights))
         pool.map(_cpu_worker, jobs, chunksize=1)
-    dt = time.perf_counter() - t0
+        dt = time.perf_counter() - t0
     return {"value": n / dt, "unit": UNIT, "cores": min(procs, n), "kind": "port",
             "sample": f"{n} frames of the same workload ({wl['W']}x{wl['H']}), oracle/sbs_layered.py numpy layer loop, "
                       f"one frame per process on {min(procs, n)} of {cores} host cores; single-frame latency {one:.2f} s"}
 
 
+def cpu_baseline(wl, frames, raw, budget_s):
+    r = reference_cpu_fps(wl, frames, raw, budget_s=budget_s)
+    return r if r is not None else cpu_port_fps(wl, frames, raw, budget_s=budget_s)
+
+
 def run_reference(args, wl, name):
-    """--impl reference: the CPU port of the reference's warp on this box's host cores."""
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    B = min(wl["B"], 1 + (os.cpu_count() or 1) * 4)
+    cores = os.cpu_count() or 1
+    B = min(wl["B"], max(8, cores * 4))
     sub = dict(wl, B=B)
     frames, lowres = make_inputs(sub, seed=100)
     from oracle import sbs_layered as O
     raw = np.stack([O.bicubic_resize(lowres[t], wl["H"], wl["W"], 1.0) for t in range(B)])
     vals = []
     for i in range(args.warmup + args.steps):
-        r = cpu_port_fps(sub, frames, raw, budget_s=args.cpu_budget / max(1, args.steps))
+        if i < args.warmup and i > 0:
+            continue                                                 # one warm-up pass is enough for a CPU arm
+        r = cpu_baseline(sub, frames, raw, budget_s=args.cpu_budget / max(1, args.steps))
         if i >= args.warmup:
             vals.append(r)
     v = float(np.mean([r["value"] for r in vals]))
-    n_frames = sum(int(r["sample"].split()[0]) for r in vals)
+    n_frames = sum(int(r.get("frames", r["sample"].split()[0])) for r in vals)
     cpu = dict(vals[-1], value=v)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
@@ -468,8 +757,11 @@ def main():
     ap.add_argument("--bind", action="store_true",
                     help="bind the process to the CPUs sysfs lists as local to its GPU (shard.bind_near_gpu); off by default: "
                          "not yet measured on a multi-socket 8-GPU box")
-    ap.add_argument("--video-frames", type=int, default=0,
-                    help="also stream an N-frame synthetic video (e.g. 18000 = 10 min of 1080p30), sharded by clip range over the ranks")
+    ap.add_argument("--video-frames", type=int, default=3600,
+                    help="stream an N-frame synthetic video sharded by clip range over the ranks (BASELINE.json configs[4]; default "
+                         "3600 = 2 min of 1080p30 so that the default run stays short, 18000 = the full 10 minutes, 0 = skip)")
+    ap.add_argument("--no-4k", dest="also_4k", action="store_false", help="skip the 4k_wide_b16 sub-record (configs[2])")
+    ap.add_argument("--no-producer", action="store_true", help="skip the depth producer timing")
     ap.add_argument("--host-opt", action="append", default=[], help="library option name=value for the host-API context")
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (vrsbs_set_option)")
     ap.add_argument("--pageable", action="store_true", help="also time the host API with pageable numpy buffers")

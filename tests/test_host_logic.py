@@ -105,8 +105,9 @@ def test_synth_is_deterministic_and_shaped():
 
 
 def test_bench_reference_arm_prints_the_contract_line():
-    """`bench.py --impl reference` (the CPU port timed on the host cores) runs without a GPU and prints one JSON line
-    with the keys the driver reads; under a multi-rank launch only rank 0 works."""
+    """`bench.py --impl reference` (the unmodified reference on the host cores; the numpy port only where no copy of the
+    reference exists) runs without a GPU and prints one JSON line with the keys the driver reads; under a multi-rank
+    launch only rank 0 works."""
     import json
     import os
     import subprocess
@@ -122,9 +123,16 @@ def test_bench_reference_arm_prints_the_contract_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "sbs_frames_per_sec_warp_stage" and d["unit"] == "frames/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "frames" in d["cpu_baseline"]["sample"]
+    from oracle import ref_driver
+    kind = "reference" if ref_driver.reference_available() else "port"
+    assert d["cpu_baseline"]["kind"] == kind and d["cpu_baseline"]["cores"] >= 1 and "frames" in d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and d["gpu_launches"] == 0
+    if kind == "reference":                                 # a box without any copy of the reference: the port
+        outp = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(env, VRSBS_NO_REFERENCE="1"), cwd=root)
+        assert outp.returncode == 0, outp.stderr[-2000:]
+        dp = json.loads([l for l in outp.stdout.splitlines() if l.startswith("{")][0])
+        assert dp["cpu_baseline"]["kind"] == "port" and dp["value"] > 0
     # any other rank exits 0 without output
     out1 = subprocess.run(cmd, capture_output=True, text=True, timeout=120, env=dict(env, RANK="1", WORLD_SIZE="2"), cwd=root)
     assert out1.returncode == 0 and out1.stdout.strip() == ""

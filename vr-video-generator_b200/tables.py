@@ -73,17 +73,19 @@ def blur_kernel_shape(height):
     return k * 2 + 3, k * 2 + 1
 
 
-def gaussian_weights(kx, ky, sigma=3.0):
-    """fp32 [ky,kx] kernel exactly as torchvision 0.26 `_get_gaussian_kernel2d` builds it on the
-    CPU (same torch ops, same order): softmax(-(linspace(-lim,lim,k)/sigma)^2), outer product."""
+def gaussian_weights(kx, ky, sigma=3.0, device=None):
+    """fp32 [ky,kx] kernel exactly as torchvision 0.26 `_get_gaussian_kernel2d` builds it (same torch ops, same
+    order): softmax(-(linspace(-lim,lim,k)/sigma)^2), outer product.  `device` = where the torch ops run: the
+    reference's torchvision builds the kernel on the image's device (CUDA in production, the CPU under the golden
+    fixtures' device proxy); None = CPU.  tests/test_gpu_reference_cuda.py measures whether the two differ."""
     import torch
 
     def one(n):
         lim = (n - 1) / (2.0 * math.sqrt(2.0))
-        x = torch.linspace(-lim, lim, steps=n, dtype=torch.float32)
+        x = torch.linspace(-lim, lim, steps=n, dtype=torch.float32, device=device)
         return torch.softmax(x.div(sigma).pow(2).neg(), dim=0)
 
-    return (one(ky).unsqueeze(-1) * one(kx)).contiguous().numpy()
+    return (one(ky).unsqueeze(-1) * one(kx)).contiguous().cpu().numpy()
 
 
 def clip_ranges(start_frame, end_frame, video_length, num_workers):
