@@ -172,7 +172,9 @@ int  vrsbs_get_stage_times(vrsbs_ctx *ctx, double ms[VRSBS_NUM_STAGES], uint64_t
  *   k_warp_ws, 0 = barrier-synchronised k_warp_fused), "ws_scatter_warps" (scatter/destination split of k_warp_ws),
  *   "smooth_in_warp" (see vrsbs_process_batch), "fast_tables" (0 forces the slow membership path),
  *   "scatter_mode" of the general row kernel (2 = atomicMax for every key, 1 = plain store + verify),
- *   "blur_screen" (1 = one-multiply screening sum before the exact integer blur, 0 = exact sum for every hole),
+ *   "blur_sep" (1 = separable screening kernel k_blur_sep when the weights are near rank 1, 0 = k_blur_holes_fixed,
+ *   2 = k_blur_sep with every value sent to its exact fallback),
+ *   "blur_screen" (1 = screening sum before the exact integer blur, 0 = exact sum for every hole),
  *   "commit_mode", "lowres_tiled", "bicubic_contract", "blocks_per_sm", "host_chunk", "copy_threads",
  *   "pageable_direct", "host_right_half", "stage_timing". */
 int  vrsbs_set_option(vrsbs_ctx *ctx, const char *name, int value);

@@ -283,13 +283,15 @@ def test_blur_weight_paths(oracle_lib):
     # specialised instantiations; 7x5 runs the generic integer kernel
     for w in (O.gaussian_weights(11, 9), O.gaussian_weights(19, 17), O.gaussian_weights(9, 7), O.gaussian_weights(13, 11),
               O.gaussian_weights(7, 5), asym):
-        ctx = _ctx(H, W, 0.08, -0.05, 1, w)
-        sbs, _, _, masks = _run_device(ctx, frames, raw)
         want, stages = _oracle_run(oracle_lib, dict(fg=0.08, bg=-0.05, step=1), frames, raw, w)
-        assert masks.sum() > 500
-        for t in range(2):
-            assert np.array_equal(sbs[t], want[t]), (w.shape, t, int((sbs[t] != want[t]).sum()))
-        ctx.close()
+        for sep in (1, 0):                                      # separable screening kernel (default) / 2-D screening kernel
+            ctx = _ctx(H, W, 0.08, -0.05, 1, w)
+            ctx.set_option("blur_sep", sep)
+            sbs, _, _, masks = _run_device(ctx, frames, raw)
+            assert masks.sum() > 500
+            for t in range(2):
+                assert np.array_equal(sbs[t], want[t]), (w.shape, sep, t, int((sbs[t] != want[t]).sum()))
+            ctx.close()
 
 
 def test_rejected_frames():
@@ -583,24 +585,29 @@ def test_warp_specialised_splits(split, oracle_lib):
         ctx.close()
 
 
-@pytest.mark.parametrize("screen", [1, 0])
+@pytest.mark.parametrize("screen", ["sep", "sep_all_exact", "fixed", "fixed_exact"])
 def test_blur_screening_is_exact(screen, oracle_lib):
-    """Every pixel a hole (zero depth), so the blur evaluates ~390k values per frame: the one-multiply screening
-    sum followed by the exact sum for the undecided values (blur_screen=1) and the exact sum for every value
-    (blur_screen=0) both equal the oracle bit for bit, for the 1080p (11x9, 2 parts) and the 4K (19x17, 3 parts)
-    gaussians, on random bytes and on a two-level image (sums cluster, more near-ties)."""
+    """Every pixel a hole (zero depth), so the blur evaluates ~390k values per frame.  All four evaluation routes equal the
+    oracle bit for bit: the separable screening kernel with its exact fallback for the undecided values (default), the same
+    kernel with EVERY value sent to the fallback, the 2-D one-multiply screening kernel (blur_sep=0), and the exact 2-D sum
+    for every value (blur_screen=0) - for the 1080p (11x9, 2 parts), 4K (19x17, 3 parts), 720p and 1440p gaussians, on
+    random bytes, on a two-level image (sums cluster, more near-ties; 0/255 maximises the separable kernel's error) and on
+    a constant image (every sum lands on the same near-integer)."""
     rng = np.random.default_rng(23)
     H, W = 270, 480
-    frames = rng.integers(0, 256, size=(2, H, W, 3), dtype=np.uint8)
+    frames = rng.integers(0, 256, size=(3, H, W, 3), dtype=np.uint8)
     frames[1] = np.where(rng.random((H, W, 3)) < 0.5, 0, 255).astype(np.uint8)
-    raw = np.zeros((2, H, W), dtype=np.float16)
+    frames[2] = 255
+    frames[2, : H // 2] = 127
+    raw = np.zeros((3, H, W), dtype=np.float16)
     for w in (O.gaussian_weights(11, 9), O.gaussian_weights(19, 17), O.gaussian_weights(9, 7), O.gaussian_weights(13, 11)):
         ctx = _ctx(H, W, 0.025, -0.01, 1, w)
-        ctx.set_option("blur_screen", screen)
+        ctx.set_option("blur_sep", {"sep": 1, "sep_all_exact": 2}.get(screen, 0))
+        ctx.set_option("blur_screen", 0 if screen == "fixed_exact" else 1)
         sbs, _, infos, masks = _run_device(ctx, frames, raw)
         want, _ = _oracle_run(oracle_lib, dict(fg=0.025, bg=-0.01, step=1), frames, raw, w)
         assert infos[0].holes == H * W
-        for t in range(2):
+        for t in range(3):
             assert np.array_equal(sbs[t], want[t]), (w.shape, screen, t, int((sbs[t] != want[t]).sum()))
         ctx.close()
 

@@ -166,6 +166,8 @@ __global__ void __launch_bounds__(256, 4) k_blur_holes_fixed(BlurArgs a, const _
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int W = a.W, H = a.H;
     uint16_t *Tw = reinterpret_cast<uint16_t *>(blur_smem) + (size_t)warp * (G * TSZ);
+    pdl_launch_dependents();
+    pdl_wait();
     const uint32_t count = *a.hole_count;
     const size_t pitch = (size_t)W * 6;
 
@@ -411,11 +413,227 @@ __host__ __device__ constexpr size_t blur_fixed_warp_smem() {
     return (size_t)blur_group<CX>() * ((size_t)(CY + 1) * COLS + 32) * sizeof(uint16_t);
 }
 
+// ---- separable screening: the default hole blur for torchvision's gaussians ------------------------------------
+// The reference's 2-D kernel is w[i][j] = fl32(ky[i] * kx[j]): not separable bit for bit, but within 2^-24 relative
+// of a rank-1 kernel.  The blurred value is defined by the EXACT sum of w[i][j] * pixel (see above); what decides the
+// output byte is on which side of a half-integer that sum falls.  So the sum is first evaluated with a separable
+// integer kernel A[i][j] = hy[|i-cy|] * hx[|j-cx|] (scale 2^s, s = 52): one vertical pass per staged byte column
+// (V[c] = sum_i hy[i] * (row(y-i)[c] + row(y+i)[c]), 32-bit, done once per footprint column while staging) and one
+// horizontal pass per hole and channel (sum_j hx[j] * (V[c-3j] + V[c+3j]), CX+1 64-bit multiply-adds instead of
+// (CX+1)(CY+1) taps).  The host computes, in exact integer arithmetic over the caller's actual weights, a bound eps on
+// |exact - separable| * 2^s for any pixel content (vrsbs_set_blur_weights); a value whose separable sum lies further
+// than eps from every half-integer is decided.  The others - about 2 * eps = 0.02-0.04 % of the values, which includes
+// every true tie - are recomputed EXACTLY (PARTS-way integer sum over the 2-D weights, straight from global memory).
+// The result is therefore bit-identical to k_blur_holes / k_blur_holes_fixed and to the oracle for every input;
+// tests run every pixel of all-hole frames through all three.
+template <int CX, int CY>
+struct BlurSepWeights { uint32_t hy[CY + 1]; uint32_t hx[CX + 1]; uint32_t s, eps32; };
+
+constexpr int kBlurSepGroup = 8;                   // list entries staged per warp before their holes are evaluated together
+
+template <int CX>
+__host__ __device__ constexpr int blur_sep_vcols() {
+    constexpr int PHASE = ((-3 * CX) % 4 + 4) % 4;
+    return (PHASE + 3 * (32 + 2 * CX) + 3) / 4 * 4;
+}
+template <int CX>
+__host__ __device__ constexpr size_t blur_sep_warp_smem() { return (size_t)kBlurSepGroup * (blur_sep_vcols<CX>() + 16) * sizeof(uint32_t); }
+
+// exact blurred value of one (pixel, channel) from global memory: the rare path behind the separable screening
+template <int PARTS>
+__device__ __noinline__ uint32_t blur_exact_global(const uint8_t *left, size_t pitch, int H, int W, int y, int x, int ch,
+                                                   const uint32_t *wq, int cx, int cy, int S) {
+    constexpr int PBITS = PARTS == 2 ? 15 : 13;
+    uint32_t acc[PARTS];
+#pragma unroll
+    for (int p = 0; p < PARTS; ++p) acc[p] = 0u;
+    const int nw = (cy + 1) * (cx + 1);
+    for (int i = -cy; i <= cy; ++i) {
+        const uint8_t *rowp = left + (size_t)reflect_idx(y + i, H) * pitch + ch;
+        const uint32_t *wr = wq + (i < 0 ? -i : i) * (cx + 1);
+        for (int j = -cx; j <= cx; ++j) {
+            const uint32_t v = rowp[(size_t)min(max(reflect_idx(x + j, W), 0), W - 1) * 3];
+#pragma unroll
+            for (int p = 0; p < PARTS; ++p) acc[p] += v * __ldg(wr + p * nw + (j < 0 ? -j : j));
+        }
+    }
+    unsigned long long total = 0ull;
+#pragma unroll
+    for (int p = PARTS - 1; p >= 0; --p) total = (total << PBITS) + acc[p];
+    unsigned long long q = total >> S;
+    const unsigned long long r = total & ((1ull << S) - 1ull), half = 1ull << (S - 1);
+    q += (r > half || (r == half && (q & 1ull))) ? 1ull : 0ull;
+    return (uint32_t)q;
+}
+
+template <int PARTS, int CX, int CY>
+__global__ void __launch_bounds__(256, 4) k_blur_sep(BlurArgs a, const __grid_constant__ BlurSepWeights<CX, CY> wts) {
+    constexpr int KX = 2 * CX + 1, NPX = 32 + KX - 1;
+    constexpr int PHASE = ((-3 * CX) % 4 + 4) % 4;                    // (96 w - 3 CX) mod 4: the same for every word
+    constexpr int NWORDS = (PHASE + 3 * NPX + 3) / 4;                 // aligned 32-bit words that cover the footprint
+    constexpr int VCOLS = NWORDS * 4;
+    constexpr int G = kBlurSepGroup;
+    constexpr int TAILW = NWORDS > 32 ? NWORDS - 32 : 0;              // words past the 32nd (wide footprints)
+    static_assert(NWORDS <= 64 && VCOLS == blur_sep_vcols<CX>(), "footprint layout");
+    extern __shared__ __align__(16) uint8_t blur_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int W = a.W, H = a.H;
+    uint32_t *Vw = reinterpret_cast<uint32_t *>(blur_smem) + (size_t)warp * (G * (VCOLS + 16));
+    uint16_t *tasktab = reinterpret_cast<uint16_t *>(Vw + G * VCOLS);  // [G * 32]: (entry << 8 | pixel) of every hole of the group
+    pdl_launch_dependents();
+    pdl_wait();                                  // the warp kernel's frame, hole mask and hole list
+    const uint32_t count = *a.hole_count;
+    const size_t pitch = (size_t)W * 6;
+
+    // entry metadata, one group ahead: lane g (< G) holds (list entry, mask with the strip columns removed) of entry e0 + g
+    auto fetch_meta = [&](uint32_t e0, uint32_t &ent, uint32_t &m) {
+        ent = 0u; m = 0u;
+        if (lane < G && e0 < count && e0 + lane < count) {
+            ent = a.hole_list[e0 + lane];
+            const uint32_t row = ent >> 8;
+            const int xw = (int)(ent & 0xffu) * 32;
+            const int strip = a.tabs[(int)(((unsigned long long)row * a.magic_h) >> 40)].strip;
+            m = a.hole_mask[(size_t)row * a.Wwords + (ent & 0xffu)];
+            if (strip > xw) m = (strip - xw >= 32) ? 0u : (m & ~((1u << (strip - xw)) - 1u));
+        }
+    };
+    auto decode = [&](uint32_t ent, int &b, int &y, int &xw) {
+        const uint32_t row = ent >> 8;
+        b = (int)(((unsigned long long)row * a.magic_h) >> 40);
+        y = (int)row - b * H;
+        xw = (int)(ent & 0xffu) * 32;
+    };
+    // vertical pass on one aligned word (4 byte columns) of the footprint: V = sum_i hy[i] * (row(y-i) + row(y+i)), on packed
+    // u16 pair sums; the row pairs are loaded CH at a time (2 * CH loads in flight per lane)
+    auto stage_word = [&](uint32_t *Vdst, const uint8_t *colp, int y) {
+        constexpr int CH = 4;
+        const bool inside = (y - CY >= 0) && (y + CY < H);
+        const uint8_t *pc = colp + (size_t)y * pitch;
+        const uint32_t c0 = __ldg(reinterpret_cast<const uint32_t *>(pc));
+        uint32_t V0, V1, V2, V3;
+#pragma unroll
+        for (int i0 = 1; i0 <= CY; i0 += CH) {
+            uint32_t p[CH], q[CH];
+#pragma unroll
+            for (int k = 0; k < CH; ++k) {
+                const int i = i0 + k;
+                if (i > CY) continue;
+                if (inside) {
+                    p[k] = __ldg(reinterpret_cast<const uint32_t *>(pc - (size_t)i * pitch));
+                    q[k] = __ldg(reinterpret_cast<const uint32_t *>(pc + (size_t)i * pitch));
+                } else {
+                    p[k] = __ldg(reinterpret_cast<const uint32_t *>(colp + (size_t)reflect_idx(y - i, H) * pitch));
+                    q[k] = __ldg(reinterpret_cast<const uint32_t *>(colp + (size_t)reflect_idx(y + i, H) * pitch));
+                }
+            }
+            if (i0 == 1) {
+                const uint32_t lo = __byte_perm(c0, 0u, 0x4140), hi = __byte_perm(c0, 0u, 0x4342);
+                V0 = (lo & 0xffffu) * wts.hy[0]; V1 = (lo >> 16) * wts.hy[0]; V2 = (hi & 0xffffu) * wts.hy[0]; V3 = (hi >> 16) * wts.hy[0];
+            }
+#pragma unroll
+            for (int k = 0; k < CH; ++k) {
+                const int i = i0 + k;
+                if (i > CY) continue;
+                const uint32_t lo = __byte_perm(p[k], 0u, 0x4140) + __byte_perm(q[k], 0u, 0x4140);
+                const uint32_t hi = __byte_perm(p[k], 0u, 0x4342) + __byte_perm(q[k], 0u, 0x4342);
+                V0 += (lo & 0xffffu) * wts.hy[i]; V1 += (lo >> 16) * wts.hy[i];
+                V2 += (hi & 0xffffu) * wts.hy[i]; V3 += (hi >> 16) * wts.hy[i];
+            }
+        }
+        if (CY == 0) {
+            const uint32_t lo = __byte_perm(c0, 0u, 0x4140), hi = __byte_perm(c0, 0u, 0x4342);
+            V0 = (lo & 0xffffu) * wts.hy[0]; V1 = (lo >> 16) * wts.hy[0]; V2 = (hi & 0xffffu) * wts.hy[0]; V3 = (hi >> 16) * wts.hy[0];
+        }
+        *reinterpret_cast<uint4 *>(Vdst) = make_uint4(V0, V1, V2, V3);
+    };
+
+    const uint32_t stride = gridDim.x * nwarps * G;
+    uint32_t ent_n, m_n;
+    fetch_meta((blockIdx.x * nwarps + warp) * G, ent_n, m_n);
+    for (uint32_t e0 = (blockIdx.x * nwarps + warp) * G; e0 < count; e0 += stride) {
+        const uint32_t ent_c = ent_n, m_c = m_n;
+        fetch_meta(e0 + stride, ent_n, m_n);
+        __syncwarp();
+        // ---- stage: hole table + V columns of up to G entries ----
+        uint32_t nholes = 0, border = 0, live = 0;
+#pragma unroll 2
+        for (int g = 0; g < G; ++g) {
+            const uint32_t ent = __shfl_sync(0xffffffffu, ent_c, g), m = __shfl_sync(0xffffffffu, m_c, g);
+            if (m == 0u) continue;
+            live |= 1u << g;
+            int b, y, xw;
+            decode(ent, b, y, xw);
+            if ((m >> lane) & 1u) tasktab[nholes + __popc(m & ((1u << lane) - 1u))] = (uint16_t)((g << 8) | lane);
+            nholes += (uint32_t)__popc(m);
+            const uint8_t *left = a.sbs + (size_t)b * H * pitch;
+            uint32_t *V = Vw + g * VCOLS;
+            if (xw - CX >= 0 && xw + 31 + CX < W) {
+                if (NWORDS >= 32 || lane < NWORDS) stage_word(V + 4 * lane, left + (3 * (xw - CX) - PHASE) + 4 * lane, y);
+            } else {
+                // border words: byte by byte with reflect padding (phase 0)
+                border |= 1u << g;
+                for (int c = lane; c < 3 * NPX; c += 32) {
+                    const int px = c / 3, ch = c - px * 3;
+                    const int X = min(max(reflect_idx(xw - CX + px, W), 0), W - 1);
+                    const uint8_t *colp = left + (size_t)X * 3 + ch;
+                    uint32_t acc = (uint32_t)colp[(size_t)y * pitch] * wts.hy[0];
+#pragma unroll
+                    for (int i = 1; i <= CY; ++i)
+                        acc += ((uint32_t)colp[(size_t)reflect_idx(y - i, H) * pitch] + (uint32_t)colp[(size_t)reflect_idx(y + i, H) * pitch]) * wts.hy[i];
+                    V[c] = acc;
+                }
+            }
+        }
+        if (TAILW > 0) {
+            // words past the 32nd of the interior entries: lane = (entry, tail word), several entries per pass
+            constexpr int EPP = TAILW > 0 ? 32 / (TAILW > 0 ? TAILW : 1) : 1;   // entries per pass
+#pragma unroll
+            for (int gb = 0; gb < G; gb += EPP) {
+                const int tg = gb + lane / (TAILW > 0 ? TAILW : 1), tw = lane % (TAILW > 0 ? TAILW : 1);
+                const uint32_t ent = __shfl_sync(0xffffffffu, ent_c, tg & 31);
+                const bool on = tg < G && tg < gb + EPP && ((live & ~border) >> tg) & 1u;
+                if (on) {
+                    int b, y, xw;
+                    decode(ent, b, y, xw);
+                    stage_word(Vw + tg * VCOLS + 4 * (32 + tw), a.sbs + (size_t)b * H * pitch + (3 * (xw - CX) - PHASE) + 4 * (32 + tw), y);
+                }
+            }
+        }
+        __syncwarp();
+        // ---- evaluate: task = (hole of the group, channel), 32 tasks per pass ----
+        const uint32_t tasks = 3u * nholes;
+        for (uint32_t t0 = 0; t0 < tasks; t0 += 32) {
+            const uint32_t task = t0 + lane;
+            const bool on = task < tasks;
+            const uint32_t hidx = on ? task / 3u : 0u, ch = task - hidx * 3u;
+            const uint32_t code = tasktab[hidx];
+            const uint32_t g = code >> 8, xo = code & 0xffu;
+            const uint32_t ent = __shfl_sync(0xffffffffu, ent_c, g);
+            if (!on) continue;
+            const uint32_t phase = ((border >> g) & 1u) ? 0u : (uint32_t)PHASE;
+            const uint32_t *Vc = Vw + g * VCOLS + phase + 3u * (xo + CX) + ch;
+            unsigned long long acc = (unsigned long long)Vc[0] * wts.hx[0];
+#pragma unroll
+            for (int j = 1; j <= CX; ++j) acc += (unsigned long long)(Vc[-3 * j] + Vc[3 * j]) * wts.hx[j];
+            const uint32_t r32 = (uint32_t)(acc >> (wts.s - 32u));                 // top 32 bits of the fractional part
+            uint32_t q = (uint32_t)(acc >> wts.s) + (r32 >> 31);
+            const uint32_t row = ent >> 8, xw = (ent & 0xffu) * 32u;
+            if (r32 - 0x80000000u + wts.eps32 <= 2u * wts.eps32) {                  // within eps of a half-integer: exact sum decides
+                int b, y, xw_;
+                decode(ent, b, y, xw_);
+                q = blur_exact_global<PARTS>(a.sbs + (size_t)b * H * pitch, pitch, H, W, y, (int)(xw + xo), (int)ch, a.wq, CX, CY, a.wshift);
+            }
+            a.plane[((size_t)row * W + xw + xo) * 3 + ch] = (uint8_t)q;
+        }
+    }
+}
+
 // plane -> SBS frame for the listed holes right of the strip, then result_img[:, 0:strip] = img[:, 0:strip]
 // (PredictAndGenerate.py:196).  A warp takes 32 list entries at a time: lane l fetches entry l's word index, mask
 // and strip (one round of dependent loads for 32 entries), then the warp walks the entries, lane = pixel.
 __global__ void __launch_bounds__(256) k_blur_commit(BlurArgs a, int do_commit) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    pdl_wait();                                  // every blurred value is in the plane
     const uint32_t count = (do_commit & 1) ? *a.hole_count : 0u;      // do_commit: bit 0 = hole values, bit 1 = skip the strip (experiments)
     constexpr int E = 4;                                   // entries per warp step: four independent load chains in flight
     for (uint32_t e0 = (blockIdx.x * nwarps + warp) * E; e0 < count; e0 += gridDim.x * nwarps * E) {

@@ -162,6 +162,14 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 // make generic-proxy smem writes visible to the async proxy (before a bulk store reads them)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// become resident while its predecessor in the stream is still draining; pdl_wait() blocks until the predecessor grid
+// has completed and its writes are visible (a no-op for a normal launch), pdl_launch_dependents() lets the successor's
+// CTAs be scheduled as soon as every CTA of this grid has got that far.  Every kernel of the default route executes
+// pdl_wait() before its first global read, so completion is transitive along the chain.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __host__ __device__ __forceinline__ int wrap_mod(int v, int n) {
     v %= n;
     return v < 0 ? v + n : v;

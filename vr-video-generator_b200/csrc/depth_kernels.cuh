@@ -143,6 +143,7 @@ __device__ __forceinline__ uint32_t h16_key(uint32_t u) {
 template <bool STORE>
 __global__ void __launch_bounds__(256) k_depth_pass(DepthMaxArgs a) {
     extern __shared__ uint32_t s_red[];          // [B] keys
+    pdl_launch_dependents();
     for (int i = threadIdx.x; i < a.B; i += blockDim.x) s_red[i] = 0;
     __syncthreads();
     const size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

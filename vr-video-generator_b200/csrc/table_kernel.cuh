@@ -64,6 +64,8 @@ __global__ void __launch_bounds__(256) k_build_tables(TableArgs a) {
 
     const int b = blockIdx.x;
     FrameTab *tab = a.tabs + b;
+    pdl_launch_dependents();
+    pdl_wait();                                  // the frame maxima of the depth pass
 
     // this frame's own range for every frame up to b, in parallel (the divisions are the expensive part) ...
     double *s_cur0 = s_val, *s_cur1 = s_sorted;                      // both reused as mark buffers afterwards

@@ -12,6 +12,7 @@
 #include <deque>
 #include <mutex>
 #include <thread>
+#include <utility>
 #include <vector>
 
 #include "blur_holes.cuh"
@@ -179,6 +180,10 @@ struct vrsbs_ctx {
     std::vector<uint32_t> wq_host, wh_host;   // exact parts / screening weights floor(w * 2^s1) of the integer blur
     uint32_t ws1 = 1, wrmax = 2;
     int blur_screen = 1;
+    std::vector<uint32_t> sep_hy, sep_hx;     // separable screening kernel of k_blur_sep (scale 2^sep_s), empty if the weights are not near rank 1
+    uint32_t sep_s = 0, sep_eps32 = 0;
+    int blur_sep = 1;
+    int pdl = 1;                              // option: programmatic dependent launch along tables -> warp -> blur -> commit                         // option: 1 = k_blur_sep when the weights allow it, 0 = k_blur_holes_fixed
     int kx = 0, ky = 0, wparts = 0, wshift = 0;
     int ent_cap = 0, lut_cap = 0;        // fast-path table capacities of the last vrsbs_build_tables
     int key_pad = 0;                     // fast path: bound on |signed layer offset| in pixels (multiple of 32)
@@ -295,6 +300,20 @@ struct StageTimer {
         c->stamps.push_back({stage, a, b});
     }
 };
+
+// Kernel launch with the programmatic-dependent-launch attribute (see common.cuh): only for kernels that execute
+// pdl_wait() before their first global read, and only directly behind another kernel of this library (events recorded
+// for stage timing, or a memset, in between simply turn the edge back into an ordinary one).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 // ---- stage launchers (stream-ordered, no host sync) ---------------------------------------------------
 int clear_counters(vrsbs_ctx *c, Scratch &s, int B, cudaStream_t st) {
@@ -428,7 +447,7 @@ int launch_tables(vrsbs_ctx *c, Scratch &s, int B, int H, int W, cudaStream_t st
     const size_t smem = sizeof(double) * 2 * (size_t)(c->max_layers + 2 > B ? c->max_layers + 2 : B) +
                         sizeof(int) * (size_t)(c->max_layers + 2);
     StageTimer timer(c, st, 1);
-    k_build_tables<<<B, 256, smem, st>>>(a);
+    CU_TRY(c, launch_pdl(c->pdl != 0, k_build_tables, dim3(B), dim3(256), smem, st, a));
     CU_TRY(c, cudaGetLastError());
     c->launches++;
     c->state_idx ^= 1;
@@ -499,7 +518,7 @@ int launch_ws_inst(vrsbs_ctx *c, const FusedArgs &a, cudaStream_t st, bool *laun
     long long iters = (long long)a.B * a.H, grid = (long long)c->sm_count * occ;
     if (grid > iters) grid = iters;
     StageTimer timer(c, st, 2);
-    kern<<<(unsigned)grid, NT, w.lay.total, st>>>(w);
+    CU_TRY(c, launch_pdl(c->pdl != 0, kern, dim3((unsigned)grid), dim3(NT), w.lay.total, st, w));
     CU_TRY(c, cudaGetLastError());
     c->launches++;
     *launched = true;
@@ -532,7 +551,7 @@ bool fused_capable(const vrsbs_ctx *c, const void *frames, const void *depth, co
 // hole values -> SBS frame (when blur is on) and strip restore, one kernel
 int launch_commit(vrsbs_ctx *c, const BlurArgs &b, int do_commit, cudaStream_t st) {
     StageTimer timer(c, st, 4);
-    k_blur_commit<<<(unsigned)(c->sm_count * 32), 256, 0, st>>>(b, do_commit);   // short latency-bound tasks: one or two per warp
+    CU_TRY(c, launch_pdl(c->pdl != 0, k_blur_commit, dim3((unsigned)(c->sm_count * 32)), dim3(256), 0, st, b, do_commit));   // short latency-bound tasks: one or two per warp
     CU_TRY(c, cudaGetLastError());
     c->launches++;
     return VRSBS_OK;
@@ -557,7 +576,24 @@ int launch_blur_fixed(vrsbs_ctx *c, const BlurArgs &b, cudaStream_t st) {
     int occ = 0;
     CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, bsmem));
     if (occ < 1) occ = 1;
-    kern<<<(unsigned)(c->sm_count * occ), warps * 32, bsmem, st>>>(b, wts);
+    CU_TRY(c, launch_pdl(c->pdl != 0, kern, dim3((unsigned)(c->sm_count * occ)), dim3(warps * 32), bsmem, st, b, wts));
+    return VRSBS_OK;
+}
+
+template <int PARTS, int CX, int CY>
+int launch_blur_sep(vrsbs_ctx *c, const BlurArgs &b, cudaStream_t st) {
+    BlurSepWeights<CX, CY> wts;
+    memcpy(wts.hy, c->sep_hy.data(), sizeof(wts.hy));
+    memcpy(wts.hx, c->sep_hx.data(), sizeof(wts.hx));
+    wts.s = c->sep_s; wts.eps32 = c->blur_sep == 2 ? 0x7fffffffu : c->sep_eps32;   // blur_sep = 2 (tests): every value takes the exact path
+    auto kern = k_blur_sep<PARTS, CX, CY>;
+    const int warps = 8;
+    const size_t bsmem = blur_sep_warp_smem<CX>() * warps;
+    CU_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+    int occ = 0;
+    CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, bsmem));
+    if (occ < 1) occ = 1;
+    CU_TRY(c, launch_pdl(c->pdl != 0, kern, dim3((unsigned)(c->sm_count * occ)), dim3(warps * 32), bsmem, st, b, wts));
     return VRSBS_OK;
 }
 
@@ -573,6 +609,22 @@ int launch_blur(vrsbs_ctx *c, Scratch &s, const uint8_t *frames, int B, int H, i
     {
         StageTimer timer(c, st, 3);
         bool done = false;
+        const bool sep = c->blur_sep && c->blur_screen && !c->sep_hy.empty();
+#define VRSBS_BLUR_SEP(P, CXv, CYv)                                                     \
+        if (!done && sep && aligned && c->wparts == P && cx == CXv && cy == CYv) {      \
+            int rc = launch_blur_sep<P, CXv, CYv>(c, b, st);                            \
+            if (rc) return rc;                                                          \
+            done = true;                                                                \
+        }
+        VRSBS_BLUR_SEP(2, 5, 4)        // 1080p: 11 x 9
+        VRSBS_BLUR_SEP(3, 5, 4)
+        VRSBS_BLUR_SEP(2, 9, 8)        // 4K: 19 x 17
+        VRSBS_BLUR_SEP(3, 9, 8)
+        VRSBS_BLUR_SEP(2, 4, 3)        // 720p: 9 x 7
+        VRSBS_BLUR_SEP(3, 4, 3)
+        VRSBS_BLUR_SEP(2, 6, 5)        // 1440p: 13 x 11
+        VRSBS_BLUR_SEP(3, 6, 5)
+#undef VRSBS_BLUR_SEP
 #define VRSBS_BLUR_FIXED(P, CXv, CYv)                                                   \
         if (!done && aligned && c->wparts == P && cx == CXv && cy == CYv) {             \
             int rc = launch_blur_fixed<P, CXv, CYv>(c, b, st);                          \
@@ -936,6 +988,56 @@ int vrsbs_set_blur_weights(vrsbs_ctx *c, const float *w, int kx, int ky) {
             CU_TRY(c, dmalloc(&c->wq, q.size()));
             CU_TRY(c, cudaMemcpy(c->wq, q.data(), sizeof(uint32_t) * q.size(), cudaMemcpyHostToDevice));
             c->wparts = parts; c->wshift = S;
+            // separable screening kernel (k_blur_sep): A[i][j] = hy[i] * hx[j] ~ w[i][j] * 2^s, taken from the centre row and
+            // column; eps = 255 * max(sum of positive, sum of negative) errors, in exact integer arithmetic
+            c->sep_hy.clear(); c->sep_hx.clear();
+            const double wcc = (double)w[cy * kx + cx];
+            if (wcc > 0.0 && S <= 100) {
+                const int a_bits = 30;
+                int b_bits = 22;
+                std::vector<uint32_t> hy(cy + 1), hx(cx + 1);
+                bool ok = false;
+                for (; b_bits >= 12 && !ok; --b_bits) {
+                    unsigned long long vsum = 0;
+                    for (int i = 0; i <= cy; ++i) {
+                        const double f = (double)w[(cy - i) * kx + cx] / sqrt(wcc);
+                        hy[i] = (uint32_t)llround(ldexp(f, b_bits));
+                        vsum += (i ? 2ull : 1ull) * hy[i];
+                    }
+                    ok = 2ull * 255ull * vsum < (1ull << 32);
+                    if (ok) break;
+                }
+                if (ok) {
+                    unsigned __int128 total = 0;
+                    bool fits = true;
+                    for (int j = 0; j <= cx; ++j) {
+                        const double f = (double)w[cy * kx + (cx - j)] / sqrt(wcc);
+                        const double v = ldexp(f, a_bits);
+                        if (!(v < 4294967295.0)) { fits = false; break; }
+                        hx[j] = (uint32_t)llround(v);
+                    }
+                    const int s_bits = a_bits + b_bits;
+                    if (fits && s_bits >= 40 && s_bits <= 60) {
+                        // common scale 2^m, m = max(s, S): errors e = A * 2^(m-s) - Wint * 2^(m-S)
+                        const int m = s_bits > S ? s_bits : S;
+                        unsigned __int128 pos = 0, neg = 0;
+                        for (int i = 0; i < ky; ++i)
+                            for (int j = 0; j < kx; ++j) {
+                                const int di = i < cy ? cy - i : i - cy, dj = j < cx ? cx - j : j - cx;
+                                const unsigned __int128 A = ((unsigned __int128)hy[di] * hx[dj]) << (m - s_bits);
+                                const unsigned __int128 Wi = ((unsigned __int128)(unsigned long long)ldexp((double)w[i * kx + j], S)) << (m - S);
+                                total += (unsigned __int128)hy[di] * hx[dj];
+                                if (A >= Wi) pos += A - Wi; else neg += Wi - A;
+                            }
+                        unsigned __int128 e = (pos > neg ? pos : neg) * 255u;
+                        e = (e >> (m - s_bits)) + 2;                                   // units of 2^-s, rounded up
+                        const unsigned __int128 e32 = (e >> (s_bits - 32)) + 2;        // units of 2^-32 of one output step
+                        if (total * 255u < ((unsigned __int128)1 << 63) && e32 < (1u << 22)) {   // < 0.1 % of the values undecided
+                            c->sep_hy = hy; c->sep_hx = hx; c->sep_s = (uint32_t)s_bits; c->sep_eps32 = (uint32_t)e32;
+                        }
+                    }
+                }
+            }
         }
     }
     return VRSBS_OK;
@@ -1190,6 +1292,8 @@ int vrsbs_set_option(vrsbs_ctx *c, const char *name, int value) {
     else if (!strcmp(name, "warp_ws")) c->warp_ws = value != 0;
     else if (!strcmp(name, "commit_mode")) c->commit_mode = value;
     else if (!strcmp(name, "blur_screen")) c->blur_screen = value ? 1 : 0;
+    else if (!strcmp(name, "blur_sep")) c->blur_sep = value;
+    else if (!strcmp(name, "pdl")) c->pdl = value ? 1 : 0;
     else if (!strcmp(name, "ws_scatter_warps")) c->ws_scatter_warps = value;
     else return fail(c, VRSBS_E_INVALID, "unknown option %s", name);
     return VRSBS_OK;

@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_ws(WsArgs wa) {
     const long long F = (long long)B * H;
     const long long f_lo = F * blockIdx.x / gridDim.x, f_hi = F * (blockIdx.x + 1) / gridDim.x;
     const int N = (int)(f_hi - f_lo);
+    pdl_launch_dependents();
     if (N <= 0) return;
 
     for (int i = tid; i < 2 * (int)(wa.lay.keys_stride / 16); i += NT) sts_zero128(sb + wa.lay.keys + 16u * i);
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_ws(WsArgs wa) {
         fence_mbar_init();
     }
     __syncthreads();
+    pdl_wait();                                  // tables (and, through them, the smoothed depth) are complete; the set-up above overlapped their tail
 
     int y0 = (int)(f_lo / B), t0 = (int)(f_lo - (long long)y0 * B);
     auto next_yt = [&](int &y, int &t) { if (++t == B) { t = 0; ++y; } };
