@@ -33,6 +33,7 @@ struct BlurArgs {
     const uint32_t *hole_mask;   // [B][H][Wwords]
     const uint32_t *hole_list;   // (global row << 8 | word index) of the mask words that contain holes
     const uint32_t *hole_count;
+    uint32_t *ticket;            // pre-zeroed work counter of k_blur_sep (next group of list entries)
     uint8_t *plane;              // [B,H,W,3] scratch: blurred values of hole pixels
     const uint32_t *wq;          // integer path: [PARTS][(cy+1)][(cx+1)] parts of w * 2^S, low part first (i = |dy|, j = |dx|)
     const float *weights;        // generic: [ky][kx]
@@ -547,12 +548,21 @@ __global__ void __launch_bounds__(256, 4) k_blur_sep(BlurArgs a, const __grid_co
         *reinterpret_cast<uint4 *>(Vdst) = make_uint4(V0, V1, V2, V3);
     };
 
-    const uint32_t stride = gridDim.x * nwarps * G;
+    // Groups of G list entries are handed out by a global ticket counter (the work per entry varies with its hole count,
+    // and a static split leaves a quarter of the warp slots idle at the end).  Tickets run two groups ahead: the atomic's
+    // round trip and the list -> mask / strip load chain of the next group both overlap the current group's work.
+    auto grab = [&]() -> uint32_t { return lane == 0 ? atomicAdd(a.ticket, 1u) : 0u; };
+    uint32_t t_a = __shfl_sync(0xffffffffu, grab(), 0);
+    uint32_t t_b_raw = grab();
     uint32_t ent_n, m_n;
-    fetch_meta((blockIdx.x * nwarps + warp) * G, ent_n, m_n);
-    for (uint32_t e0 = (blockIdx.x * nwarps + warp) * G; e0 < count; e0 += stride) {
+    fetch_meta(t_a * G, ent_n, m_n);
+    for (;;) {
+        const uint32_t e0 = t_a * G;
+        if (e0 >= count) break;
         const uint32_t ent_c = ent_n, m_c = m_n;
-        fetch_meta(e0 + stride, ent_n, m_n);
+        t_a = __shfl_sync(0xffffffffu, t_b_raw, 0);
+        fetch_meta(t_a * G, ent_n, m_n);
+        t_b_raw = grab();
         __syncwarp();
         // ---- stage: hole table + V columns of up to G entries ----
         uint32_t nholes = 0, border = 0, live = 0;

@@ -30,7 +30,7 @@ namespace {
 thread_local char g_create_error[256] = "";
 
 struct Scratch {                 // per-batch device scratch; one per pipeline slot
-    uint32_t *frame_max = nullptr, *frame_nan = nullptr;   // one allocation: [B] max | [B] nan | [1] hole_count
+    uint32_t *frame_max = nullptr, *frame_nan = nullptr;   // one allocation: [B] max | [B] nan | [1] hole_count | [1] blur ticket
     FrameTab *tabs = nullptr;
     float2 *bounds = nullptr;
     int *offm = nullptr;
@@ -183,7 +183,9 @@ struct vrsbs_ctx {
     std::vector<uint32_t> sep_hy, sep_hx;     // separable screening kernel of k_blur_sep (scale 2^sep_s), empty if the weights are not near rank 1
     uint32_t sep_s = 0, sep_eps32 = 0;
     int blur_sep = 1;
-    int pdl = 1;                              // option: programmatic dependent launch along tables -> warp -> blur -> commit                         // option: 1 = k_blur_sep when the weights allow it, 0 = k_blur_holes_fixed
+    int pdl = 0;                              // option (bit mask): programmatic dependent launch of 1 tables, 2 warp, 4 blur, 8 commit.
+                                              // Measured slower than plain stream order with all four edges on (0.532 vs 0.512 ms per
+                                              // 1080p step), so off by default                         // option: 1 = k_blur_sep when the weights allow it, 0 = k_blur_holes_fixed
     int kx = 0, ky = 0, wparts = 0, wshift = 0;
     int ent_cap = 0, lut_cap = 0;        // fast-path table capacities of the last vrsbs_build_tables
     int key_pad = 0;                     // fast path: bound on |signed layer offset| in pixels (multiple of 32)
@@ -255,7 +257,7 @@ void free_scratch(Scratch &s) {
 int alloc_scratch(vrsbs_ctx *c, Scratch &s) {
     const size_t B = c->max_batch, L = c->max_layers;
     const size_t mask_words = B * c->max_h * ((c->max_w + 31) / 32);
-    CU_TRY(c, dmalloc(&s.frame_max, 2 * B + 1));
+    CU_TRY(c, dmalloc(&s.frame_max, 2 * B + 2));
     s.frame_nan = s.frame_max + B;
     s.hole_count = s.frame_max + 2 * B;
     CU_TRY(c, dmalloc(&s.tabs, B));
@@ -318,14 +320,14 @@ cudaError_t launch_pdl(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, 
 // ---- stage launchers (stream-ordered, no host sync) ---------------------------------------------------
 int clear_counters(vrsbs_ctx *c, Scratch &s, int B, cudaStream_t st) {
     (void)B;
-    CU_TRY(c, cudaMemsetAsync(s.frame_max, 0, sizeof(uint32_t) * (2 * c->max_batch + 1), st));
+    CU_TRY(c, cudaMemsetAsync(s.frame_max, 0, sizeof(uint32_t) * (2 * c->max_batch + 2), st));
     s.holes_dirty = false;
     return VRSBS_OK;
 }
 
 // the hole work list must start empty for every warp launch (a second vrsbs_warp_batch without a depth call in between)
 int fresh_hole_list(vrsbs_ctx *c, Scratch &s, cudaStream_t st) {
-    if (s.holes_dirty) CU_TRY(c, cudaMemsetAsync(s.hole_count, 0, sizeof(uint32_t), st));
+    if (s.holes_dirty) CU_TRY(c, cudaMemsetAsync(s.hole_count, 0, 2 * sizeof(uint32_t), st));   // hole count + blur ticket
     s.holes_dirty = true;
     return VRSBS_OK;
 }
@@ -447,7 +449,7 @@ int launch_tables(vrsbs_ctx *c, Scratch &s, int B, int H, int W, cudaStream_t st
     const size_t smem = sizeof(double) * 2 * (size_t)(c->max_layers + 2 > B ? c->max_layers + 2 : B) +
                         sizeof(int) * (size_t)(c->max_layers + 2);
     StageTimer timer(c, st, 1);
-    CU_TRY(c, launch_pdl(c->pdl != 0, k_build_tables, dim3(B), dim3(256), smem, st, a));
+    CU_TRY(c, launch_pdl((c->pdl & 1) != 0, k_build_tables, dim3(B), dim3(256), smem, st, a));
     CU_TRY(c, cudaGetLastError());
     c->launches++;
     c->state_idx ^= 1;
@@ -518,7 +520,7 @@ int launch_ws_inst(vrsbs_ctx *c, const FusedArgs &a, cudaStream_t st, bool *laun
     long long iters = (long long)a.B * a.H, grid = (long long)c->sm_count * occ;
     if (grid > iters) grid = iters;
     StageTimer timer(c, st, 2);
-    CU_TRY(c, launch_pdl(c->pdl != 0, kern, dim3((unsigned)grid), dim3(NT), w.lay.total, st, w));
+    CU_TRY(c, launch_pdl((c->pdl & 2) != 0, kern, dim3((unsigned)grid), dim3(NT), w.lay.total, st, w));
     CU_TRY(c, cudaGetLastError());
     c->launches++;
     *launched = true;
@@ -551,7 +553,7 @@ bool fused_capable(const vrsbs_ctx *c, const void *frames, const void *depth, co
 // hole values -> SBS frame (when blur is on) and strip restore, one kernel
 int launch_commit(vrsbs_ctx *c, const BlurArgs &b, int do_commit, cudaStream_t st) {
     StageTimer timer(c, st, 4);
-    CU_TRY(c, launch_pdl(c->pdl != 0, k_blur_commit, dim3((unsigned)(c->sm_count * 32)), dim3(256), 0, st, b, do_commit));   // short latency-bound tasks: one or two per warp
+    CU_TRY(c, launch_pdl((c->pdl & 8) != 0, k_blur_commit, dim3((unsigned)(c->sm_count * 32)), dim3(256), 0, st, b, do_commit));   // short latency-bound tasks: one or two per warp
     CU_TRY(c, cudaGetLastError());
     c->launches++;
     return VRSBS_OK;
@@ -576,7 +578,7 @@ int launch_blur_fixed(vrsbs_ctx *c, const BlurArgs &b, cudaStream_t st) {
     int occ = 0;
     CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, bsmem));
     if (occ < 1) occ = 1;
-    CU_TRY(c, launch_pdl(c->pdl != 0, kern, dim3((unsigned)(c->sm_count * occ)), dim3(warps * 32), bsmem, st, b, wts));
+    CU_TRY(c, launch_pdl((c->pdl & 4) != 0, kern, dim3((unsigned)(c->sm_count * occ)), dim3(warps * 32), bsmem, st, b, wts));
     return VRSBS_OK;
 }
 
@@ -593,7 +595,7 @@ int launch_blur_sep(vrsbs_ctx *c, const BlurArgs &b, cudaStream_t st) {
     int occ = 0;
     CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, bsmem));
     if (occ < 1) occ = 1;
-    CU_TRY(c, launch_pdl(c->pdl != 0, kern, dim3((unsigned)(c->sm_count * occ)), dim3(warps * 32), bsmem, st, b, wts));
+    CU_TRY(c, launch_pdl((c->pdl & 4) != 0, kern, dim3((unsigned)(c->sm_count * occ)), dim3(warps * 32), bsmem, st, b, wts));
     return VRSBS_OK;
 }
 
@@ -601,7 +603,7 @@ int launch_blur(vrsbs_ctx *c, Scratch &s, const uint8_t *frames, int B, int H, i
     if (!s.plane) CU_TRY(c, dmalloc(&s.plane, (size_t)c->max_batch * c->max_h * c->max_w * 3));
     BlurArgs b{};
     b.frames = frames; b.sbs = sbs; b.tabs = s.tabs; b.hole_mask = s.hole_mask; b.hole_list = s.hole_list;
-    b.hole_count = s.hole_count; b.plane = s.plane; b.wq = c->wq; b.weights = c->weights;
+    b.hole_count = s.hole_count; b.ticket = s.hole_count + 1; b.plane = s.plane; b.wq = c->wq; b.weights = c->weights;
     b.B = B; b.H = H; b.W = W; b.Wwords = (W + 31) / 32; b.kx = c->kx; b.ky = c->ky; b.wshift = c->wshift;
     b.magic_h = ((1ull << 40) + (unsigned long long)H - 1) / (unsigned long long)H;
     const int cx = c->kx / 2, cy = c->ky / 2;
@@ -1293,7 +1295,7 @@ int vrsbs_set_option(vrsbs_ctx *c, const char *name, int value) {
     else if (!strcmp(name, "commit_mode")) c->commit_mode = value;
     else if (!strcmp(name, "blur_screen")) c->blur_screen = value ? 1 : 0;
     else if (!strcmp(name, "blur_sep")) c->blur_sep = value;
-    else if (!strcmp(name, "pdl")) c->pdl = value ? 1 : 0;
+    else if (!strcmp(name, "pdl")) c->pdl = value & 15;
     else if (!strcmp(name, "ws_scatter_warps")) c->ws_scatter_warps = value;
     else return fail(c, VRSBS_E_INVALID, "unknown option %s", name);
     return VRSBS_OK;
