@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VRSBS_ABI_VERSION 1
+#define VRSBS_ABI_VERSION 2
 
 enum {
     VRSBS_OK            = 0,
@@ -148,6 +148,26 @@ int  vrsbs_process_host(vrsbs_ctx *ctx, const uint8_t *frames_host, const void *
                         int B, int H, int W, int lowres_h, int lowres_w, float scaler,
                         uint8_t *sbs_host);
 
+/* ---- asynchronous host-buffer entry: decode and encode overlap the kernels -----------------------------------
+ * vrsbs_submit_host enqueues one batch (the copies in, the kernels and the copy out of its chunks, on the library's
+ * three streams) and returns; vrsbs_collect blocks until that batch's SBS frames are complete in sbs_host and reports
+ * its per-frame status like vrsbs_process_host.  Batches run in submission order and share the clip-range state, so
+ * sub-clip k+1 uploads and warps while the caller encodes sub-clip k and decodes sub-clip k+2 - what the serial loop of
+ * nibba_woka (PredictAndGenerate.py:216-250) cannot do.  All host buffers must be page-locked and stay valid until
+ * collected; at most three chunks are in flight, so submit itself blocks while the pipeline is full.
+ * frames_host may be pitched: row y of frame t starts at frames_host + t * frame_pitch + y * frame_row_pitch
+ * (0 = packed).  With VRSBS_HOST_RIGHT_IN_PLACE the caller has decoded its frames straight into the right halves of
+ * sbs_host (frames_host = sbs_host + 3W, frame_row_pitch = 6W, frame_pitch = 6WH): the input then never gets copied
+ * on the host and only the synthesised left halves come back across PCIe.  depth_host as in vrsbs_process_host. */
+#define VRSBS_HOST_RIGHT_IN_PLACE 1u
+int  vrsbs_submit_host(vrsbs_ctx *ctx, const uint8_t *frames_host, size_t frame_row_pitch, size_t frame_pitch,
+                       const void *depth_host, int B, int H, int W, int lowres_h, int lowres_w, float scaler,
+                       uint8_t *sbs_host, unsigned flags, uint64_t *ticket);
+int  vrsbs_collect(vrsbs_ctx *ctx, uint64_t ticket);
+/* Orders the host pipeline's kernels behind everything queued so far on `producer_stream` (a depth producer that left
+ * its output on the device): an event wait on the device, the host is not blocked. */
+int  vrsbs_host_depends_on(vrsbs_ctx *ctx, void *producer_stream);
+
 /* ---- introspection (parity tiers T1..T3, error reporting) ------------------------------------------
  * All of these synchronise `stream` first. */
 int  vrsbs_get_frame_info(vrsbs_ctx *ctx, int B, vrsbs_frame_info *info_host, void *stream);
@@ -176,7 +196,8 @@ int  vrsbs_get_stage_times(vrsbs_ctx *ctx, double ms[VRSBS_NUM_STAGES], uint64_t
  *   2 = k_blur_sep with every value sent to its exact fallback),
  *   "blur_screen" (1 = screening sum before the exact integer blur, 0 = exact sum for every hole),
  *   "commit_mode", "lowres_tiled", "bicubic_contract", "blocks_per_sm", "host_chunk", "copy_threads",
- *   "pageable_direct", "host_right_half", "stage_timing". */
+ *   "pageable_direct", "host_right_half", "host_async" (0 = page-locked callers of vrsbs_process_host use the blocking
+ *   chunk loop instead of submit + collect), "pdl" (bit mask of programmatic-dependent-launch edges), "stage_timing". */
 int  vrsbs_set_option(vrsbs_ctx *ctx, const char *name, int value);
 
 #ifdef __cplusplus

@@ -52,6 +52,8 @@ def _reference_loop(begin, end, video_length, max_count, missing=()):
         if i == min(end, video_length) - 1:
             frame_list.append(raw)
         if len(frame_list) == max_count or i == min(end - 1, video_length - 1):
+            if i == begin:
+                return []              # step_taken == 0: the progress print raises, the handler returns (see shard.flush_ranges)
             out.append((f"{last_i}_{i}.mp4", frame_list))
             last_i, frame_list = i + 1, []
     return out
@@ -72,11 +74,27 @@ class _FakeProcessor:
         assert depths.shape[0] == frames.shape[0]
         return np.concatenate([frames, frames], axis=2)
 
+    # the asynchronous pair the pipelined loop uses: the "warp" happens at collect, like a real in-flight batch
+    def submit_batch(self, frames, depths, out, scaler=1.0):
+        assert depths.shape[0] == frames.shape[0] and out.shape[0] == frames.shape[0]
+        assert frames.base is not None and np.shares_memory(frames, out), "frames must be decoded into the SBS buffer's right half"
+        self.calls.append(len(frames))
+        self.pending = getattr(self, "pending", {})
+        t = len(self.calls)
+        self.pending[t] = (frames, out)
+        return t
 
+    def collect(self, ticket):
+        frames, out = self.pending.pop(ticket)
+        W = frames.shape[2]
+        out[:, :, :W] = frames
+
+
+@pytest.mark.parametrize("pipelined", [True, False])
 @pytest.mark.parametrize("begin,end,length,max_count,missing", [
     (0, 40, 100, 15, ()), (7, 23, 100, 15, (9,)), (0, 1000, 33, 15, ()), (5, 6, 100, 15, ()), (0, 31, 31, 15, ()),
     (0, 16, 100, 15, ()), (10, 41, 100, 5, (10, 40))])
-def test_worker_control_flow_matches_reference(begin, end, length, max_count, missing):
+def test_worker_control_flow_matches_reference(begin, end, length, max_count, missing, pipelined):
     H, W = 2, 3
     def read(i):
         if i in missing:
@@ -87,7 +105,8 @@ def test_worker_control_flow_matches_reference(begin, end, length, max_count, mi
     got = []
     args = argparse.Namespace(Max_Frame_Count=max_count)
     names = worker.sbs_worker(begin, end, read, lambda rgb: np.zeros((len(rgb), H, W), np.float16),
-                              lambda n, sbs: got.append((n, sbs.copy())), args, length, H, W, processor=_FakeProcessor())
+                              lambda n, sbs: got.append((n, sbs.copy())), args, length, H, W, processor=_FakeProcessor(),
+                              pipelined=pipelined)
     want = _reference_loop(begin, end, length, max_count, missing)
     assert names == [n for n, _ in want]
     for (n, sbs), (wn, idx) in zip(got, want):

@@ -9,18 +9,20 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvrsbs.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # every symbol include/vrsbs.h declares (tests check that the library exports exactly these)
 SYMBOLS = [
     "vrsbs_abi_version", "vrsbs_create", "vrsbs_destroy", "vrsbs_last_error", "vrsbs_reset",
     "vrsbs_get_range_state", "vrsbs_set_range_state", "vrsbs_set_blur_weights",
     "vrsbs_depth_from_lowres", "vrsbs_depth_from_full", "vrsbs_build_tables", "vrsbs_warp_batch",
-    "vrsbs_process_batch", "vrsbs_process_host", "vrsbs_get_frame_info", "vrsbs_get_tables",
+    "vrsbs_process_batch", "vrsbs_process_host", "vrsbs_submit_host", "vrsbs_collect", "vrsbs_host_depends_on",
+    "vrsbs_get_frame_info", "vrsbs_get_tables",
     "vrsbs_get_hole_mask", "vrsbs_get_stage_times", "vrsbs_launch_count", "vrsbs_set_option",
 ]
 
 FRAME_NAN, FRAME_OVERFLOW, FRAME_GENERIC = 1, 2, 4
+HOST_RIGHT_IN_PLACE = 1
 
 
 class VrsbsError(RuntimeError):
@@ -71,6 +73,10 @@ def load():
     lib.vrsbs_warp_batch.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp]
     lib.vrsbs_process_batch.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp, vp]
     lib.vrsbs_process_host.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, cf, vp]
+    lib.vrsbs_submit_host.argtypes = [vp, vp, ctypes.c_size_t, ctypes.c_size_t, vp, ci, ci, ci, ci, ci, cf, vp, ctypes.c_uint,
+                                      ctypes.POINTER(ctypes.c_uint64)]
+    lib.vrsbs_collect.argtypes = [vp, ctypes.c_uint64]
+    lib.vrsbs_host_depends_on.argtypes = [vp, vp]
     lib.vrsbs_get_frame_info.argtypes = [vp, ci, ctypes.POINTER(FrameInfo), vp]
     lib.vrsbs_get_tables.argtypes = [vp, ci, ci, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int32),
                                      ctypes.POINTER(ctypes.c_uint16), ctypes.POINTER(ctypes.c_uint16), vp]
@@ -161,6 +167,19 @@ class Context:
 
     def process_host(self, frames_ptr, depth_ptr, B, H, W, lh, lw, scaler, sbs_ptr):
         self.check(self.lib.vrsbs_process_host(self.handle, frames_ptr, depth_ptr, B, H, W, lh, lw, scaler, sbs_ptr))
+
+    def submit_host(self, frames_ptr, row_pitch, frame_pitch, depth_ptr, B, H, W, lh, lw, scaler, sbs_ptr, flags=0):
+        """Asynchronous vrsbs_process_host: returns a ticket for collect()."""
+        t = ctypes.c_uint64()
+        self.check(self.lib.vrsbs_submit_host(self.handle, frames_ptr, row_pitch, frame_pitch, depth_ptr, B, H, W, lh, lw,
+                                              scaler, sbs_ptr, flags, ctypes.byref(t)))
+        return int(t.value)
+
+    def collect(self, ticket):
+        self.check(self.lib.vrsbs_collect(self.handle, ticket))
+
+    def host_depends_on(self, stream):
+        self.check(self.lib.vrsbs_host_depends_on(self.handle, stream))
 
     # --- introspection -------------------------------------------------------------------------
     def frame_info(self, B, stream=0):

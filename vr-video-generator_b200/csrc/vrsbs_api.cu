@@ -43,6 +43,7 @@ struct Scratch {                 // per-batch device scratch; one per pipeline s
     uint8_t *blobs = nullptr;        // [B][kBlobMax] fast-path tables
     uint8_t *plane = nullptr;        // [B,H,W,3] blurred hole values (allocated on first blur)
     bool holes_dirty = false;        // a warp kernel has appended to hole_list since hole_count was last cleared
+    int cap_batch = 0;               // frames this scratch set was allocated for
 };
 
 constexpr int kEntCapMax = 255, kLutCapMax = 8192;
@@ -204,6 +205,16 @@ struct vrsbs_ctx {
     int pageable_direct = 0;             // option: 1 = hand pageable host pointers to cudaMemcpyAsync instead of staging them
     int host_right_half = 1;             // option: 1 = the right half of the SBS frame (= the caller's input) is copied on the host
     CopyPool *pool = nullptr;            // created on first use by vrsbs_process_host
+    int host_async = 1;                  // option: page-locked callers of vrsbs_process_host go through submit + collect
+    int skip_right = 0;                  // set around the host pipeline's warp launches: the right half stays on the host
+    // asynchronous host pipeline (vrsbs_submit_host / vrsbs_collect)
+    struct Inflight { uint64_t ticket; int rc; int chunks; char err[256]; };
+    std::vector<Inflight> inflight;      // submitted, not yet collected
+    uint64_t next_ticket = 1;
+    uint64_t slot_ticket[kSlots] = {0, 0, 0};   // 0 = slot free
+    int slot_n[kSlots] = {0, 0, 0}, slot_first[kSlots] = {0, 0, 0};
+    long long chunk_seq = 0;             // chunks enqueued so far: slot = chunk_seq % kSlots
+    cudaEvent_t dep_event = nullptr;     // vrsbs_host_depends_on
     // options / accounting
     int scatter_mode = 2;
     int bicubic_contract = 1;
@@ -254,8 +265,9 @@ void free_scratch(Scratch &s) {
     s = Scratch{};
 }
 
-int alloc_scratch(vrsbs_ctx *c, Scratch &s) {
-    const size_t B = c->max_batch, L = c->max_layers;
+int alloc_scratch(vrsbs_ctx *c, Scratch &s, int cap_batch) {
+    const size_t B = cap_batch, L = c->max_layers;
+    s.cap_batch = cap_batch;
     const size_t mask_words = B * c->max_h * ((c->max_w + 31) / 32);
     CU_TRY(c, dmalloc(&s.frame_max, 2 * B + 2));
     s.frame_nan = s.frame_max + B;
@@ -320,7 +332,7 @@ cudaError_t launch_pdl(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, 
 // ---- stage launchers (stream-ordered, no host sync) ---------------------------------------------------
 int clear_counters(vrsbs_ctx *c, Scratch &s, int B, cudaStream_t st) {
     (void)B;
-    CU_TRY(c, cudaMemsetAsync(s.frame_max, 0, sizeof(uint32_t) * (2 * c->max_batch + 2), st));
+    CU_TRY(c, cudaMemsetAsync(s.frame_max, 0, sizeof(uint32_t) * (2 * s.cap_batch + 2), st));
     s.holes_dirty = false;
     return VRSBS_OK;
 }
@@ -600,7 +612,7 @@ int launch_blur_sep(vrsbs_ctx *c, const BlurArgs &b, cudaStream_t st) {
 }
 
 int launch_blur(vrsbs_ctx *c, Scratch &s, const uint8_t *frames, int B, int H, int W, uint8_t *sbs, cudaStream_t st) {
-    if (!s.plane) CU_TRY(c, dmalloc(&s.plane, (size_t)c->max_batch * c->max_h * c->max_w * 3));
+    if (!s.plane) CU_TRY(c, dmalloc(&s.plane, (size_t)s.cap_batch * c->max_h * c->max_w * 3));
     BlurArgs b{};
     b.frames = frames; b.sbs = sbs; b.tabs = s.tabs; b.hole_mask = s.hole_mask; b.hole_list = s.hole_list;
     b.hole_count = s.hole_count; b.ticket = s.hole_count + 1; b.plane = s.plane; b.wq = c->wq; b.weights = c->weights;
@@ -676,6 +688,7 @@ FusedArgs make_fused_args(vrsbs_ctx *c, Scratch &s, const uint8_t *frames, const
     a.hole_mask = s.hole_mask; a.hole_list = s.hole_list; a.hole_count = s.hole_count;
     a.B = B; a.H = H; a.W = W; a.Lcap = c->max_layers; a.Wwords = (W + 31) / 32;
     a.first = 0;
+    a.skip_right = c->skip_right;
     a.blob_bytes = blob_bytes(c->ent_cap, c->lut_cap); a.ent_bytes = blob_ent_bytes(c->ent_cap); a.key_pad = c->key_pad;
     a.w0 = c->sw.w_now; a.w1 = c->sw.w_prev1; a.w2 = c->sw.w_prev2;
     const FusedSmem L = fused_smem_layout(W, a.blob_bytes);
@@ -851,7 +864,7 @@ int vrsbs_create(vrsbs_ctx **out, int device, int max_h, int max_w, int max_batc
         for (int i = 0; i < 2; ++i)
             for (int j = 0; j < 2; ++j) CU_TRY(c, dmalloc(&c->hist[i][j], n));
         CU_TRY(c, dmalloc(&c->state, 2));
-        int rc = alloc_scratch(c, c->scratch[0]);
+        int rc = alloc_scratch(c, c->scratch[0], c->max_batch);
         if (rc) return rc;
         vrsbs_params p = c->params;
         return vrsbs_reset(c, &p);
@@ -875,6 +888,7 @@ int vrsbs_destroy(vrsbs_ctx *c) {
     cudaFree(c->state); cudaFree(c->weights); cudaFree(c->wq);
     for (int i = 0; i < kSlots; ++i) { free_scratch(c->scratch[i]); free_slot(c->slot[i]); }
     if (c->st_in) { cudaStreamDestroy(c->st_in); cudaStreamDestroy(c->st_k); cudaStreamDestroy(c->st_out); }
+    if (c->dep_event) cudaEventDestroy(c->dep_event);
     delete c->pool;
     for (auto &s : c->stamps) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (auto e : c->event_pool) cudaEventDestroy(e);
@@ -1103,8 +1117,17 @@ int vrsbs_process_host(vrsbs_ctx *c, const uint8_t *frames, const void *depth, i
     int rc = check_dims(c, 1, H, W);
     if (rc) return rc;
     if (!frames || !depth || !sbs) return fail(c, VRSBS_E_INVALID, "NULL buffer");
+    if (!c->inflight.empty()) return fail(c, VRSBS_E_STATE, "vrsbs_process_host with %zu submitted batches not yet collected", c->inflight.size());
     const bool lowres = lh > 0 && lw > 0;
     DeviceGuard g(c->device);
+    if (c->host_async && !c->pageable_direct && c->host_right_half != 2 && !(c->fused && c->smooth_in_warp) && is_pinned(frames) && is_pinned(sbs) &&
+        (is_device(depth) || is_pinned(depth))) {
+        // page-locked buffers: the asynchronous pipeline, collected right away (same result, one code path to maintain)
+        uint64_t t = 0;
+        rc = vrsbs_submit_host(c, frames, 0, 0, depth, B, H, W, lh, lw, scaler, sbs, 0u, &t);
+        if (rc) return rc;
+        return vrsbs_collect(c, t);
+    }
     int chunk = c->host_chunk < c->max_batch ? c->host_chunk : c->max_batch;
     if (chunk < 1) chunk = 1;
     const size_t fb = (size_t)H * W * 3, sb = fb * 2, db = (size_t)H * W * 2;
@@ -1119,7 +1142,14 @@ int vrsbs_process_host(vrsbs_ctx *c, const uint8_t *frames, const void *depth, i
     // synthesised half across PCIe (halves the D2H traffic, which is the longer leg)
     const bool host_right = c->host_right_half != 0;
     for (int i = 0; i < kSlots; ++i) {
-        if (!c->scratch[i].tabs && (rc = alloc_scratch(c, c->scratch[i]))) return rc;
+        if (!c->scratch[i].tabs && (rc = alloc_scratch(c, c->scratch[i], chunk))) return rc;
+        if (c->scratch[i].cap_batch < chunk) {            // host_chunk was raised after the first call
+            CU_TRY(c, cudaDeviceSynchronize());
+            free_scratch(c->scratch[i]);
+            if ((rc = alloc_scratch(c, c->scratch[i], chunk))) return rc;
+        }
+        if (c->params.blur && !c->scratch[i].plane)       // not inside the pipeline: cudaMalloc synchronises the device
+            CU_TRY(c, dmalloc(&c->scratch[i].plane, (size_t)c->scratch[i].cap_batch * c->max_h * c->max_w * 3));
         if ((rc = ensure_slot(c, c->slot[i], fb * chunk, dib * chunk, db * chunk, sb * chunk, !pin_f || !pin_d, !pin_s))) return rc;
     }
     const bool need_pool = !pin_f || !pin_d || !pin_s || host_right;
@@ -1150,7 +1180,8 @@ int vrsbs_process_host(vrsbs_ctx *c, const uint8_t *frames, const void *depth, i
     auto drain = [&](int si) -> int {     // wait for slot si's chunk, deliver its output, check its status
         HostSlot &s = c->slot[si];
         if (!pending_n[si]) return VRSBS_OK;
-        CU_TRY(c, cudaEventSynchronize(s.out_done));
+        const cudaError_t ee = cudaEventSynchronize(s.out_done);
+        if (ee != cudaSuccess) { pending_n[si] = 0; return fail(c, VRSBS_E_CUDA, "cudaEventSynchronize failed: %s", cudaGetErrorString(ee)); }
         const int n = pending_n[si], first = pending_first[si];
         if (!pin_s) {
             uint8_t *dst = sbs + (size_t)first * sb;
@@ -1161,10 +1192,18 @@ int vrsbs_process_host(vrsbs_ctx *c, const uint8_t *frames, const void *depth, i
         return frame_status_error(c, s.pin_tabs, n, first);
     };
     auto drain_all = [&](int rc_in) -> int {          // never leave work in flight behind an error return
+        if (rc_in) { cudaStreamSynchronize(c->st_in); cudaStreamSynchronize(c->st_k); cudaStreamSynchronize(c->st_out); }
+        c->skip_right = 0;
         for (int i = 0; i < kSlots; ++i) { int r = drain(i); if (!rc_in) rc_in = r; }
         if (pool) for (int i = 0; i < kSlots; ++i) { pool->wait(tk_in[i]); pool->wait(tk_in2[i]); pool->wait(tk_out[i]); pool->wait(tk_right[i]); }
         return rc_in;
     };
+#define CU_TRY_DRAIN(call)                                                                             \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return drain_all(fail(c, VRSBS_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__)); \
+    } while (0)
     stage_in(0);
     for (int ci = 0; ci < nchunks; ++ci) {
         const int si = ci % kSlots, first = ci * chunk, n = count_of(ci);
@@ -1180,14 +1219,15 @@ int vrsbs_process_host(vrsbs_ctx *c, const uint8_t *frames, const void *depth, i
         if (pool) { pool->wait(tk_in[si]); pool->wait(tk_in2[si]); }
         if (!pin_f) hf = s.pin_frames;
         if (!pin_d) hd = s.pin_depth;
-        CU_TRY(c, cudaMemcpyAsync(s.dev_frames, hf, fb * n, cudaMemcpyHostToDevice, c->st_in));
-        if (!dev_d) CU_TRY(c, cudaMemcpyAsync(s.dev_depth_in, hd, dib * n, cudaMemcpyHostToDevice, c->st_in));
+        CU_TRY_DRAIN(cudaMemcpyAsync(s.dev_frames, hf, fb * n, cudaMemcpyHostToDevice, c->st_in));
+        if (!dev_d) CU_TRY_DRAIN(cudaMemcpyAsync(s.dev_depth_in, hd, dib * n, cudaMemcpyHostToDevice, c->st_in));
         const __half *din = dev_d ? (const __half *)hd : (const __half *)s.dev_depth_in;
-        CU_TRY(c, cudaEventRecord(s.in_done, c->st_in));
+        CU_TRY_DRAIN(cudaEventRecord(s.in_done, c->st_in));
         if (host_right && c->host_right_half != 2)               // right halves: caller's frames -> caller's output, on the pool
             { pool->wait(tk_right[si]); tk_right[si] = pool->submit(sbs + (size_t)first * sb + row3, 2 * row3, frames + (size_t)first * fb, row3, row3, (size_t)n * H); }
-        CU_TRY(c, cudaStreamWaitEvent(c->st_k, s.in_done, 0));
+        CU_TRY_DRAIN(cudaStreamWaitEvent(c->st_k, s.in_done, 0));
         Scratch &sc = c->scratch[si];
+        c->skip_right = host_right ? 1 : 0;                      // nobody reads the right half of dev_sbs then
         if (use_fused) {
             rc = launch_process_fused(c, sc, s.dev_frames, din, n, H, W, s.dev_sbs, c->st_k);
         } else {
@@ -1196,23 +1236,196 @@ int vrsbs_process_host(vrsbs_ctx *c, const uint8_t *frames, const void *depth, i
             if (!rc) rc = launch_tables(c, sc, n, H, W, c->st_k);
             if (!rc) rc = launch_warp(c, sc, s.dev_frames, (const __half *)s.dev_depth, n, H, W, s.dev_sbs, c->st_k);
         }
+        c->skip_right = 0;
         if (rc) return drain_all(rc);
-        CU_TRY(c, cudaMemcpyAsync(s.pin_tabs, sc.tabs, sizeof(FrameTab) * n, cudaMemcpyDeviceToHost, c->st_k));
-        CU_TRY(c, cudaEventRecord(s.k_done, c->st_k));
-        CU_TRY(c, cudaStreamWaitEvent(c->st_out, s.k_done, 0));
+        CU_TRY_DRAIN(cudaMemcpyAsync(s.pin_tabs, sc.tabs, sizeof(FrameTab) * n, cudaMemcpyDeviceToHost, c->st_k));
+        CU_TRY_DRAIN(cudaEventRecord(s.k_done, c->st_k));
+        CU_TRY_DRAIN(cudaStreamWaitEvent(c->st_out, s.k_done, 0));
         if (pool) pool->wait(tk_out[si]);                        // the slot's pinned output has been delivered
         if (host_right) {
             // left halves only: [n*H rows] x W*3 bytes out of rows of 2*W*3
-            if (pin_s) CU_TRY(c, cudaMemcpy2DAsync(sbs + (size_t)first * sb, 2 * row3, s.dev_sbs, 2 * row3, row3, (size_t)n * H, cudaMemcpyDeviceToHost, c->st_out));
-            else CU_TRY(c, cudaMemcpy2DAsync(s.pin_sbs, row3, s.dev_sbs, 2 * row3, row3, (size_t)n * H, cudaMemcpyDeviceToHost, c->st_out));
+            if (pin_s) CU_TRY_DRAIN(cudaMemcpy2DAsync(sbs + (size_t)first * sb, 2 * row3, s.dev_sbs, 2 * row3, row3, (size_t)n * H, cudaMemcpyDeviceToHost, c->st_out));
+            else CU_TRY_DRAIN(cudaMemcpy2DAsync(s.pin_sbs, row3, s.dev_sbs, 2 * row3, row3, (size_t)n * H, cudaMemcpyDeviceToHost, c->st_out));
         } else {
             uint8_t *ho = pin_s ? sbs + (size_t)first * sb : s.pin_sbs;
-            CU_TRY(c, cudaMemcpyAsync(ho, s.dev_sbs, sb * n, cudaMemcpyDeviceToHost, c->st_out));
+            CU_TRY_DRAIN(cudaMemcpyAsync(ho, s.dev_sbs, sb * n, cudaMemcpyDeviceToHost, c->st_out));
         }
-        CU_TRY(c, cudaEventRecord(s.out_done, c->st_out));
+        CU_TRY_DRAIN(cudaEventRecord(s.out_done, c->st_out));
         pending_n[si] = n; pending_first[si] = first;
     }
     return drain_all(VRSBS_OK);
+#undef CU_TRY_DRAIN
+}
+
+// ---- asynchronous host pipeline ----------------------------------------------------------------------------------
+namespace {
+
+vrsbs_ctx::Inflight *find_inflight(vrsbs_ctx *c, uint64_t ticket) {
+    for (auto &f : c->inflight) if (f.ticket == ticket) return &f;
+    return nullptr;
+}
+
+// Waits for the chunk that occupies slot si, records its per-frame status on the batch it belongs to, frees the slot.
+void retire_slot(vrsbs_ctx *c, int si) {
+    if (!c->slot_ticket[si]) return;
+    HostSlot &s = c->slot[si];
+    vrsbs_ctx::Inflight *f = find_inflight(c, c->slot_ticket[si]);
+    const cudaError_t e = cudaEventSynchronize(s.out_done);
+    if (f) {
+        if (e != cudaSuccess && !f->rc) {
+            f->rc = VRSBS_E_CUDA;
+            snprintf(f->err, sizeof f->err, "cudaEventSynchronize failed: %s", cudaGetErrorString(e));
+        } else if (!f->rc) {
+            char keep[256];
+            memcpy(keep, c->err, sizeof keep);
+            const int rc = frame_status_error(c, s.pin_tabs, c->slot_n[si], c->slot_first[si]);
+            if (rc) { f->rc = rc; memcpy(f->err, c->err, sizeof f->err); }
+            memcpy(c->err, keep, sizeof keep);
+        }
+        f->chunks--;
+    }
+    c->slot_ticket[si] = 0;
+}
+
+// An enqueue failed half way: let everything already queued finish, then fail every batch in flight.
+int abort_inflight(vrsbs_ctx *c, int rc) {
+    if (c->st_in) { cudaStreamSynchronize(c->st_in); cudaStreamSynchronize(c->st_k); cudaStreamSynchronize(c->st_out); }
+    c->skip_right = 0;
+    for (int i = 0; i < kSlots; ++i) c->slot_ticket[i] = 0;
+    for (auto &f : c->inflight) if (!f.rc) { f.rc = rc; memcpy(f.err, c->err, sizeof f.err); f.chunks = 0; }
+    return rc;
+}
+
+}  // namespace
+
+int vrsbs_host_depends_on(vrsbs_ctx *c, void *producer_stream) {
+    if (!c) return VRSBS_E_INVALID;
+    DeviceGuard g(c->device);
+    if (!c->st_in) {
+        CU_TRY(c, cudaStreamCreateWithFlags(&c->st_in, cudaStreamNonBlocking));
+        CU_TRY(c, cudaStreamCreateWithFlags(&c->st_k, cudaStreamNonBlocking));
+        CU_TRY(c, cudaStreamCreateWithFlags(&c->st_out, cudaStreamNonBlocking));
+    }
+    if (!c->dep_event) CU_TRY(c, cudaEventCreateWithFlags(&c->dep_event, cudaEventDisableTiming));
+    CU_TRY(c, cudaEventRecord(c->dep_event, (cudaStream_t)producer_stream));
+    CU_TRY(c, cudaStreamWaitEvent(c->st_k, c->dep_event, 0));      // every kernel of the host pipeline runs on st_k, in order
+    return VRSBS_OK;
+}
+
+int vrsbs_submit_host(vrsbs_ctx *c, const uint8_t *frames, size_t frame_row_pitch, size_t frame_pitch, const void *depth,
+                      int B, int H, int W, int lh, int lw, float scaler, uint8_t *sbs, unsigned flags, uint64_t *ticket) {
+    if (!c) return VRSBS_E_INVALID;
+    if (!ticket) return fail(c, VRSBS_E_INVALID, "ticket is NULL");
+    *ticket = 0;
+    if (B < 1) return fail(c, VRSBS_E_INVALID, "batch %d", B);
+    int rc = check_dims(c, 1, H, W);
+    if (rc) return rc;
+    if (!frames || !depth || !sbs) return fail(c, VRSBS_E_INVALID, "NULL buffer");
+    const size_t row3 = (size_t)W * 3, fb = (size_t)H * row3, sb = fb * 2, db = (size_t)H * W * 2;
+    if (!frame_row_pitch) frame_row_pitch = row3;
+    if (!frame_pitch) frame_pitch = frame_row_pitch * H;
+    if (frame_row_pitch < row3 || frame_pitch < frame_row_pitch * (size_t)(H - 1) + row3)
+        return fail(c, VRSBS_E_INVALID, "frame pitches %zu / %zu too small for %dx%d", frame_row_pitch, frame_pitch, W, H);
+    const bool in_place = (flags & VRSBS_HOST_RIGHT_IN_PLACE) != 0;
+    if (in_place && (frames != sbs + row3 || frame_row_pitch != 2 * row3 || frame_pitch != sb))
+        return fail(c, VRSBS_E_INVALID, "VRSBS_HOST_RIGHT_IN_PLACE: frames must be the right halves of sbs_host (frames = sbs + 3W, row pitch 6W)");
+    const bool lowres = lh > 0 && lw > 0;
+    const size_t dib = lowres ? (size_t)lh * lw * 2 : db;
+    DeviceGuard g(c->device);
+    const bool dev_d = is_device(depth);
+    if (!is_pinned(frames) || !is_pinned(sbs) || !(dev_d || is_pinned(depth)))
+        return fail(c, VRSBS_E_INVALID, "vrsbs_submit_host needs page-locked host buffers (cudaHostAlloc / cudaHostRegister); "
+                                          "vrsbs_process_host stages pageable ones");
+    int chunk = c->host_chunk < c->max_batch ? c->host_chunk : c->max_batch;
+    if (chunk < 1) chunk = 1;
+    bool grow = false;
+    for (int i = 0; i < kSlots; ++i)
+        grow = grow || c->slot[i].cap_frames < fb * chunk || c->slot[i].cap_depth_in < dib * chunk || c->slot[i].cap_depth < db * chunk ||
+               c->slot[i].cap_sbs < sb * chunk || !c->scratch[i].tabs || c->scratch[i].cap_batch < chunk ||
+               (c->params.blur && !c->scratch[i].plane);
+    if (grow) {                                           // (re)allocation: nothing may be in flight on the old buffers
+        for (int i = 0; i < kSlots; ++i) retire_slot(c, i);
+        if (c->st_in) CU_TRY(c, cudaDeviceSynchronize());
+        for (int i = 0; i < kSlots; ++i) {
+            if (c->scratch[i].tabs && c->scratch[i].cap_batch < chunk) free_scratch(c->scratch[i]);
+            if (!c->scratch[i].tabs && (rc = alloc_scratch(c, c->scratch[i], i == 0 ? c->max_batch : chunk))) return rc;
+            if (c->params.blur && !c->scratch[i].plane)
+                CU_TRY(c, dmalloc(&c->scratch[i].plane, (size_t)c->scratch[i].cap_batch * c->max_h * c->max_w * 3));
+            if ((rc = ensure_slot(c, c->slot[i], fb * chunk, dib * chunk, db * chunk, sb * chunk, false, false))) return rc;
+        }
+    }
+    fast_caps(c, H, W, &c->ent_cap, &c->lut_cap);
+    if ((rc = check_blur_ready(c, H, W))) return rc;
+    const bool plain = frame_row_pitch == row3 && frame_pitch == fb;
+    // without the in-place layout the right halves are the caller's own frames: copied host to host by the pool
+    const bool host_right = !in_place && c->host_right_half != 0;
+    if (host_right && !c->pool) {
+        c->pool = new (std::nothrow) CopyPool(c->copy_threads);
+        if (!c->pool) return fail(c, VRSBS_E_NOMEM, "cannot start the host copy threads");
+    }
+    vrsbs_ctx::Inflight job{};
+    job.ticket = c->next_ticket++;
+    const int nchunks = (B + chunk - 1) / chunk;
+    job.chunks = nchunks;
+    c->inflight.push_back(job);
+#define CU_TRY_ABORT(call)                                                                             \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return abort_inflight(c, fail(c, VRSBS_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__)); \
+    } while (0)
+    std::vector<int> right_tickets;
+    for (int ci = 0; ci < nchunks; ++ci) {
+        const int si = (int)(c->chunk_seq++ % kSlots), first = ci * chunk, n = (B - first < chunk) ? B - first : chunk;
+        HostSlot &s = c->slot[si];
+        retire_slot(c, si);                                // blocks while the pipeline is full (three chunks in flight)
+        const uint8_t *hf = frames + (size_t)first * frame_pitch;
+        const uint8_t *hd = (const uint8_t *)depth + (size_t)first * dib;
+        if (plain) CU_TRY_ABORT(cudaMemcpyAsync(s.dev_frames, hf, fb * n, cudaMemcpyHostToDevice, c->st_in));
+        else if (frame_pitch == frame_row_pitch * (size_t)H)   // one pitched copy for the whole chunk
+            CU_TRY_ABORT(cudaMemcpy2DAsync(s.dev_frames, row3, hf, frame_row_pitch, row3, (size_t)n * H, cudaMemcpyHostToDevice, c->st_in));
+        else
+            for (int t = 0; t < n; ++t)
+                CU_TRY_ABORT(cudaMemcpy2DAsync(s.dev_frames + (size_t)t * fb, row3, hf + (size_t)t * frame_pitch, frame_row_pitch, row3, H, cudaMemcpyHostToDevice, c->st_in));
+        if (!dev_d) CU_TRY_ABORT(cudaMemcpyAsync(s.dev_depth_in, hd, dib * n, cudaMemcpyHostToDevice, c->st_in));
+        const __half *din = dev_d ? (const __half *)hd : (const __half *)s.dev_depth_in;
+        CU_TRY_ABORT(cudaEventRecord(s.in_done, c->st_in));
+        if (host_right)
+            right_tickets.push_back(c->pool->submit(sbs + (size_t)first * sb + row3, 2 * row3, hf, frame_row_pitch, row3, (size_t)n * H));
+        CU_TRY_ABORT(cudaStreamWaitEvent(c->st_k, s.in_done, 0));
+        Scratch &sc = c->scratch[si];
+        c->skip_right = 1;                                 // the right half never leaves the host
+        if (lowres) rc = launch_depth(c, sc, nullptr, din, n, H, W, lh, lw, scaler, (__half *)s.dev_depth, c->st_k);
+        else rc = launch_depth(c, sc, din, nullptr, n, H, W, 0, 0, 1.f, (__half *)s.dev_depth, c->st_k);
+        if (!rc) rc = launch_tables(c, sc, n, H, W, c->st_k);
+        if (!rc) rc = launch_warp(c, sc, s.dev_frames, (const __half *)s.dev_depth, n, H, W, s.dev_sbs, c->st_k);
+        c->skip_right = 0;
+        if (rc) return abort_inflight(c, rc);
+        CU_TRY_ABORT(cudaMemcpyAsync(s.pin_tabs, sc.tabs, sizeof(FrameTab) * n, cudaMemcpyDeviceToHost, c->st_k));
+        CU_TRY_ABORT(cudaEventRecord(s.k_done, c->st_k));
+        CU_TRY_ABORT(cudaStreamWaitEvent(c->st_out, s.k_done, 0));
+        CU_TRY_ABORT(cudaMemcpy2DAsync(sbs + (size_t)first * sb, 2 * row3, s.dev_sbs, 2 * row3, row3, (size_t)n * H, cudaMemcpyDeviceToHost, c->st_out));
+        CU_TRY_ABORT(cudaEventRecord(s.out_done, c->st_out));
+        c->slot_ticket[si] = job.ticket; c->slot_n[si] = n; c->slot_first[si] = first;
+    }
+#undef CU_TRY_ABORT
+    for (int t : right_tickets) c->pool->wait(t);          // host-to-host right halves (only without the in-place layout)
+    *ticket = job.ticket;
+    return VRSBS_OK;
+}
+
+int vrsbs_collect(vrsbs_ctx *c, uint64_t ticket) {
+    if (!c) return VRSBS_E_INVALID;
+    DeviceGuard g(c->device);
+    vrsbs_ctx::Inflight *f = find_inflight(c, ticket);
+    if (!f) return fail(c, VRSBS_E_INVALID, "unknown or already collected ticket %llu", (unsigned long long)ticket);
+    for (int i = 0; i < kSlots; ++i)
+        if (c->slot_ticket[i] == ticket) retire_slot(c, i);
+    f = find_inflight(c, ticket);
+    const int rc = f->rc;
+    if (rc) memcpy(c->err, f->err, sizeof c->err);
+    c->inflight.erase(c->inflight.begin() + (f - c->inflight.data()));
+    return rc;
 }
 
 int vrsbs_get_frame_info(vrsbs_ctx *c, int B, vrsbs_frame_info *info, void *stream) {
@@ -1296,6 +1509,7 @@ int vrsbs_set_option(vrsbs_ctx *c, const char *name, int value) {
     else if (!strcmp(name, "blur_screen")) c->blur_screen = value ? 1 : 0;
     else if (!strcmp(name, "blur_sep")) c->blur_sep = value;
     else if (!strcmp(name, "pdl")) c->pdl = value & 15;
+    else if (!strcmp(name, "host_async")) c->host_async = value ? 1 : 0;
     else if (!strcmp(name, "ws_scatter_warps")) c->ws_scatter_warps = value;
     else return fail(c, VRSBS_E_INVALID, "unknown option %s", name);
     return VRSBS_OK;

@@ -49,6 +49,7 @@ struct FusedArgs {
     uint32_t *hole_count;      // pre-zeroed
     int B, H, W, Lcap, Wwords;
     int first;                 // frame 0 of the batch is the first frame of the clip range
+    int skip_right;            // 1: do not store the right half of the SBS row (the host pipeline's caller already holds it)
     uint32_t blob_bytes, ent_bytes;
     int key_pad;               // fast path: |signed offset| <= key_pad pixels (multiple of 32); only segments closer than
                                // that to a row end can wrap
@@ -382,7 +383,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_fused(FusedArgs a) {
         if (tid == 0) {
             uint8_t *go = a.sbs + (size_t)row * img_bytes * 2;
             bulk_s2g_a(go, sa_out, img_bytes);
-            bulk_s2g_a(go + img_bytes, sa_imgrow, img_bytes);
+            if (!a.skip_right) bulk_s2g_a(go + img_bytes, sa_imgrow, img_bytes);
             bulk_commit();
             if (n + 2 < N) issue_main(n + 2, y2, t2, c2, t2 == 0);
             if (SMOOTH && bnd1 && n + 1 < N) issue_hist(n + 1, y1, t1, h1_1, h2_1);

@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_ws(WsArgs wa) {
             if (elect) {
                 uint8_t *go = a.sbs + (size_t)row * img_bytes * 2;
                 bulk_s2g_a(go, sa_out, img_bytes);
-                bulk_s2g_a(go + img_bytes, sa_imgrow, img_bytes);
+                if (!a.skip_right) bulk_s2g_a(go + img_bytes, sa_imgrow, img_bytes);
                 bulk_commit();
             }
             __syncwarp();

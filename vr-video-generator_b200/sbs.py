@@ -40,6 +40,8 @@ class SbsProcessor:
         self._ctx = None
         self._shape = None          # (H, W) the context was created for
         self._blur = True
+        self._inflight = {}         # ticket -> arrays of a submitted batch (kept alive until collected)
+        self._depth_pool = []       # recycled page-locked staging buffers for host depth given to submit_batch
 
     # ------------------------------------------------------------------------------------------
     def _context(self, H, W):
@@ -134,25 +136,76 @@ class SbsProcessor:
         the device).  Returns numpy [B,H,2W,3].  Pipelined (pinned double buffering)."""
         f = _as_numpy(frames)
         B, H, W, _ = f.shape
-        if isinstance(depths, torch.Tensor) and depths.is_cuda:
-            # the depth producer's output is still on the device (same process): used where it is, no H2D of depth
-            _check_cuda(depths, torch.float16)
-            torch.cuda.current_stream(depths.device).synchronize()
-            dshape, dptr = tuple(depths.shape), depths.data_ptr()
-        else:
-            d = _as_numpy(depths)
-            if d.dtype != np.float16:
-                raise TypeError(f"depth must be float16 (the producer's autocast dtype), got {d.dtype}")
-            dshape, dptr = d.shape, d.ctypes.data
-        if len(dshape) != 3 or dshape[0] != B:
-            raise ValueError(f"depth {dshape} does not match {B} frames")
-        lowres = tuple(dshape[1:]) != (H, W)
         ctx = self._context(H, W)
+        dshape, dptr, _keep = self._depth_arg(ctx, depths, B)
+        lowres = tuple(dshape[1:]) != (H, W)
         if out is None:
             out = np.empty((B, H, 2 * W, 3), dtype=np.uint8)
         ctx.process_host(f.ctypes.data, dptr, B, H, W, dshape[1] if lowres else 0,
                          dshape[2] if lowres else 0, float(scaler), out.ctypes.data)
         return out
+
+    def submit_batch(self, frames, depths, out, scaler=1.0):
+        """Asynchronous `left_side_sbs_batch` for PAGE-LOCKED buffers (see `pinned_sbs_buffer`): enqueues the copies and
+        kernels of this batch and returns a ticket; `collect(ticket)` blocks until `out` holds the SBS frames.  Batches
+        run in submission order and share the clip-range state, so the caller can decode the next sub-clip and encode the
+        previous one while this one is on the GPU (vrsbs_submit_host).  `frames` may be `out[:, :, W:, :]` - the caller
+        decoded straight into the right halves of the SBS buffer: nothing is copied on the host then, and only the
+        synthesised left halves cross PCIe on the way back.  The arrays must stay alive and untouched until collected."""
+        B, H, W, _ = frames.shape
+        if out.shape != (B, H, 2 * W, 3) or out.dtype != np.uint8 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous uint8 [B,H,2W,3] array")
+        if frames.dtype != np.uint8 or frames.strides[2:] != (3, 1):
+            raise ValueError("frames must be uint8 with packed pixels and rows")
+        ctx = self._context(H, W)
+        dshape, dptr, keep = self._depth_arg(ctx, depths, B)
+        staged = None
+        if not (isinstance(depths, torch.Tensor) and (depths.is_cuda or depths.is_pinned())):
+            # pageable host depth (what a result queue delivers): one copy into a recycled page-locked buffer
+            staged = self._pinned_depth(keep.nbytes)
+            view = staged.numpy()[:keep.nbytes].view(np.float16).reshape(keep.shape)
+            np.copyto(view, keep)
+            dptr, keep = view.ctypes.data, (staged, view)
+        lowres = tuple(dshape[1:]) != (H, W)
+        fptr = frames.ctypes.data
+        in_place = fptr == out.ctypes.data + 3 * W and frames.strides[:2] == (out.strides[0], out.strides[1])
+        t = ctx.submit_host(fptr, frames.strides[1], frames.strides[0], dptr, B, H, W, dshape[1] if lowres else 0,
+                            dshape[2] if lowres else 0, float(scaler), out.ctypes.data,
+                            _native.HOST_RIGHT_IN_PLACE if in_place else 0)
+        self._inflight[t] = (frames, keep, out, staged)
+        return t
+
+    def collect(self, ticket):
+        """Block until the batch behind `ticket` is complete; raises if the device rejected one of its frames."""
+        try:
+            self._ctx.collect(ticket)
+        finally:
+            entry = self._inflight.pop(ticket, None)
+            if entry is not None and entry[3] is not None:
+                self._depth_pool.append(entry[3])
+
+    def _pinned_depth(self, nbytes):
+        for i, t in enumerate(self._depth_pool):
+            if t.numel() >= nbytes:
+                return self._depth_pool.pop(i)
+        return torch.empty((nbytes,), dtype=torch.uint8).pin_memory()
+
+    def _depth_arg(self, ctx, depths, B):
+        """(shape, pointer, object to keep alive) of a depth batch given as numpy / CPU tensor / CUDA tensor."""
+        if isinstance(depths, torch.Tensor) and depths.is_cuda:
+            # the depth producer's output is still on the device (same process): used where it is, no H2D of depth; the
+            # library's kernels are ordered behind the producer's stream by an event (the host does not wait)
+            _check_cuda(depths, torch.float16)
+            ctx.host_depends_on(torch.cuda.current_stream(depths.device).cuda_stream)
+            dshape, dptr, keep = tuple(depths.shape), depths.data_ptr(), depths
+        else:
+            d = _as_numpy(depths)
+            if d.dtype != np.float16:
+                raise TypeError(f"depth must be float16 (the producer's autocast dtype), got {d.dtype}")
+            dshape, dptr, keep = d.shape, d.ctypes.data, d
+        if len(dshape) != 3 or dshape[0] != B:
+            raise ValueError(f"depth {dshape} does not match {B} frames")
+        return dshape, dptr, keep
 
     def warp_batch_device(self, frames, raw_depth, out=None, depth_scratch=None):
         """Device-resident batch on the current stream, asynchronous: frames [B,H,W,3] uint8 CUDA,
@@ -185,6 +238,17 @@ class SbsProcessor:
         out = torch.empty_like(raw_dev)
         ctx.depth_from_full(raw_dev.data_ptr(), B, H, W, out.data_ptr(), self._stream())
         return out
+
+
+def pinned_sbs_buffer(n, H, W):
+    """Page-locked SBS buffer for `submit_batch`: (out [n,H,2W,3] uint8 numpy, frames view out[:, :, W:, :], owner).
+    Decode into the frames view (e.g. `np.copyto(frames[i], bgr[:, :, ::-1])`), submit, and after `collect` hand `out`
+    to the encoder - the right halves were never copied.  Keep `owner` (the torch tensor) alive as long as the arrays."""
+    t = torch.empty((n, H, 2 * W, 3), dtype=torch.uint8)
+    if torch.cuda.is_available():             # (CPU-only hosts run the worker's control-flow tests with a fake processor)
+        t = t.pin_memory()
+    out = t.numpy()
+    return out, out[:, :, W:, :], t
 
 
 def _as_numpy(x):

@@ -63,8 +63,13 @@ def flush_ranges(begin, end, video_length, max_frame_count):
     """The sub-clips one worker writes, exactly as nibba_woka's loop names them (PredictAndGenerate.py:221-250):
     [(last_i, i, frames)] -> file f"{last_i}_{i}.mp4" holding `frames` frames.  Frame i-1 is appended at iteration i
     (one-frame look-ahead) and the final frame at the last iteration, so a full sub-clip "0_15" holds frames 0..14
-    and the next one is named from 16."""
+    and the next one is named from 16.  A range of exactly one frame writes NOTHING: the reference's progress print
+    divides by `step_taken = i - begin` (:237-238), which is zero when the first flush happens at i == begin; the
+    ZeroDivisionError lands in the worker's catch-all handler (:259-272), which logs it and returns before ffmpeg is
+    started (probed by running the unmodified loop, tests/test_reference_callers.py)."""
     stop = min(end, video_length)
+    if stop - begin == 1:
+        return []
     out, pending, last_i = [], 0, begin
     for i in range(begin, stop):
         if i != begin:
