@@ -15,8 +15,9 @@
  *   - calls taking a stream are asynchronous and stream-ordered (stream = a cudaStream_t cast to
  *     void*, NULL = the legacy default stream); nothing synchronises the host unless stated;
  *   - a context is NOT thread-safe; use one per (process, device, clip range);
- *   - frames are uint8 RGB, [H,W,3] row-major (what `left_side_sbs` receives); depth is IEEE fp16
- *     (the producer's autocast dtype); an SBS frame is [H,2W,3] = [warped view | input frame].
+ *   - frames are uint8 RGB, [H,W,3] row-major (what `left_side_sbs` receives); full-resolution depth is
+ *     IEEE fp16 or fp32 (vrsbs_params.depth_dtype; the DPT-resolution map is always fp16); an SBS frame is
+ *     [H,2W,3] = [warped view | input frame].
  *   - there is no CPU fallback: without a CUDA device vrsbs_create fails.
  */
 #ifndef VRSBS_H
@@ -56,7 +57,17 @@ typedef struct vrsbs_params {
     int    offset_step_size;   /* --offset_step_size (PredictAndGenerate.py:344, default 1)      */
     int    blur;               /* 1 = full path; 0 = stop after hole fill (pre-blur view, strip  */
                                /*     not restored) — parity tiers T3/T4 only                    */
+    int    depth_dtype;        /* VRSBS_DEPTH_F16 (default) or VRSBS_DEPTH_F32: element type of    */
+                               /*     every full-resolution depth buffer of this clip range.  The  */
+                               /*     reference is dtype-agnostic: smoothing (:139-142), the max    */
+                               /*     (:102) and the bin comparison (:173) run in the tensor's      */
+                               /*     dtype.  fp16 is what autocast produced with the reference's   */
+                               /*     pinned torch; torch >= 2.4 on CUDA returns fp32 from the     */
+                               /*     bicubic tail (upsample_bicubic2d is on autocast's fp32 list). */
+                               /*     fp32 runs the general row kernel (slower, same contract).    */
 } vrsbs_params;
+
+enum { VRSBS_DEPTH_F16 = 0, VRSBS_DEPTH_F32 = 1 };
 
 /* What the device decided for one frame (the python lists `get_cutoff` returns, flattened). */
 typedef struct vrsbs_frame_info {
@@ -175,6 +186,9 @@ int  vrsbs_get_frame_info(vrsbs_ctx *ctx, int B, vrsbs_frame_info *info_host, vo
  * fp16 bit patterns.  Any output pointer may be NULL.  cap = capacity in elements of each array. */
 int  vrsbs_get_tables(vrsbs_ctx *ctx, int frame, int cap, double *cutoffs, int32_t *offsets,
                       uint16_t *lo_f16, uint16_t *hi_f16, void *stream);
+/* The [lo, hi) bounds the device compares the depth against, as floats (exact in both depth dtypes: fp16-narrowed
+ * values for fp16 depth, fp32-narrowed ones for fp32 depth).  Returns L. */
+int  vrsbs_get_bounds(vrsbs_ctx *ctx, int frame, int cap, float *lo, float *hi, void *stream);
 /* Hole bitmask of the last vrsbs_warp_batch: [B,H,ceil(W/32)] uint32, bit x%32 of word x/32. */
 int  vrsbs_get_hole_mask(vrsbs_ctx *ctx, int B, int H, int W, uint32_t *mask_host, void *stream);
 /* Number of kernels this library has launched on this context (bench.py's gpu_launches). */

@@ -70,14 +70,12 @@ static inline int reflect(int i, int n) { if (i < 0) i = -i; if (i >= n) i = 2 *
  * optional pre_blur [H,W,3] (view after hole fill, before blur and strip).
  * Returns the number of hole pixels, or -1 on bad arguments.
  */
-long sbs_oracle_warp_frame(const uint8_t *img, const uint16_t *depth, int H, int W, int L,
-                           const uint16_t *lo16, const uint16_t *hi16, const int *off,
-                           int fill_layer, int strip, int kx, int ky, const float *weights,
-                           uint8_t *sbs, int16_t *winner_out, uint8_t *pre_blur_out)
+static long warp_core(const uint8_t *img, const float *depthf, const uint16_t *depth16, int H, int W, int L,
+                      const float *lo, const float *hi, const int *off,
+                      int fill_layer, int strip, int kx, int ky, const float *weights,
+                      uint8_t *sbs, int16_t *winner_out, uint8_t *pre_blur_out)
 {
     if (H <= 0 || W <= 0 || L <= 0 || L > 32767 || fill_layer < 0 || fill_layer >= L) return -1;
-    float *lo = malloc(sizeof(float) * L), *hi = malloc(sizeof(float) * L);
-    for (int k = 0; k < L; ++k) { lo[k] = h2f(lo16[k]); hi[k] = h2f(hi16[k]); }
     int16_t *winner = winner_out ? winner_out : malloc(sizeof(int16_t) * (size_t)H * W);
     uint8_t *pre = pre_blur_out ? pre_blur_out : malloc((size_t)H * W * 3);
     const size_t pitch = (size_t)W * 6;
@@ -90,7 +88,8 @@ long sbs_oracle_warp_frame(const uint8_t *img, const uint16_t *depth, int H, int
         uint8_t *p = pre + (size_t)y * W * 3;
         for (int x = 0; x < W; ++x) win[x] = -1;
         for (int x = 0; x < W; ++x) {
-            float d = h2f(depth[(size_t)y * W + x]);
+            /* the comparison runs in the depth dtype (:173): fp16 values and fp16-rounded bounds, or fp32 and fp32 */
+            float d = depthf ? depthf[(size_t)y * W + x] : h2f(depth16[(size_t)y * W + x]);
             for (int k = 0; k < L; ++k)
                 if (lo[k] <= d && d < hi[k]) {
                     int xd = wrap(x + off[k], W);
@@ -127,10 +126,58 @@ long sbs_oracle_warp_frame(const uint8_t *img, const uint16_t *depth, int H, int
         if (strip > 0) memcpy(out, src, (size_t)(strip < W ? strip : W) * 3);
         memcpy(out + (size_t)W * 3, src, (size_t)W * 3);
     }
-    free(lo); free(hi);
     if (!winner_out) free(winner);
     if (!pre_blur_out) free(pre);
     return holes;
 }
 
-int sbs_oracle_abi_version(void) { return 1; }
+long sbs_oracle_warp_frame(const uint8_t *img, const uint16_t *depth, int H, int W, int L,
+                           const uint16_t *lo16, const uint16_t *hi16, const int *off,
+                           int fill_layer, int strip, int kx, int ky, const float *weights,
+                           uint8_t *sbs, int16_t *winner_out, uint8_t *pre_blur_out)
+{
+    if (L <= 0 || L > 32767) return -1;
+    float *lo = malloc(sizeof(float) * L), *hi = malloc(sizeof(float) * L);
+    for (int k = 0; k < L; ++k) { lo[k] = h2f(lo16[k]); hi[k] = h2f(hi16[k]); }
+    long r = warp_core(img, NULL, depth, H, W, L, lo, hi, off, fill_layer, strip, kx, ky, weights, sbs, winner_out, pre_blur_out);
+    free(lo); free(hi);
+    return r;
+}
+
+/* fp32 depth (what torch >= 2.4's CUDA autocast hands the warp: upsample_bicubic2d is on autocast's fp32 list):
+ * smoothing in fp32 (:139-142 with an fp32 tensor), bounds narrowed double -> float, comparison in fp32 (:173). */
+void sbs_oracle_smooth_f32(const float *raw, const float *h1, const float *h0, float *out, size_t n,
+                           float w_now, float w1, float w0)
+{
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; ++i) {
+        float d = raw[i] * w_now;
+        float t = h1[i] * w1;
+        d = d + t;
+        t = h0[i] * w0;
+        out[i] = d + t;
+    }
+}
+
+float sbs_oracle_max_f32(const float *d, size_t n)
+{
+    float m = -INFINITY;
+    int nan = 0;
+#pragma omp parallel for reduction(max : m) reduction(| : nan) schedule(static)
+    for (size_t i = 0; i < n; ++i) {
+        float v = d[i];
+        if (v != v) nan = 1;
+        else if (v > m) m = v;
+    }
+    return nan ? NAN : m;
+}
+
+long sbs_oracle_warp_frame_f32(const uint8_t *img, const float *depth, int H, int W, int L,
+                               const float *lo, const float *hi, const int *off,
+                               int fill_layer, int strip, int kx, int ky, const float *weights,
+                               uint8_t *sbs, int16_t *winner_out, uint8_t *pre_blur_out)
+{
+    return warp_core(img, depth, NULL, H, W, L, lo, hi, off, fill_layer, strip, kx, ky, weights, sbs, winner_out, pre_blur_out);
+}
+
+int sbs_oracle_abi_version(void) { return 2; }

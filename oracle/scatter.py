@@ -43,6 +43,15 @@ def lib():
                                             ctypes.POINTER(ctypes.c_float), u8p,
                                             ctypes.POINTER(ctypes.c_int16), u8p]
         l.sbs_oracle_warp_frame.restype = ctypes.c_long
+        f32p = ctypes.POINTER(ctypes.c_float)
+        l.sbs_oracle_smooth_f32.argtypes = [f32p, f32p, f32p, f32p, ctypes.c_size_t, ctypes.c_float, ctypes.c_float, ctypes.c_float]
+        l.sbs_oracle_smooth_f32.restype = None
+        l.sbs_oracle_max_f32.argtypes = [f32p, ctypes.c_size_t]
+        l.sbs_oracle_max_f32.restype = ctypes.c_float
+        l.sbs_oracle_warp_frame_f32.argtypes = [u8p, f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, f32p, f32p,
+                                                ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                ctypes.c_int, f32p, u8p, ctypes.POINTER(ctypes.c_int16), u8p]
+        l.sbs_oracle_warp_frame_f32.restype = ctypes.c_long
         _lib = l
     return _lib
 
@@ -52,13 +61,20 @@ def _p(a, ct):
 
 
 def smooth_depth(state, raw):
-    """Same contract as sbs_layered.smooth_depth, fp16 only."""
-    assert raw.dtype == np.float16
+    """Same contract as sbs_layered.smooth_depth (fp16 or fp32 depth)."""
+    assert raw.dtype in (np.float16, np.float32)
     raw = np.ascontiguousarray(raw)
     hist = state.history
     while len(hist) < 2:
         hist.append(raw.copy())
     out = np.empty_like(raw)
+    if raw.dtype == np.float32:
+        lib().sbs_oracle_smooth_f32(_p(raw, ctypes.c_float), _p(hist[1], ctypes.c_float), _p(hist[0], ctypes.c_float),
+                                    _p(out, ctypes.c_float), raw.size, np.float32(state.w_now), np.float32(state.taps[0]),
+                                    np.float32(state.taps[1]))
+        del hist[0]
+        hist.append(raw.copy())
+        return out
     lib().sbs_oracle_smooth_f16(_p(raw.view(np.uint16), ctypes.c_uint16),
                                 _p(hist[1].view(np.uint16), ctypes.c_uint16),
                                 _p(hist[0].view(np.uint16), ctypes.c_uint16),
@@ -72,13 +88,16 @@ def smooth_depth(state, raw):
 
 def depth_max(depth):
     depth = np.ascontiguousarray(depth)
+    if depth.dtype == np.float32:
+        return float(lib().sbs_oracle_max_f32(_p(depth, ctypes.c_float), depth.size))
     return float(lib().sbs_oracle_max_f16(_p(depth.view(np.uint16), ctypes.c_uint16), depth.size))
 
 
 def warp_frame(img, depth, marks, steps, offsets, weights=None, stages=None):
     H, W, _ = img.shape
     n = len(steps)
-    lo, hi = L.layer_bounds(marks, steps, np.float16)
+    f32 = depth.dtype == np.float32
+    lo, hi = L.layer_bounds(marks, steps, np.float32 if f32 else np.float16)
     off = np.asarray(offsets, dtype=np.int32)
     kx, ky = L.blur_kernel_shape(H)
     if weights is None:
@@ -92,11 +111,17 @@ def warp_frame(img, depth, marks, steps, offsets, weights=None, stages=None):
     pre = np.empty((H, W, 3), dtype=np.uint8)
     fill = int(n * 3 / 5)
     sw = L.strip_width(offsets[-1], W)
-    holes = lib().sbs_oracle_warp_frame(
-        _p(img, ctypes.c_uint8), _p(depth.view(np.uint16), ctypes.c_uint16), H, W, n,
-        _p(lo.view(np.uint16), ctypes.c_uint16), _p(hi.view(np.uint16), ctypes.c_uint16),
-        _p(off, ctypes.c_int), fill, sw, kx, ky, _p(weights, ctypes.c_float),
-        _p(sbs, ctypes.c_uint8), _p(winner, ctypes.c_int16), _p(pre, ctypes.c_uint8))
+    if f32:
+        holes = lib().sbs_oracle_warp_frame_f32(
+            _p(img, ctypes.c_uint8), _p(depth, ctypes.c_float), H, W, n, _p(lo, ctypes.c_float), _p(hi, ctypes.c_float),
+            _p(off, ctypes.c_int), fill, sw, kx, ky, _p(weights, ctypes.c_float),
+            _p(sbs, ctypes.c_uint8), _p(winner, ctypes.c_int16), _p(pre, ctypes.c_uint8))
+    else:
+        holes = lib().sbs_oracle_warp_frame(
+            _p(img, ctypes.c_uint8), _p(depth.view(np.uint16), ctypes.c_uint16), H, W, n,
+            _p(lo.view(np.uint16), ctypes.c_uint16), _p(hi.view(np.uint16), ctypes.c_uint16),
+            _p(off, ctypes.c_int), fill, sw, kx, ky, _p(weights, ctypes.c_float),
+            _p(sbs, ctypes.c_uint8), _p(winner, ctypes.c_int16), _p(pre, ctypes.c_uint8))
     if holes < 0:
         raise ValueError("sbs_oracle_warp_frame: bad arguments")
     if stages is not None:

@@ -12,6 +12,7 @@ if ROOT not in sys.path:
 
 SMALL_CASES = ["small_a", "small_b", "small_step3", "small_neg", "small_zero", "small_pospos", "small_negneg", "medium"]
 FULL_CASES = ["full_1080p_cfg1", "full_1080p_step2", "full_4k_wide"]
+F32_CASES = ["small_f32", "medium_f32"]          # fp32 depth (torch >= 2.4 CUDA autocast): run through the general row kernel
 
 
 def pytest_configure(config):
@@ -50,6 +51,8 @@ def regenerate_inputs(meta):
         raw = (raw.astype(np.float32) - np.float32(meta["shift"])).astype(np.float16)
     for t in meta["zero"]:
         raw[t] = 0
+    if meta.get("f32"):
+        raw = raw.astype(np.float32) * np.float32(1.00037)
     for key, arr in (("frames", frames), ("raw_depth", raw)):
         got = hashlib.sha256(np.ascontiguousarray(arr).tobytes()).hexdigest()
         assert got == meta["inputs_sha"][key], f"synthetic {key} not reproducible on this host"

@@ -60,6 +60,10 @@ CASES = {
     # same-sign offsets reach the warp as typed (the CLI's fix-up at PredictAndGenerate.py:387-393 never touches args_god)
     "small_pospos": dict(H=96, W=160, n=3, fg=0.12, bg=0.04, step=1, frames="noise", depth="stress", lo=(30, 50), seed=12),
     "small_negneg": dict(H=96, W=160, n=3, fg=-0.04, bg=-0.12, step=1, frames="noise", depth="scene", lo=(30, 50), seed=13),
+    # fp32 depth: what torch >= 2.4's CUDA autocast delivers (upsample_bicubic2d is on its fp32 list); values are NOT fp16-
+    # representable (x 1.00037), so smoothing, the max and the bin comparisons really run in fp32
+    "small_f32":   dict(H=120, W=160, n=4, fg=0.05, bg=-0.03, step=1, frames="noise", depth="stress", lo=(37, 50), seed=14, f32=True),
+    "medium_f32":  dict(H=270, W=480, n=3, fg=0.025, bg=-0.01, step=1, frames="gradient", depth="scene", lo=(74, 132), seed=15, f32=True),
     "medium":      dict(H=270, W=480, n=4, fg=0.025, bg=-0.015, step=1, frames="gradient", depth="scene", lo=(74, 132), seed=6),
     "full_1080p_cfg1":  dict(H=1080, W=1920, n=3, fg=0.025, bg=-0.015, step=1, frames="noise", depth="stress", lo=(518, 924), seed=7, full=True),
     "full_1080p_step2": dict(H=1080, W=1920, n=2, fg=0.025, bg=-0.01, step=2, frames="gradient", depth="scene", lo=(518, 924), seed=8, full=True),
@@ -74,6 +78,8 @@ def case_inputs(c):
     raw = full_depth(c["depth"], c["n"], c["H"], c["W"], c["seed"], c["lo"], 1.0, c.get("shift", 0.0))
     for t in c.get("zero", ()):
         raw[t] = 0
+    if c.get("f32"):
+        raw = raw.astype(np.float32) * np.float32(1.00037)
     return frames, raw
 
 
@@ -85,7 +91,7 @@ def run_case(name, c):
     st = O.WarpState(c["fg"], c["bg"], c["step"])
     weights = O.gaussian_weights(*O.blur_kernel_shape(H))
     meta = dict(params={k: c[k] for k in ("H", "W", "n", "fg", "bg", "step", "frames", "depth", "seed")},
-                lowres=list(c["lo"]), shift=c.get("shift", 0.0), zero=list(c.get("zero", ())),
+                lowres=list(c["lo"]), shift=c.get("shift", 0.0), zero=list(c.get("zero", ())), f32=bool(c.get("f32", False)),
                 weights=hexlist(weights.ravel()), weights_shape=list(weights.shape),
                 inputs_sha=dict(frames=sha(frames), raw_depth=sha(raw)), frames=[])
     lefts = []

@@ -11,7 +11,7 @@ import queue
 import numpy as np
 import pytest
 
-from conftest import FULL_CASES, GOLDEN, SMALL_CASES, golden_weights, load_case, unhex
+from conftest import F32_CASES, FULL_CASES, GOLDEN, SMALL_CASES, golden_weights, load_case, unhex
 
 pytestmark = pytest.mark.gpu
 
@@ -30,10 +30,10 @@ def _sha(a):
 MODES = [0, 1, 2, 3, 4, 5, 6]
 
 
-def _ctx(H, W, fg, bg, step, weights=None, blur=True, max_batch=8, max_layers=512, mode=0):
+def _ctx(H, W, fg, bg, step, weights=None, blur=True, max_batch=8, max_layers=512, mode=0, f32=False):
     from vr_video_generator_b200 import _native, tables
     ctx = _native.Context(0, H, W, max_batch, max_layers)
-    ctx.reset(fg, bg, step, blur)
+    ctx.reset(fg, bg, step, blur, _native.DEPTH_F32 if f32 else _native.DEPTH_F16)
     if weights is None:
         weights = tables.gaussian_weights(*tables.blur_kernel_shape(H))
     ctx.set_blur_weights(weights)
@@ -55,7 +55,7 @@ def _run_device(ctx, frames, raw, splits=None):
     f = torch.from_numpy(np.ascontiguousarray(frames)).cuda()
     r = torch.from_numpy(np.ascontiguousarray(raw)).cuda()
     out = torch.empty((n, H, 2 * W, 3), dtype=torch.uint8, device="cuda")
-    dep = torch.empty((n, H, W), dtype=torch.float16, device="cuda")
+    dep = torch.empty((n, H, W), dtype=r.dtype, device="cuda")
     infos, masks = [], []
     s = torch.cuda.current_stream().cuda_stream
     t = 0
@@ -107,6 +107,78 @@ def test_small_cases_match_reference(name, mode, oracle_lib):
         assert np.array_equal(sbs[t], want[t])
         assert _sha(sbs[t]) == fm["sha256"]
     ctx.close()
+
+
+@pytest.mark.parametrize("splits", [None, [1, 2], [2, 1, 1]])
+@pytest.mark.parametrize("name", F32_CASES)
+def test_fp32_depth_matches_reference(name, splits, oracle_lib):
+    """fp32 depth (what torch >= 2.4's CUDA autocast hands the warp): smoothing, max and the bin comparison in fp32 -
+    byte-identical to the UNMODIFIED reference fed the same fp32 maps (fixtures generated by the reference), fp32 bit
+    patterns of the smoothed depth and of the bounds equal to the oracle's, state carried across batch splits."""
+    meta, frames, raw, ref_left = load_case(name)
+    assert raw.dtype == np.float32
+    p = meta["params"]
+    w = golden_weights(meta)
+    if splits is not None and sum(splits) != p["n"]:
+        splits = [1] * p["n"]
+    ctx = _ctx(p["H"], p["W"], p["fg"], p["bg"], p["step"], w, f32=True)
+    sbs, dep, infos, masks = _run_device(ctx, frames, raw, splits)
+    want, stages = _oracle_run(oracle_lib, p, frames, raw, w)
+    for t in range(p["n"]):
+        fm = meta["frames"][t]
+        assert dep.dtype == np.float32 and np.array_equal(dep[t].view(np.uint32), stages[t]["depth"].view(np.uint32))
+        assert infos[t].layers == fm["layers"] and infos[t].limit_step == fm["limit"] and infos[t].holes == fm["holes"]
+        assert list(infos[t].offset_range) == unhex(fm["range"])
+        assert np.array_equal(masks[t], stages[t]["holes"])
+        assert np.array_equal(sbs[t][:, :p["W"]], ref_left[t]), f"{name}[{t}] differs from the reference"
+        assert np.array_equal(sbs[t], want[t]) and _sha(sbs[t]) == fm["sha256"]
+    if splits is None:
+        for t in range(p["n"]):
+            lo, hi = ctx.bounds(t)
+            lo_ref, hi_ref = O.layer_bounds(unhex(meta["frames"][t]["cutoffs"]), unhex(meta["frames"][t]["steps"]), np.float32)
+            assert np.array_equal(lo.view(np.uint32), lo_ref.view(np.uint32)) and np.array_equal(hi.view(np.uint32), hi_ref.view(np.uint32))
+    ctx.close()
+
+
+def test_fp32_depth_through_the_dropin_and_the_host_pipeline(oracle_lib):
+    """The drop-in SbsProcessor with fp32 depth on the queue (per-frame call), the batched host call, submit / collect and
+    the DPT-resolution route (fp32 tail: bicubic on the fp32 view of the fp16 map, no narrowing, `* scaler` in fp32)."""
+    import vr_video_generator_b200 as pkg
+    from vr_video_generator_b200.sbs import pinned_sbs_buffer
+    meta, frames, raw, ref_left = load_case("medium_f32")
+    p = meta["params"]
+    H, W, n = p["H"], p["W"], p["n"]
+    args = argparse.Namespace(offset_fg=p["fg"], offset_bg=p["bg"], offset_step_size=p["step"])
+    proc = pkg.SbsProcessor(None, 0, args, max_batch=2)
+    q = queue.Queue()
+    for t in range(n):
+        q.put(torch.from_numpy(raw[t]))
+        got = proc.left_side_sbs(frames[t], None, q)
+        assert np.array_equal(got[:, :W], ref_left[t]) and np.array_equal(got[:, W:], frames[t]), t
+    proc.reset_state()
+    got = proc.left_side_sbs_batch(frames, raw)
+    assert np.array_equal(got[:, :, :W], ref_left)
+    proc.reset_state()
+    out, view, _ = pinned_sbs_buffer(n, H, W)
+    np.copyto(view, frames)
+    proc.collect(proc.submit_batch(view, raw, out))
+    assert np.array_equal(out[:, :, :W], ref_left)
+    proc.reset_state()
+    dev = proc.warp_batch_device(torch.from_numpy(frames).cuda(), torch.from_numpy(raw).cuda())
+    assert np.array_equal(dev.cpu().numpy()[:, :, :W], ref_left)
+    proc.close()
+    # DPT-resolution route with an fp32 clip: equals torch's own fp32 bicubic (what autocast runs) within 1e-6 relative, and
+    # the frames equal the full-resolution route fed that map
+    from vr_video_generator_b200 import synth
+    lo = synth.depth_scene(n, 74, 132, seed=15)
+    p32 = pkg.SbsProcessor(None, 0, args, max_batch=4, depth_dtype="float32")
+    got_lo = p32.left_side_sbs_batch(frames, lo, scaler=1.618)
+    up = torch.nn.functional.interpolate(torch.from_numpy(lo).cuda().float()[:, None], (H, W), mode="bicubic", align_corners=True)[:, 0] * 1.618
+    assert up.dtype == torch.float32
+    p32b = pkg.SbsProcessor(None, 0, args, max_batch=4)
+    want_lo = p32b.left_side_sbs_batch(frames, up.cpu().numpy())
+    assert np.mean(got_lo == want_lo) > 0.9995
+    p32.close(), p32b.close()
 
 
 @pytest.mark.parametrize("name", SMALL_CASES)

@@ -4,12 +4,12 @@ import math
 import numpy as np
 import pytest
 
-from conftest import FULL_CASES, SMALL_CASES, load_meta, unhex
+from conftest import F32_CASES, FULL_CASES, SMALL_CASES, load_meta, unhex
 from oracle import sbs_layered as O
 from vr_video_generator_b200 import synth, tables
 
 
-@pytest.mark.parametrize("name", SMALL_CASES + FULL_CASES)
+@pytest.mark.parametrize("name", SMALL_CASES + F32_CASES + FULL_CASES)
 def test_layer_tables_match_reference_lists(name):
     """T1 on the host mirror: exact doubles against the lists the reference's get_cutoff returned."""
     meta = load_meta(name)

@@ -5,7 +5,7 @@ import hashlib
 import numpy as np
 import pytest
 
-from conftest import FULL_CASES, SMALL_CASES, golden_weights, load_case, unhex
+from conftest import F32_CASES, FULL_CASES, SMALL_CASES, golden_weights, load_case, unhex
 from oracle import sbs_layered as O
 
 
@@ -24,7 +24,7 @@ def _check_tables(stages, fm):
     assert int(stages["fill_layer"]) == fm["fill_layer"]
 
 
-@pytest.mark.parametrize("name", SMALL_CASES)
+@pytest.mark.parametrize("name", SMALL_CASES + F32_CASES)
 @pytest.mark.parametrize("impl", ["layered", "scatter"])
 def test_small_cases_bit_exact(name, impl, oracle_lib):
     meta, frames, raw, ref_left = load_case(name)

@@ -17,11 +17,12 @@ SYMBOLS = [
     "vrsbs_get_range_state", "vrsbs_set_range_state", "vrsbs_set_blur_weights",
     "vrsbs_depth_from_lowres", "vrsbs_depth_from_full", "vrsbs_build_tables", "vrsbs_warp_batch",
     "vrsbs_process_batch", "vrsbs_process_host", "vrsbs_submit_host", "vrsbs_collect", "vrsbs_host_depends_on",
-    "vrsbs_get_frame_info", "vrsbs_get_tables",
+    "vrsbs_get_frame_info", "vrsbs_get_tables", "vrsbs_get_bounds",
     "vrsbs_get_hole_mask", "vrsbs_get_stage_times", "vrsbs_launch_count", "vrsbs_set_option",
 ]
 
 FRAME_NAN, FRAME_OVERFLOW, FRAME_GENERIC = 1, 2, 4
+DEPTH_F16, DEPTH_F32 = 0, 1
 HOST_RIGHT_IN_PLACE = 1
 
 
@@ -33,7 +34,7 @@ class VrsbsError(RuntimeError):
 
 class Params(ctypes.Structure):
     _fields_ = [("offset_fg", ctypes.c_double), ("offset_bg", ctypes.c_double),
-                ("offset_step_size", ctypes.c_int), ("blur", ctypes.c_int)]
+                ("offset_step_size", ctypes.c_int), ("blur", ctypes.c_int), ("depth_dtype", ctypes.c_int)]
 
 
 class FrameInfo(ctypes.Structure):
@@ -80,6 +81,7 @@ def load():
     lib.vrsbs_get_frame_info.argtypes = [vp, ci, ctypes.POINTER(FrameInfo), vp]
     lib.vrsbs_get_tables.argtypes = [vp, ci, ci, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int32),
                                      ctypes.POINTER(ctypes.c_uint16), ctypes.POINTER(ctypes.c_uint16), vp]
+    lib.vrsbs_get_bounds.argtypes = [vp, ci, ci, ctypes.POINTER(cf), ctypes.POINTER(cf), vp]
     lib.vrsbs_get_hole_mask.argtypes = [vp, ci, ci, ci, ctypes.POINTER(ctypes.c_uint32), vp]
     lib.vrsbs_get_stage_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]
     lib.vrsbs_launch_count.argtypes = [vp]
@@ -126,8 +128,8 @@ class Context:
             pass
 
     # --- state -------------------------------------------------------------------------------
-    def reset(self, offset_fg, offset_bg, offset_step_size, blur=True):
-        p = Params(offset_fg, offset_bg, offset_step_size, 1 if blur else 0)
+    def reset(self, offset_fg, offset_bg, offset_step_size, blur=True, depth_dtype=DEPTH_F16):
+        p = Params(offset_fg, offset_bg, offset_step_size, 1 if blur else 0, depth_dtype)
         self.check(self.lib.vrsbs_reset(self.handle, ctypes.byref(p)))
 
     def get_range_state(self):
@@ -199,6 +201,16 @@ class Context:
             off.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), lo.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)),
             hi.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)), stream))
         return cut[:L + 1].copy(), off[:L].copy(), lo[:L].view(np.float16).copy(), hi[:L].view(np.float16).copy()
+
+    def bounds(self, frame, stream=0):
+        """(lo, hi) float32 arrays: the bounds the device compares against (exact for fp16 and fp32 depth)."""
+        import numpy as np
+        cap = self.max_layers
+        lo = np.empty(cap, dtype=np.float32)
+        hi = np.empty(cap, dtype=np.float32)
+        L = self.check(self.lib.vrsbs_get_bounds(self.handle, frame, cap, lo.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+                                                 hi.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), stream))
+        return lo[:L].copy(), hi[:L].copy()
 
     def hole_mask(self, B, H, W, stream=0):
         import numpy as np

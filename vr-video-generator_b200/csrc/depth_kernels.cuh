@@ -324,6 +324,88 @@ __global__ void __launch_bounds__(256) k_depth_lowres(DepthArgs a) {
     }
 }
 
+// ---- fp32 depth (general route) ---------------------------------------------------------------------------------
+// The reference's warp is dtype-agnostic, and torch >= 2.4's CUDA autocast puts upsample_bicubic2d on its fp32 list,
+// so a producer running `infer_image_gpu` under autocast(fp16) hands the warp an fp32 map (measured on the B200 box).
+// Smoothing then runs in fp32 (PredictAndGenerate.py:139-142: one rounding per op), the tail is bicubic on the fp32 view
+// of the fp16 DPT output WITHOUT narrowing, `* scaler` in fp32.  One pixel per thread for all frames of the batch.
+struct DepthArgs32 {
+    const float *raw;         // [B, n] full-res raw depth (full variant)
+    const __half *lowres;     // [B, h, w] DPT output (lowres variant)
+    float *out;               // [B, n] smoothed
+    float *hist1, *hist2;     // [n] raw depth of frames t-1, t-2
+    uint32_t *frame_max, *frame_nan;
+    SmoothWeights sw;
+    int B, H, W, h, w, first;
+    float scaler, scale_y, scale_x;
+};
+
+__device__ __forceinline__ float smooth3_f32(float cur, float p1, float p2, float w0, float w1, float w2) {
+    float d = __fmul_rn(cur, w0);
+    d = __fadd_rn(d, __fmul_rn(p1, w1));
+    return __fadd_rn(d, __fmul_rn(p2, w2));
+}
+
+template <bool LOWRES, bool CONTRACT>
+__global__ void __launch_bounds__(256) k_depth_f32(DepthArgs32 a) {
+    extern __shared__ uint32_t s_red[];
+    uint32_t *s_max = s_red, *s_nan = s_red + a.B;
+    for (int i = threadIdx.x; i < 2 * a.B; i += blockDim.x) s_red[i] = 0;
+    __syncthreads();
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const bool active = x < a.W && y < a.H;
+    const size_t n = (size_t)a.H * a.W;
+    const size_t pix = active ? (size_t)y * a.W + x : 0;
+    float cx[4], cy[4];
+    int ix[4], iy[4];
+    if (LOWRES) {
+        float rx = __fmul_rn(a.scale_x, (float)x), ry = __fmul_rn(a.scale_y, (float)y);
+        int fx = (int)floorf(rx), fy = (int)floorf(ry);
+        Cubic<CONTRACT>::coeffs(rx - (float)fx, cx);
+        Cubic<CONTRACT>::coeffs(ry - (float)fy, cy);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            ix[k] = max(min(fx - 1 + k, a.w - 1), 0);
+            iy[k] = max(min(fy - 1 + k, a.h - 1), 0) * a.w;
+        }
+    }
+    float p1 = 0.f, p2 = 0.f;
+    if (active && !a.first) { p1 = a.hist1[pix]; p2 = a.hist2[pix]; }
+    for (int t = 0; t < a.B; ++t) {
+        uint32_t enc = 0;
+        bool nan = false;
+        if (active) {
+            float cur;
+            if (LOWRES) {
+                const __half *src = a.lowres + (size_t)t * a.h * a.w;
+                float rows[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    rows[k] = Cubic<CONTRACT>::dot4(h2f(__ldg(src + iy[k] + ix[0])), h2f(__ldg(src + iy[k] + ix[1])),
+                                                    h2f(__ldg(src + iy[k] + ix[2])), h2f(__ldg(src + iy[k] + ix[3])), cx);
+                cur = Cubic<CONTRACT>::dot4(rows[0], rows[1], rows[2], rows[3], cy);
+                if (a.scaler != 1.0f) cur = __fmul_rn(cur, a.scaler);
+            } else {
+                cur = __ldg(a.raw + (size_t)t * n + pix);
+            }
+            if (a.first && t == 0) p1 = p2 = cur;
+            const float res = smooth3_f32(cur, p1, p2, a.sw.w_now, a.sw.w_prev1, a.sw.w_prev2);
+            a.out[(size_t)t * n + pix] = res;
+            if (res != res) nan = true; else enc = f2ord(res);
+            p2 = p1;
+            p1 = cur;
+        }
+        frame_max_commit(enc, nan, t, s_max, s_nan);
+    }
+    if (active) { a.hist1[pix] = p1; a.hist2[pix] = p2; }
+    __syncthreads();
+    for (int t = threadIdx.x; t < a.B; t += blockDim.x) {
+        if (s_max[t]) atomicMax(&a.frame_max[t], s_max[t]);
+        if (s_nan[t]) atomicOr(&a.frame_nan[t], 1u);
+    }
+}
+
 // ---- low-res DPT output in, tiled: horizontal interpolations shared by the output rows that use them --------
 // Same arithmetic as k_depth_lowres (ATen's: four row interpolations, then one column interpolation, every
 // mul/add in the same order), but a CTA owns a 64 x 16 output tile and first computes the row interpolation

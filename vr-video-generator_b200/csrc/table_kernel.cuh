@@ -28,6 +28,7 @@ struct TableArgs {
     int step, B, H, W, Lcap;
     int ent_cap, lut_cap;        // capacity of the blob's entry table (layers) and cell LUT (bytes)
     int key_pad;                 // fast path: every signed offset (shortest way round the row) must satisfy |off| <= key_pad
+    int f32;                     // 1: the depth is fp32 - bounds narrowed double -> float only, no fast-path tables
 };
 
 // LUT value for the cell of depth values [vmin, vmax] (monotone bounds required): e such that every
@@ -150,9 +151,11 @@ __global__ void __launch_bounds__(256) k_build_tables(TableArgs a) {
         // round(c / top * span + r0)
         int off = clamp_int(py_round(__dadd_rn(__dmul_rn(__ddiv_rn(c, top), span), r0)));
         // python double -> float -> half (c10::Half has only a float constructor)
-        __half lo = __float2half_rn(__double2float_rn(__dsub_rn(c, __dmul_rn(0.05, s))));
-        __half hi = __float2half_rn(__double2float_rn(__dadd_rn(c, __dmul_rn(1.05, s))));
-        const float2 bd = make_float2(__half2float(lo), __half2float(hi));
+        const float lo32 = __double2float_rn(__dsub_rn(c, __dmul_rn(0.05, s))), hi32 = __double2float_rn(__dadd_rn(c, __dmul_rn(1.05, s)));
+        __half lo = __float2half_rn(lo32);
+        __half hi = __float2half_rn(hi32);
+        // the comparison runs in the depth dtype (:173): fp16 depth sees the fp16-narrowed bounds, fp32 depth the fp32 ones
+        const float2 bd = a.f32 ? make_float2(lo32, hi32) : make_float2(__half2float(lo), __half2float(hi));
         bounds[k] = bd;
         s_bounds[k] = bd;                                      // (s_val region: every read of the marks is behind two barriers)
         a.lo16[(size_t)b * a.Lcap + k] = __half_as_ushort(lo);
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(256) k_build_tables(TableArgs a) {
     LayerEnt *ent = reinterpret_cast<LayerEnt *>(blob + 16);
     uint8_t *lut = blob + 16 + ent_bytes;
     const float fmax = s_max;
-    bool ok = mono && !s_bad && !a.frame_nan[b] && L <= a.ent_cap && L <= 255 && a.W * 4 <= 65535 && fmax < 60000.f;
+    bool ok = !a.f32 && mono && !s_bad && !a.frame_nan[b] && L <= a.ent_cap && L <= 255 && a.W * 4 <= 65535 && fmax < 60000.f;
     // (the LUT search binary-searches the bounds thousands of times: they are in shared memory already)
     const uint32_t maxbits = (fmax > 0.f) ? (uint32_t)__half_as_ushort(__float2half_rn(fmax)) : 0u;
     {

@@ -164,7 +164,8 @@ private:
 struct vrsbs_ctx {
     int device = 0, max_h = 0, max_w = 0, max_batch = 0, max_layers = 0;
     int sm_count = 0;
-    vrsbs_params params{0.025, -0.01, 1, 1};
+    vrsbs_params params{0.025, -0.01, 1, 1, VRSBS_DEPTH_F16};
+    int f32 = 0;                         // params.depth_dtype == VRSBS_DEPTH_F32: every depth pointer is float, general route
     SmoothWeights sw{};
     // clip-range state
     __half *hist[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [set][0: raw t-1, 1: raw t-2]; set hist_idx is current
@@ -352,11 +353,33 @@ int check_state_dims(vrsbs_ctx *c, int H, int W) {
 }
 
 // staged route: smoothed depth is materialised (vrsbs_depth_from_full / vrsbs_depth_from_lowres)
-int launch_depth(vrsbs_ctx *c, Scratch &s, const __half *raw, const __half *lowres, int B, int H, int W, int h, int w,
-                 float scaler, __half *out, cudaStream_t st) {
+int launch_depth(vrsbs_ctx *c, Scratch &s, const void *raw_v, const __half *lowres, int B, int H, int W, int h, int w,
+                 float scaler, void *out_v, cudaStream_t st) {
     int rc = check_state_dims(c, H, W);
     if (rc) return rc;
     if ((rc = clear_counters(c, s, B, st))) return rc;
+    if (c->f32) {
+        DepthArgs32 a{};
+        a.raw = static_cast<const float *>(raw_v); a.lowres = lowres; a.out = static_cast<float *>(out_v);
+        a.hist1 = reinterpret_cast<float *>(c->hist[c->hist_idx][0]); a.hist2 = reinterpret_cast<float *>(c->hist[c->hist_idx][1]);
+        a.frame_max = s.frame_max; a.frame_nan = s.frame_nan; a.sw = c->sw;
+        a.B = B; a.H = H; a.W = W; a.h = h; a.w = w; a.first = c->depth_frames == 0; a.scaler = scaler;
+        a.scale_y = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f;
+        a.scale_x = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
+        const size_t smem32 = sizeof(uint32_t) * 2 * B;
+        dim3 grid((W + 31) / 32, (H + 7) / 8);
+        StageTimer timer(c, st, 0);
+        if (raw_v) k_depth_f32<false, true><<<grid, 256, smem32, st>>>(a);
+        else if (c->bicubic_contract) k_depth_f32<true, true><<<grid, 256, smem32, st>>>(a);
+        else k_depth_f32<true, false><<<grid, 256, smem32, st>>>(a);
+        CU_TRY(c, cudaGetLastError());
+        c->launches++;
+        c->depth_frames += B;
+        c->state_h = H; c->state_w = W;
+        return VRSBS_OK;
+    }
+    const __half *raw = static_cast<const __half *>(raw_v);
+    __half *out = static_cast<__half *>(out_v);
     DepthArgs a{};
     a.raw = raw; a.lowres = lowres; a.out = out; a.hist1 = c->hist[c->hist_idx][0]; a.hist2 = c->hist[c->hist_idx][1];
     a.frame_max = s.frame_max; a.frame_nan = s.frame_nan; a.sw = c->sw;
@@ -455,7 +478,7 @@ int launch_tables(vrsbs_ctx *c, Scratch &s, int B, int H, int W, cudaStream_t st
     a.tabs = s.tabs; a.bounds = s.bounds; a.offm = s.offm; a.cutoffs = s.cutoffs; a.offsets = s.offsets;
     a.lo16 = s.lo16; a.hi16 = s.hi16;
     a.offset_fg = c->params.offset_fg; a.offset_bg = c->params.offset_bg; a.step = c->params.offset_step_size;
-    a.B = B; a.H = H; a.W = W; a.Lcap = c->max_layers;
+    a.B = B; a.H = H; a.W = W; a.Lcap = c->max_layers; a.f32 = c->f32;
     fast_caps(c, H, W, &c->ent_cap, &c->lut_cap);
     a.blobs = s.blobs; a.ent_cap = c->ent_cap; a.lut_cap = c->lut_cap; a.key_pad = c->key_pad;
     const size_t smem = sizeof(double) * 2 * (size_t)(c->max_layers + 2 > B ? c->max_layers + 2 : B) +
@@ -468,10 +491,10 @@ int launch_tables(vrsbs_ctx *c, Scratch &s, int B, int H, int W, cudaStream_t st
     return VRSBS_OK;
 }
 
-template <int MODE, bool TMA, int NT>
+template <int MODE, bool TMA, int NT, bool F32 = false>
 int launch_warp_inst(vrsbs_ctx *c, const WarpArgs &a, cudaStream_t st) {
-    auto kern = k_warp_rows<MODE, TMA, NT>;
-    const size_t smem = warp_smem_layout(a.W, a.Lcap).total;
+    auto kern = k_warp_rows<MODE, TMA, NT, F32>;
+    const size_t smem = warp_smem_layout(a.W, a.Lcap, F32 ? 4 : 2).total;
     CU_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = c->blocks_per_sm;
     if (occ <= 0) CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
@@ -486,11 +509,11 @@ int launch_warp_inst(vrsbs_ctx *c, const WarpArgs &a, cudaStream_t st) {
     return VRSBS_OK;
 }
 
-template <int MODE, bool TMA>
+template <int MODE, bool TMA, bool F32 = false>
 int launch_warp_nt(vrsbs_ctx *c, const WarpArgs &a, cudaStream_t st) {
-    if (a.W <= 2048) return launch_warp_inst<MODE, TMA, 256>(c, a, st);
-    if (a.W <= 4096) return launch_warp_inst<MODE, TMA, 512>(c, a, st);
-    return launch_warp_inst<MODE, TMA, 1024>(c, a, st);
+    if (a.W <= 2048) return launch_warp_inst<MODE, TMA, 256, F32>(c, a, st);
+    if (a.W <= 4096) return launch_warp_inst<MODE, TMA, 512, F32>(c, a, st);
+    return launch_warp_inst<MODE, TMA, 1024, F32>(c, a, st);
 }
 
 template <bool SMOOTH, int NT>
@@ -699,11 +722,23 @@ FusedArgs make_fused_args(vrsbs_ctx *c, Scratch &s, const uint8_t *frames, const
 }
 
 // staged route, stage 3: depth is the SMOOTHED depth left by launch_depth
-int launch_warp(vrsbs_ctx *c, Scratch &s, const uint8_t *frames, const __half *depth, int B, int H, int W, uint8_t *sbs,
+int launch_warp(vrsbs_ctx *c, Scratch &s, const uint8_t *frames, const void *depth_v, int B, int H, int W, uint8_t *sbs,
                 cudaStream_t st) {
     int rc = check_blur_ready(c, H, W);
     if (rc) return rc;
     if ((rc = fresh_hole_list(c, s, st))) return rc;
+    const __half *depth = static_cast<const __half *>(depth_v);
+    if (c->f32) {                                           // fp32 depth: the general row kernel, comparison in fp32
+        WarpArgs a{};
+        a.frames = frames; a.depth = depth_v; a.sbs = sbs; a.tabs = s.tabs; a.bounds = s.bounds; a.offm = s.offm;
+        a.hole_mask = s.hole_mask; a.B = B; a.H = H; a.W = W; a.Lcap = c->max_layers; a.Wwords = (W + 31) / 32;
+        a.hole_list = s.hole_list; a.hole_count = s.hole_count;
+        const bool tma = (W % 16 == 0) && ((uintptr_t)frames % 16 == 0) && ((uintptr_t)depth_v % 16 == 0) && ((uintptr_t)sbs % 16 == 0);
+        rc = tma ? launch_warp_nt<2, true, true>(c, a, st) : launch_warp_nt<2, false, true>(c, a, st);
+        if (rc) return rc;
+        if (!c->params.blur) return VRSBS_OK;
+        return launch_blur(c, s, frames, B, H, W, sbs, st);
+    }
     if (c->fused && fused_capable(c, frames, depth, sbs, W)) {
         FusedArgs a = make_fused_args(c, s, frames, depth, B, H, W, sbs);
         bool done = false;
@@ -862,7 +897,7 @@ int vrsbs_create(vrsbs_ctx **out, int device, int max_h, int max_w, int max_batc
     auto init = [&]() -> int {
         const size_t n = (size_t)max_h * max_w;
         for (int i = 0; i < 2; ++i)
-            for (int j = 0; j < 2; ++j) CU_TRY(c, dmalloc(&c->hist[i][j], n));
+            for (int j = 0; j < 2; ++j) CU_TRY(c, dmalloc(&c->hist[i][j], 2 * n));   // fp16 or fp32 raw depth
         CU_TRY(c, dmalloc(&c->state, 2));
         int rc = alloc_scratch(c, c->scratch[0], c->max_batch);
         if (rc) return rc;
@@ -901,7 +936,10 @@ int vrsbs_reset(vrsbs_ctx *c, const vrsbs_params *p) {
     DeviceGuard g(c->device);
     if (p) {
         if (p->offset_step_size < 1) return fail(c, VRSBS_E_INVALID, "offset_step_size must be >= 1");
+        if (p->depth_dtype != VRSBS_DEPTH_F16 && p->depth_dtype != VRSBS_DEPTH_F32) return fail(c, VRSBS_E_INVALID, "depth_dtype must be VRSBS_DEPTH_F16 or VRSBS_DEPTH_F32");
+        if (!c->inflight.empty()) return fail(c, VRSBS_E_STATE, "vrsbs_reset with submitted batches not yet collected");
         c->params = *p;
+        c->f32 = p->depth_dtype == VRSBS_DEPTH_F32;
     }
     // SbsProcessor.__init__: t = 0.3; sum += t; t *= 0.4 (twice); weight of the current frame = 1 - sum
     double t = 0.3, acc = 0.0, taps[2];
@@ -1065,8 +1103,7 @@ int vrsbs_depth_from_lowres(vrsbs_ctx *c, const void *lo, int B, int h, int w, f
     if (rc) return rc;
     if (!lo || !out || h < 1 || w < 1) return fail(c, VRSBS_E_INVALID, "bad low-res depth arguments");
     DeviceGuard g(c->device);
-    return launch_depth(c, c->scratch[0], nullptr, (const __half *)lo, B, H, W, h, w, scaler, (__half *)out,
-                        (cudaStream_t)stream);
+    return launch_depth(c, c->scratch[0], nullptr, (const __half *)lo, B, H, W, h, w, scaler, out, (cudaStream_t)stream);
 }
 
 int vrsbs_depth_from_full(vrsbs_ctx *c, const void *raw, int B, int H, int W, void *out, void *stream) {
@@ -1074,8 +1111,7 @@ int vrsbs_depth_from_full(vrsbs_ctx *c, const void *raw, int B, int H, int W, vo
     if (rc) return rc;
     if (!raw || !out) return fail(c, VRSBS_E_INVALID, "NULL depth pointer");
     DeviceGuard g(c->device);
-    return launch_depth(c, c->scratch[0], (const __half *)raw, nullptr, B, H, W, 0, 0, 1.f, (__half *)out,
-                        (cudaStream_t)stream);
+    return launch_depth(c, c->scratch[0], raw, nullptr, B, H, W, 0, 0, 1.f, out, (cudaStream_t)stream);
 }
 
 int vrsbs_build_tables(vrsbs_ctx *c, int B, int H, int W, void *stream) {
@@ -1090,7 +1126,7 @@ int vrsbs_warp_batch(vrsbs_ctx *c, const uint8_t *frames, const void *depth, int
     if (rc) return rc;
     if (!frames || !depth || !sbs) return fail(c, VRSBS_E_INVALID, "NULL buffer");
     DeviceGuard g(c->device);
-    return launch_warp(c, c->scratch[0], frames, (const __half *)depth, B, H, W, sbs, (cudaStream_t)stream);
+    return launch_warp(c, c->scratch[0], frames, depth, B, H, W, sbs, (cudaStream_t)stream);
 }
 
 int vrsbs_process_batch(vrsbs_ctx *c, const uint8_t *frames, const void *raw, int B, int H, int W, void *depth_scratch,
@@ -1102,12 +1138,12 @@ int vrsbs_process_batch(vrsbs_ctx *c, const uint8_t *frames, const void *raw, in
     cudaStream_t st = (cudaStream_t)stream;
     Scratch &s = c->scratch[0];
     fast_caps(c, H, W, &c->ent_cap, &c->lut_cap);
-    if (c->fused && c->smooth_in_warp && ((size_t)H * W) % 8 == 0 && fused_capable(c, frames, raw, sbs, W))
+    if (!c->f32 && c->fused && c->smooth_in_warp && ((size_t)H * W) % 8 == 0 && fused_capable(c, frames, raw, sbs, W))
         return launch_process_fused(c, s, frames, (const __half *)raw, B, H, W, sbs, st);
     if (!depth_scratch) return fail(c, VRSBS_E_INVALID, "depth_scratch_dev is required for this frame size / alignment");
-    if ((rc = launch_depth(c, s, (const __half *)raw, nullptr, B, H, W, 0, 0, 1.f, (__half *)depth_scratch, st))) return rc;
+    if ((rc = launch_depth(c, s, raw, nullptr, B, H, W, 0, 0, 1.f, depth_scratch, st))) return rc;
     if ((rc = launch_tables(c, s, B, H, W, st))) return rc;
-    return launch_warp(c, s, frames, (const __half *)depth_scratch, B, H, W, sbs, st);
+    return launch_warp(c, s, frames, depth_scratch, B, H, W, sbs, st);
 }
 
 int vrsbs_process_host(vrsbs_ctx *c, const uint8_t *frames, const void *depth, int B, int H, int W, int lh, int lw,
@@ -1130,7 +1166,7 @@ int vrsbs_process_host(vrsbs_ctx *c, const uint8_t *frames, const void *depth, i
     }
     int chunk = c->host_chunk < c->max_batch ? c->host_chunk : c->max_batch;
     if (chunk < 1) chunk = 1;
-    const size_t fb = (size_t)H * W * 3, sb = fb * 2, db = (size_t)H * W * 2;
+    const size_t fb = (size_t)H * W * 3, sb = fb * 2, db = (size_t)H * W * (c->f32 ? 4 : 2);
     const size_t dib = lowres ? (size_t)lh * lw * 2 : db;
     const size_t row3 = (size_t)W * 3;
     const bool direct = c->pageable_direct != 0;
@@ -1158,7 +1194,7 @@ int vrsbs_process_host(vrsbs_ctx *c, const uint8_t *frames, const void *depth, i
     CopyPool *pool = c->pool;
     fast_caps(c, H, W, &c->ent_cap, &c->lut_cap);
     if ((rc = check_blur_ready(c, H, W))) return rc;
-    const bool use_fused = !dev_d && !lowres && c->fused && c->smooth_in_warp && ((size_t)H * W) % 8 == 0 &&
+    const bool use_fused = !c->f32 && !dev_d && !lowres && c->fused && c->smooth_in_warp && ((size_t)H * W) % 8 == 0 &&
                            fused_capable(c, c->slot[0].dev_frames, c->slot[0].dev_depth_in, c->slot[0].dev_sbs, W);
 
     // Three streams: st_in copies chunk i+1 in while st_k runs the kernels of chunk i and st_out copies chunk i-1
@@ -1231,10 +1267,10 @@ int vrsbs_process_host(vrsbs_ctx *c, const uint8_t *frames, const void *depth, i
         if (use_fused) {
             rc = launch_process_fused(c, sc, s.dev_frames, din, n, H, W, s.dev_sbs, c->st_k);
         } else {
-            if (lowres) rc = launch_depth(c, sc, nullptr, din, n, H, W, lh, lw, scaler, (__half *)s.dev_depth, c->st_k);
-            else rc = launch_depth(c, sc, din, nullptr, n, H, W, 0, 0, 1.f, (__half *)s.dev_depth, c->st_k);
+            if (lowres) rc = launch_depth(c, sc, nullptr, din, n, H, W, lh, lw, scaler, s.dev_depth, c->st_k);
+            else rc = launch_depth(c, sc, din, nullptr, n, H, W, 0, 0, 1.f, s.dev_depth, c->st_k);
             if (!rc) rc = launch_tables(c, sc, n, H, W, c->st_k);
-            if (!rc) rc = launch_warp(c, sc, s.dev_frames, (const __half *)s.dev_depth, n, H, W, s.dev_sbs, c->st_k);
+            if (!rc) rc = launch_warp(c, sc, s.dev_frames, s.dev_depth, n, H, W, s.dev_sbs, c->st_k);
         }
         c->skip_right = 0;
         if (rc) return drain_all(rc);
@@ -1321,7 +1357,7 @@ int vrsbs_submit_host(vrsbs_ctx *c, const uint8_t *frames, size_t frame_row_pitc
     int rc = check_dims(c, 1, H, W);
     if (rc) return rc;
     if (!frames || !depth || !sbs) return fail(c, VRSBS_E_INVALID, "NULL buffer");
-    const size_t row3 = (size_t)W * 3, fb = (size_t)H * row3, sb = fb * 2, db = (size_t)H * W * 2;
+    const size_t row3 = (size_t)W * 3, fb = (size_t)H * row3, sb = fb * 2, db = (size_t)H * W * (c->f32 ? 4 : 2);
     if (!frame_row_pitch) frame_row_pitch = row3;
     if (!frame_pitch) frame_pitch = frame_row_pitch * H;
     if (frame_row_pitch < row3 || frame_pitch < frame_row_pitch * (size_t)(H - 1) + row3)
@@ -1395,10 +1431,10 @@ int vrsbs_submit_host(vrsbs_ctx *c, const uint8_t *frames, size_t frame_row_pitc
         CU_TRY_ABORT(cudaStreamWaitEvent(c->st_k, s.in_done, 0));
         Scratch &sc = c->scratch[si];
         c->skip_right = 1;                                 // the right half never leaves the host
-        if (lowres) rc = launch_depth(c, sc, nullptr, din, n, H, W, lh, lw, scaler, (__half *)s.dev_depth, c->st_k);
-        else rc = launch_depth(c, sc, din, nullptr, n, H, W, 0, 0, 1.f, (__half *)s.dev_depth, c->st_k);
+        if (lowres) rc = launch_depth(c, sc, nullptr, din, n, H, W, lh, lw, scaler, s.dev_depth, c->st_k);
+        else rc = launch_depth(c, sc, din, nullptr, n, H, W, 0, 0, 1.f, s.dev_depth, c->st_k);
         if (!rc) rc = launch_tables(c, sc, n, H, W, c->st_k);
-        if (!rc) rc = launch_warp(c, sc, s.dev_frames, (const __half *)s.dev_depth, n, H, W, s.dev_sbs, c->st_k);
+        if (!rc) rc = launch_warp(c, sc, s.dev_frames, s.dev_depth, n, H, W, s.dev_sbs, c->st_k);
         c->skip_right = 0;
         if (rc) return abort_inflight(c, rc);
         CU_TRY_ABORT(cudaMemcpyAsync(s.pin_tabs, sc.tabs, sizeof(FrameTab) * n, cudaMemcpyDeviceToHost, c->st_k));
@@ -1458,6 +1494,21 @@ int vrsbs_get_tables(vrsbs_ctx *c, int frame, int cap, double *cutoffs, int32_t 
     if (offsets) CU_TRY(c, cudaMemcpy(offsets, s.offsets + (size_t)frame * Lc, sizeof(int32_t) * L, cudaMemcpyDeviceToHost));
     if (lo) CU_TRY(c, cudaMemcpy(lo, s.lo16 + (size_t)frame * Lc, sizeof(uint16_t) * L, cudaMemcpyDeviceToHost));
     if (hi) CU_TRY(c, cudaMemcpy(hi, s.hi16 + (size_t)frame * Lc, sizeof(uint16_t) * L, cudaMemcpyDeviceToHost));
+    return L;
+}
+
+int vrsbs_get_bounds(vrsbs_ctx *c, int frame, int cap, float *lo, float *hi, void *stream) {
+    if (!c || frame < 0 || frame >= c->max_batch || !lo || !hi) return fail(c, VRSBS_E_INVALID, "bad arguments");
+    DeviceGuard g(c->device);
+    CU_TRY(c, cudaStreamSynchronize((cudaStream_t)stream));
+    FrameTab t;
+    Scratch &s = c->scratch[0];
+    CU_TRY(c, cudaMemcpy(&t, s.tabs + frame, sizeof t, cudaMemcpyDeviceToHost));
+    const int L = t.layers;
+    if (cap < L) return fail(c, VRSBS_E_INVALID, "capacity %d < L = %d", cap, L);
+    std::vector<float2> b(L);
+    CU_TRY(c, cudaMemcpy(b.data(), s.bounds + (size_t)frame * c->max_layers, sizeof(float2) * L, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < L; ++k) { lo[k] = b[k].x; hi[k] = b[k].y; }
     return L;
 }
 

@@ -22,13 +22,15 @@
 //      straight from the staged input (never touched by a thread).
 // Lanes own interleaved pixels (x = 32*segment + lane) so that key traffic is bank-conflict free.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace vrsbs {
 
 struct WarpArgs {
     const uint8_t *frames;     // [B,H,W,3]
-    const __half *depth;       // [B,H,W] smoothed
+    const void *depth;         // [B,H,W] smoothed, fp16 (F32 = false) or fp32
     uint8_t *sbs;              // [B,H,2W,3]
     FrameTab *tabs;            // [B]
     const float2 *bounds;      // [B][Lcap]
@@ -44,11 +46,11 @@ constexpr int kMaxSeg = 8;     // 32-pixel segments per warp per row (bounds reg
 struct WarpSmem {
     size_t img[2], dep[2], out[2], keys, bounds, offm, bars, total;
 };
-__host__ __device__ inline WarpSmem warp_smem_layout(int W, int Lcap) {
+__host__ __device__ inline WarpSmem warp_smem_layout(int W, int Lcap, int depth_bytes = 2) {
     WarpSmem s;
     size_t o = 0;
     for (int i = 0; i < 2; ++i) { s.img[i] = o; o += align_up((size_t)W * 3 + 16, 128); }
-    for (int i = 0; i < 2; ++i) { s.dep[i] = o; o += align_up((size_t)W * 2, 128); }
+    for (int i = 0; i < 2; ++i) { s.dep[i] = o; o += align_up((size_t)W * depth_bytes, 128); }
     for (int i = 0; i < 2; ++i) { s.out[i] = o; o += align_up((size_t)W * 3 + 16, 128); }
     s.keys = o;   o += align_up((size_t)W * 4, 128);
     s.bounds = o; o += align_up((size_t)Lcap * 8, 16);
@@ -58,14 +60,16 @@ __host__ __device__ inline WarpSmem warp_smem_layout(int W, int Lcap) {
     return s;
 }
 
-template <int MODE, bool TMA, int NT>
+template <int MODE, bool TMA, int NT, bool F32 = false>
 __global__ void __launch_bounds__(NT) k_warp_rows(WarpArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const WarpSmem lay = warp_smem_layout(a.W, a.Lcap);
+    using DT = typename std::conditional<F32, float, __half>::type;
+    const WarpSmem lay = warp_smem_layout(a.W, a.Lcap, (int)sizeof(DT));
+    const DT *a_depth = static_cast<const DT *>(a.depth);
     // stage s of a double-buffered array lives at base + s * stride (no pointer arrays: keeps them out of local memory)
     const size_t img_stride = lay.img[1] - lay.img[0], dep_stride = lay.dep[1] - lay.dep[0], out_stride = lay.out[1] - lay.out[0];
     auto img_at = [&](int s) { return smem + lay.img[0] + s * img_stride; };
-    auto dep_at = [&](int s) { return reinterpret_cast<__half *>(smem + lay.dep[0] + s * dep_stride); };
+    auto dep_at = [&](int s) { return reinterpret_cast<DT *>(smem + lay.dep[0] + s * dep_stride); };
     auto out_at = [&](int s) { return smem + lay.out[0] + s * out_stride; };
     uint32_t *keys = reinterpret_cast<uint32_t *>(smem + lay.keys);
     float2 *bnd = reinterpret_cast<float2 *>(smem + lay.bounds);
@@ -76,7 +80,7 @@ __global__ void __launch_bounds__(NT) k_warp_rows(WarpArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = a.W, H = a.H;
     const long long total_rows = (long long)a.B * H;
-    const uint32_t img_bytes = (uint32_t)W * 3, dep_bytes = (uint32_t)W * 2;
+    const uint32_t img_bytes = (uint32_t)W * 3, dep_bytes = (uint32_t)W * (uint32_t)sizeof(DT);
     const int nseg = (W + 31) >> 5;
 
     if (TMA && tid == 0) {
@@ -89,7 +93,7 @@ __global__ void __launch_bounds__(NT) k_warp_rows(WarpArgs a) {
     auto issue_load = [&](long long row, int s) {           // thread 0 only
         mbar_expect_tx(&full[s], img_bytes + dep_bytes);
         bulk_g2s(img_at(s), a.frames + (size_t)row * img_bytes, img_bytes, &full[s]);
-        bulk_g2s(dep_at(s), a.depth + (size_t)row * W, dep_bytes, &full[s]);
+        bulk_g2s(dep_at(s), a_depth + (size_t)row * W, dep_bytes, &full[s]);
     };
 
     long long row = blockIdx.x;
@@ -112,9 +116,9 @@ __global__ void __launch_bounds__(NT) k_warp_rows(WarpArgs a) {
         } else {
             // generic path (W*3 or pointers not 16-byte aligned): cooperative byte copies
             const uint8_t *gi = a.frames + (size_t)row * img_bytes;
-            const __half *gd = a.depth + (size_t)row * W;
+            const DT *gd = a_depth + (size_t)row * W;
             uint8_t *si = img_at(s);
-            __half *sd = dep_at(s);
+            DT *sd = dep_at(s);
             for (int i = tid; i < (int)img_bytes; i += NT) si[i] = gi[i];
             for (int i = tid; i < W; i += NT) sd[i] = gd[i];
         }
@@ -141,7 +145,7 @@ __global__ void __launch_bounds__(NT) k_warp_rows(WarpArgs a) {
         if (TMA) mbar_wait(&full[s], (it >> 1) & 1);
         __syncthreads();
 
-        const __half *dep = dep_at(s);
+        const DT *dep = dep_at(s);
         uint32_t memb[kMaxSeg];                              // (ktop+1) | count<<16 per owned source pixel
 
         // ---- scatter --------------------------------------------------------------------------------
@@ -150,7 +154,8 @@ __global__ void __launch_bounds__(NT) k_warp_rows(WarpArgs a) {
             const int x = ((warp + NW * i) << 5) + lane;
             memb[i] = 0;
             if (x < W) {
-                const float d = h2f(dep[x]);
+                float d;
+                if constexpr (F32) d = dep[x]; else d = h2f(dep[x]);
                 if (!generic) {
                     int k = min(max((int)floorf(fmaf(d, gscale, gbias)), 0), L - 1);
                     while (k + 1 < L && bnd[k + 1].x <= d) ++k;

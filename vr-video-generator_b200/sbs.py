@@ -18,7 +18,7 @@ DEFAULT_MAX_LAYERS = 512
 
 class SbsProcessor:
     def __init__(self, gpu_notify_queue, gpu_notify_worker_idx, args_god, debug_config=[None],
-                 device=None, max_batch=64, max_layers=DEFAULT_MAX_LAYERS):
+                 device=None, max_batch=64, max_layers=DEFAULT_MAX_LAYERS, depth_dtype=None):
         self.debug_filePrefix = debug_config[0]
         self.gpu_notify_queue = gpu_notify_queue
         self.gpu_notify_worker_idx = gpu_notify_worker_idx
@@ -40,19 +40,38 @@ class SbsProcessor:
         self._ctx = None
         self._shape = None          # (H, W) the context was created for
         self._blur = True
+        self._ctx_f32 = False
+        # Element type of the full-resolution depth of this clip range.  The reference is dtype-agnostic (smoothing, max and
+        # bin comparison run in the tensor's dtype): fp16 is what autocast produced under the reference's pinned torch,
+        # torch >= 2.4 on CUDA hands over fp32 (upsample_bicubic2d is on autocast's fp32 list).  None = taken from the
+        # first full-resolution depth seen (fp16 when only DPT-resolution maps are given).
+        self._f32 = None if depth_dtype is None else _is_f32(depth_dtype)
         self._inflight = {}         # ticket -> arrays of a submitted batch (kept alive until collected)
         self._depth_pool = []       # recycled page-locked staging buffers for host depth given to submit_batch
 
     # ------------------------------------------------------------------------------------------
-    def _context(self, H, W):
+    def _context(self, H, W, f32=None):
+        """The native context for (H, W) and the clip's depth dtype; a new size or dtype starts a new context (and, like a
+        new reference SbsProcessor, a fresh clip state)."""
+        if f32 is not None and self._f32 is None:
+            self._f32 = bool(f32)
+        elif f32 is not None and bool(f32) != self._f32:
+            self._f32 = bool(f32)
+            self.close()
         if self._ctx is None or self._shape != (H, W):
             if self._ctx is not None:
                 self._ctx.close()
             self._ctx = _native.Context(self.device.index, H, W, self.max_batch, self.max_layers)
-            self._ctx.reset(self.offset_fg, self.offset_bg, self.offset_step_size, self._blur)
+            self._ctx_f32 = bool(self._f32)
+            self._ctx.reset(self.offset_fg, self.offset_bg, self.offset_step_size, self._blur,
+                            _native.DEPTH_F32 if self._ctx_f32 else _native.DEPTH_F16)
             kx, ky = tables.blur_kernel_shape(H)
             self._ctx.set_blur_weights(tables.gaussian_weights(kx, ky, float(self.sigmaboi)))
             self._shape = (H, W)
+        elif bool(self._f32) != self._ctx_f32:              # dtype became known after the context was made
+            self._ctx_f32 = bool(self._f32)
+            self._ctx.reset(self.offset_fg, self.offset_bg, self.offset_step_size, self._blur,
+                            _native.DEPTH_F32 if self._ctx_f32 else _native.DEPTH_F16)
         return self._ctx
 
     def _stream(self):
@@ -66,7 +85,8 @@ class SbsProcessor:
     def reset_state(self):
         """Forget depth history and range EMA (what a new reference SbsProcessor starts with)."""
         if self._ctx is not None:
-            self._ctx.reset(self.offset_fg, self.offset_bg, self.offset_step_size, self._blur)
+            self._ctx.reset(self.offset_fg, self.offset_bg, self.offset_step_size, self._blur,
+                            _native.DEPTH_F32 if self._ctx_f32 else _native.DEPTH_F16)
 
     @property
     def last_offset_range(self):
@@ -105,12 +125,11 @@ class SbsProcessor:
         :55-56): that case goes through the host pipeline (pinned staging, only the synthesised half crosses PCIe
         on the way back).  A CUDA depth tensor is used where it is."""
         H, W, _ = raw_img.shape
-        ctx = self._context(H, W)
         raw = result_queue.get()
         if not (isinstance(raw, torch.Tensor) and raw.is_cuda):
             d = _as_numpy(raw)
-            if d.dtype != np.float16:
-                raise TypeError(f"depth must be float16 (the producer's autocast dtype), got {d.dtype}")
+            _check_depth_dtype(d.dtype)
+            ctx = self._context(H, W, d.dtype == np.float32)
             if d.shape != (H, W):
                 raise ValueError(f"depth {d.shape} does not match the frame {(H, W)}")
             out = np.empty((H, 2 * W, 3), dtype=np.uint8)
@@ -120,6 +139,7 @@ class SbsProcessor:
         with torch.cuda.device(self.device):
             img = torch.from_numpy(np.ascontiguousarray(raw_img)).to(self.device, non_blocking=True)
             depth = self._smooth(self._raw_to_device(raw))
+            ctx = self._ctx
             st = self._stream()
             ctx.build_tables(1, H, W, st)
             sbs = torch.empty((1, H, 2 * W, 3), dtype=torch.uint8, device=self.device)
@@ -136,7 +156,7 @@ class SbsProcessor:
         the device).  Returns numpy [B,H,2W,3].  Pipelined (pinned double buffering)."""
         f = _as_numpy(frames)
         B, H, W, _ = f.shape
-        ctx = self._context(H, W)
+        ctx = self._context(H, W, _full_res_f32(depths, H, W))
         dshape, dptr, _keep = self._depth_arg(ctx, depths, B)
         lowres = tuple(dshape[1:]) != (H, W)
         if out is None:
@@ -157,13 +177,13 @@ class SbsProcessor:
             raise ValueError("out must be a C-contiguous uint8 [B,H,2W,3] array")
         if frames.dtype != np.uint8 or frames.strides[2:] != (3, 1):
             raise ValueError("frames must be uint8 with packed pixels and rows")
-        ctx = self._context(H, W)
+        ctx = self._context(H, W, _full_res_f32(depths, H, W))
         dshape, dptr, keep = self._depth_arg(ctx, depths, B)
         staged = None
         if not (isinstance(depths, torch.Tensor) and (depths.is_cuda or depths.is_pinned())):
             # pageable host depth (what a result queue delivers): one copy into a recycled page-locked buffer
             staged = self._pinned_depth(keep.nbytes)
-            view = staged.numpy()[:keep.nbytes].view(np.float16).reshape(keep.shape)
+            view = staged.numpy()[:keep.nbytes].view(keep.dtype).reshape(keep.shape)
             np.copyto(view, keep)
             dptr, keep = view.ctypes.data, (staged, view)
         lowres = tuple(dshape[1:]) != (H, W)
@@ -195,13 +215,13 @@ class SbsProcessor:
         if isinstance(depths, torch.Tensor) and depths.is_cuda:
             # the depth producer's output is still on the device (same process): used where it is, no H2D of depth; the
             # library's kernels are ordered behind the producer's stream by an event (the host does not wait)
-            _check_cuda(depths, torch.float16)
+            _check_depth_dtype(depths.dtype)
+            _check_cuda(depths, depths.dtype)
             ctx.host_depends_on(torch.cuda.current_stream(depths.device).cuda_stream)
             dshape, dptr, keep = tuple(depths.shape), depths.data_ptr(), depths
         else:
             d = _as_numpy(depths)
-            if d.dtype != np.float16:
-                raise TypeError(f"depth must be float16 (the producer's autocast dtype), got {d.dtype}")
+            _check_depth_dtype(d.dtype)
             dshape, dptr, keep = d.shape, d.ctypes.data, d
         if len(dshape) != 3 or dshape[0] != B:
             raise ValueError(f"depth {dshape} does not match {B} frames")
@@ -211,12 +231,13 @@ class SbsProcessor:
         """Device-resident batch on the current stream, asynchronous: frames [B,H,W,3] uint8 CUDA,
         raw_depth [B,H,W] fp16 CUDA (raw, full-res) -> sbs [B,H,2W,3] uint8 CUDA."""
         B, H, W, _ = frames.shape
-        ctx = self._context(H, W)
+        _check_depth_dtype(raw_depth.dtype)
+        ctx = self._context(H, W, raw_depth.dtype == torch.float32)
         if out is None:
             out = torch.empty((B, H, 2 * W, 3), dtype=torch.uint8, device=self.device)
         if depth_scratch is None:
-            depth_scratch = torch.empty((B, H, W), dtype=torch.float16, device=self.device)
-        _check_cuda(frames, torch.uint8), _check_cuda(raw_depth, torch.float16)
+            depth_scratch = torch.empty((B, H, W), dtype=raw_depth.dtype, device=self.device)
+        _check_cuda(frames, torch.uint8), _check_cuda(raw_depth, raw_depth.dtype)
         ctx.process_batch(frames.data_ptr(), raw_depth.data_ptr(), B, H, W, depth_scratch.data_ptr(),
                           out.data_ptr(), self._stream())
         return out
@@ -225,8 +246,7 @@ class SbsProcessor:
     def _raw_to_device(self, raw):
         if isinstance(raw, np.ndarray):
             raw = torch.from_numpy(raw)
-        if raw.dtype != torch.float16:
-            raise TypeError(f"depth must be float16 (the producer's autocast dtype), got {raw.dtype}")
+        _check_depth_dtype(raw.dtype)
         return raw.to(self.device, non_blocking=True).contiguous()
 
     def _smooth(self, raw_dev):
@@ -234,7 +254,7 @@ class SbsProcessor:
         if raw_dev.dim() == 2:
             raw_dev = raw_dev[None]
         B, H, W = raw_dev.shape
-        ctx = self._context(H, W)
+        ctx = self._context(H, W, raw_dev.dtype == torch.float32)
         out = torch.empty_like(raw_dev)
         ctx.depth_from_full(raw_dev.data_ptr(), B, H, W, out.data_ptr(), self._stream())
         return out
@@ -255,6 +275,27 @@ def _as_numpy(x):
     if isinstance(x, torch.Tensor):
         x = x.numpy()
     return np.ascontiguousarray(x)
+
+
+def _is_f32(dt):
+    return str(dt).replace("torch.", "") in ("float32", "<class 'numpy.float32'>") or dt in (np.float32, torch.float32)
+
+
+def _check_depth_dtype(dt):
+    if not (dt in (np.float16, np.float32, torch.float16, torch.float32)):
+        raise TypeError(f"depth must be float16 or float32 (what the producer's autocast hands over), got {dt}")
+
+
+def _full_res_f32(depths, H, W):
+    """True / False when `depths` is a full-resolution map (its dtype is the clip's depth dtype), None for a
+    DPT-resolution map (always fp16; the clip's dtype then decides what the device tail produces)."""
+    shape = tuple(depths.shape)
+    if len(shape) == 3 and shape[1:] == (H, W):
+        return _is_f32(depths.dtype)
+    if True:
+        if depths.dtype not in (np.float16, torch.float16):
+            raise TypeError(f"a DPT-resolution depth map must be float16 (the model's autocast output), got {depths.dtype}")
+    return None
 
 
 def _check_cuda(t, dtype):

@@ -171,7 +171,8 @@ def sbs_worker(begin, end, read_frame, depth_for, write_subclip, args_god, video
     (`SbsProcessor.submit_batch`: H2D, kernels, D2H of the synthesised halves only), and a writer thread hands the
     finished sub-clip k to `write_subclip`.  `ring` buffers of Max_Frame_Count + 1 frames circulate between the three.
     pipelined=False is the serial loop (read all, warp, write), kept for comparison and for pageable-only callers.
-    `stats`, if a dict, receives wall-clock seconds spent reading / waiting for the GPU / writing and `overlap`."""
+    `stats`, if a dict, receives wall-clock seconds spent reading / in the depth producer / waiting for the GPU / writing,
+    `overlap` (their sum over the wall clock: > 1 means the stages ran concurrently) and the busy `intervals`."""
     from .sbs import SbsProcessor
     stop = min(end, video_length)
     own = processor is None
@@ -282,7 +283,7 @@ def _worker_pipelined(begin, end, read_frame, depth_for, write_subclip, args_god
 
     th_r, th_w = threading.Thread(target=reader, daemon=True), threading.Thread(target=writer, daemon=True)
     th_r.start(), th_w.start()
-    names, prev, t_gpu = [], None, 0.0
+    names, prev, t_gpu, t_depth = [], None, 0.0, 0.0
     t_begin = time.perf_counter()
     try:
         while True:
@@ -292,7 +293,13 @@ def _worker_pipelined(begin, end, read_frame, depth_for, write_subclip, args_god
                 out, view, _ = bufs[k]
                 ticket = None
                 if n:
-                    ticket = processor.submit_batch(view[:n], depth_for(view[:n]), out[:n], scaler=scaler)
+                    t0 = time.perf_counter()
+                    depth = depth_for(view[:n])                               # the depth producer (timed separately)
+                    t1 = time.perf_counter()
+                    ticket = processor.submit_batch(view[:n], depth, out[:n], scaler=scaler)
+                    t_depth += t1 - t0
+                    busy.append(("depth", t0, t1))
+                    busy.append(("submit", t1, time.perf_counter()))
             if prev is not None:                                              # sub-clip k-1 finishes while k is on the GPU
                 pk, pn, pname, pticket = prev
                 t0 = time.perf_counter()
@@ -320,8 +327,8 @@ def _worker_pipelined(begin, end, read_frame, depth_for, write_subclip, args_god
         raise errors[0]
     if stats is not None:
         wall = time.perf_counter() - t_begin
-        stats.update(read_s=t_read[0], write_s=t_write[0], gpu_wait_s=t_gpu, wall_s=wall,
-                     overlap=(t_read[0] + t_write[0] + t_gpu) / max(wall, 1e-9), intervals=list(busy))
+        stats.update(read_s=t_read[0], write_s=t_write[0], gpu_wait_s=t_gpu, depth_s=t_depth, wall_s=wall,
+                     overlap=(t_read[0] + t_write[0] + t_gpu + t_depth) / max(wall, 1e-9), intervals=list(busy))
     return names
 
 
