@@ -149,7 +149,8 @@ def test_fp32_depth_through_the_dropin_and_the_host_pipeline(oracle_lib):
     p = meta["params"]
     H, W, n = p["H"], p["W"], p["n"]
     args = argparse.Namespace(offset_fg=p["fg"], offset_bg=p["bg"], offset_step_size=p["step"])
-    proc = pkg.SbsProcessor(None, 0, args, max_batch=2)
+    proc = pkg.SbsProcessor(None, 0, args, max_batch=4)
+    proc._context(H, W, True).set_option("host_chunk", 2)
     q = queue.Queue()
     for t in range(n):
         q.put(torch.from_numpy(raw[t]))
