@@ -440,27 +440,32 @@ __host__ __device__ constexpr int blur_sep_vcols() {
 template <int CX>
 __host__ __device__ constexpr size_t blur_sep_warp_smem() { return (size_t)kBlurSepGroup * (blur_sep_vcols<CX>() + 16) * sizeof(uint32_t); }
 
-// exact blurred value of one (pixel, channel) from global memory: the rare path behind the separable screening
-template <int PARTS>
-__device__ __noinline__ uint32_t blur_exact_global(const uint8_t *left, size_t pitch, int H, int W, int y, int x, int ch,
-                                                   const uint32_t *wq, int cx, int cy, int S) {
+// exact blurred value of one (pixel, channel) from global memory: the rare path behind the separable screening.
+// The WHOLE WARP evaluates one undecided value: the ky * kx taps are dealt out over the lanes and the PARTS partial sums
+// are added across the warp (their totals fit 32 bits for the same reason the single-thread accumulators of
+// k_blur_holes do).  One undecided lane used to walk all taps alone while 31 lanes waited: 1.2 % of the task passes of
+// a 4K frame contain such a lane, and those passes were 27 % of the kernel's executed instructions (profiles r02a_4k).
+template <int PARTS, int CX, int CY>
+__device__ __noinline__ uint32_t blur_exact_warp(const uint8_t *left, size_t pitch, int H, int W, int y, int x, int ch,
+                                                 const uint32_t *wq, int S) {
     constexpr int PBITS = PARTS == 2 ? 15 : 13;
+    constexpr int KX = 2 * CX + 1, KY = 2 * CY + 1, NTAP = KX * KY, NU = (CY + 1) * (CX + 1);
+    const int lane = threadIdx.x & 31;
     uint32_t acc[PARTS];
 #pragma unroll
     for (int p = 0; p < PARTS; ++p) acc[p] = 0u;
-    const int nw = (cy + 1) * (cx + 1);
-    for (int i = -cy; i <= cy; ++i) {
-        const uint8_t *rowp = left + (size_t)reflect_idx(y + i, H) * pitch + ch;
-        const uint32_t *wr = wq + (i < 0 ? -i : i) * (cx + 1);
-        for (int j = -cx; j <= cx; ++j) {
-            const uint32_t v = rowp[(size_t)min(max(reflect_idx(x + j, W), 0), W - 1) * 3];
+    for (int t = lane; t < NTAP; t += 32) {
+        const int i = t / KX, j = t - i * KX;
+        const int di = i - CY, dj = j - CX;
+        const int yy = reflect_idx(y + di, H), xx = min(max(reflect_idx(x + dj, W), 0), W - 1);
+        const uint32_t v = left[(size_t)yy * pitch + (size_t)xx * 3 + ch];
+        const int wi = (di < 0 ? -di : di) * (CX + 1) + (dj < 0 ? -dj : dj);
 #pragma unroll
-            for (int p = 0; p < PARTS; ++p) acc[p] += v * __ldg(wr + p * nw + (j < 0 ? -j : j));
-        }
+        for (int p = 0; p < PARTS; ++p) acc[p] += v * __ldg(wq + p * NU + wi);
     }
     unsigned long long total = 0ull;
 #pragma unroll
-    for (int p = PARTS - 1; p >= 0; --p) total = (total << PBITS) + acc[p];
+    for (int p = PARTS - 1; p >= 0; --p) total = (total << PBITS) + __reduce_add_sync(0xffffffffu, acc[p]);
     unsigned long long q = total >> S;
     const unsigned long long r = total & ((1ull << S) - 1ull), half = 1ull << (S - 1);
     q += (r > half || (r == half && (q & 1ull))) ? 1ull : 0ull;
@@ -474,10 +479,9 @@ __global__ void __launch_bounds__(256, 4) k_blur_sep(BlurArgs a, const __grid_co
     constexpr int NWORDS = (PHASE + 3 * NPX + 3) / 4;                 // aligned 32-bit words that cover the footprint
     constexpr int VCOLS = NWORDS * 4;
     constexpr int G = kBlurSepGroup;
-    constexpr int TAILW = NWORDS > 32 ? NWORDS - 32 : 0;              // words past the 32nd (wide footprints)
     static_assert(NWORDS <= 64 && VCOLS == blur_sep_vcols<CX>(), "footprint layout");
     extern __shared__ __align__(16) uint8_t blur_smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int W = a.W, H = a.H;
     uint32_t *Vw = reinterpret_cast<uint32_t *>(blur_smem) + (size_t)warp * (G * (VCOLS + 16));
     uint16_t *tasktab = reinterpret_cast<uint16_t *>(Vw + G * VCOLS);  // [G * 32]: (entry << 8 | pixel) of every hole of the group
@@ -564,48 +568,67 @@ __global__ void __launch_bounds__(256, 4) k_blur_sep(BlurArgs a, const __grid_co
         fetch_meta(t_a * G, ent_n, m_n);
         t_b_raw = grab();
         __syncwarp();
-        // ---- stage: hole table + V columns of up to G entries ----
-        uint32_t nholes = 0, border = 0, live = 0;
+        // ---- stage: hole table of up to G entries; border entries byte by byte ----
+        uint32_t nholes = 0, border = 0;
 #pragma unroll 2
         for (int g = 0; g < G; ++g) {
             const uint32_t ent = __shfl_sync(0xffffffffu, ent_c, g), m = __shfl_sync(0xffffffffu, m_c, g);
             if (m == 0u) continue;
-            live |= 1u << g;
-            int b, y, xw;
-            decode(ent, b, y, xw);
             if ((m >> lane) & 1u) tasktab[nholes + __popc(m & ((1u << lane) - 1u))] = (uint16_t)((g << 8) | lane);
             nholes += (uint32_t)__popc(m);
+            const int xw = (int)(ent & 0xffu) * 32;
+            if (xw - CX >= 0 && xw + 31 + CX < W) continue;
+            // border words: byte by byte with reflect padding (phase 0)
+            border |= 1u << g;
+            int b, y, xw_;
+            decode(ent, b, y, xw_);
             const uint8_t *left = a.sbs + (size_t)b * H * pitch;
             uint32_t *V = Vw + g * VCOLS;
-            if (xw - CX >= 0 && xw + 31 + CX < W) {
-                if (NWORDS >= 32 || lane < NWORDS) stage_word(V + 4 * lane, left + (3 * (xw - CX) - PHASE) + 4 * lane, y);
-            } else {
-                // border words: byte by byte with reflect padding (phase 0)
-                border |= 1u << g;
-                for (int c = lane; c < 3 * NPX; c += 32) {
-                    const int px = c / 3, ch = c - px * 3;
-                    const int X = min(max(reflect_idx(xw - CX + px, W), 0), W - 1);
-                    const uint8_t *colp = left + (size_t)X * 3 + ch;
-                    uint32_t acc = (uint32_t)colp[(size_t)y * pitch] * wts.hy[0];
+            for (int c = lane; c < 3 * NPX; c += 32) {
+                const int px = c / 3, ch = c - px * 3;
+                const int X = min(max(reflect_idx(xw - CX + px, W), 0), W - 1);
+                const uint8_t *colp = left + (size_t)X * 3 + ch;
+                uint32_t acc = (uint32_t)colp[(size_t)y * pitch] * wts.hy[0];
 #pragma unroll
-                    for (int i = 1; i <= CY; ++i)
-                        acc += ((uint32_t)colp[(size_t)reflect_idx(y - i, H) * pitch] + (uint32_t)colp[(size_t)reflect_idx(y + i, H) * pitch]) * wts.hy[i];
-                    V[c] = acc;
-                }
+                for (int i = 1; i <= CY; ++i)
+                    acc += ((uint32_t)colp[(size_t)reflect_idx(y - i, H) * pitch] + (uint32_t)colp[(size_t)reflect_idx(y + i, H) * pitch]) * wts.hy[i];
+                V[c] = acc;
             }
         }
-        if (TAILW > 0) {
-            // words past the 32nd of the interior entries: lane = (entry, tail word), several entries per pass
-            constexpr int EPP = TAILW > 0 ? 32 / (TAILW > 0 ? TAILW : 1) : 1;   // entries per pass
+        // ---- stage: V columns of the interior entries.  Only the aligned words a hole's taps can reach are built: the
+        // holes of a word sit in bits lo..hi, their taps in footprint bytes PHASE + 3 lo .. PHASE + 3 (hi + 2 CX) + 2.  A
+        // listed word holds 5 holes on average at 1080p (a third of the footprint is needed); the (entry, word) tasks of
+        // the whole group are dealt out 32 at a time, so sparse entries share a pass.
+        {
+            uint32_t wlo = 0, cnt = 0;
+            if (lane < G && m_c != 0u && !((border >> lane) & 1u)) {
+                const int lo = __ffs((int)m_c) - 1, hi = 31 - __clz((int)m_c);
+                wlo = (uint32_t)(PHASE + 3 * lo) >> 2;
+                cnt = ((uint32_t)(PHASE + 3 * (hi + 2 * CX) + 2) >> 2) - wlo + 1u;
+            }
+            uint32_t incl = cnt;                                         // inclusive prefix sum over lanes 0 .. G-1
 #pragma unroll
-            for (int gb = 0; gb < G; gb += EPP) {
-                const int tg = gb + lane / (TAILW > 0 ? TAILW : 1), tw = lane % (TAILW > 0 ? TAILW : 1);
-                const uint32_t ent = __shfl_sync(0xffffffffu, ent_c, tg & 31);
-                const bool on = tg < G && tg < gb + EPP && ((live & ~border) >> tg) & 1u;
-                if (on) {
+            for (int d = 1; d < G; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, G - 1);
+            const uint32_t excl = incl - cnt;
+            for (uint32_t base = 0; base < total; base += 32) {
+                const uint32_t task = base + lane;
+                int g = 0;                                               // number of entries that end at or before this task
+#pragma unroll
+                for (int step = G / 2; step >= 1; step >>= 1) {
+                    const uint32_t probe = __shfl_sync(0xffffffffu, incl, g + step - 1);
+                    if (probe <= task) g += step;
+                }
+                g = min(g, G - 1);
+                const uint32_t ent = __shfl_sync(0xffffffffu, ent_c, g);
+                const uint32_t k = task - __shfl_sync(0xffffffffu, excl, g) + __shfl_sync(0xffffffffu, wlo, g);
+                if (task < total) {
                     int b, y, xw;
                     decode(ent, b, y, xw);
-                    stage_word(Vw + tg * VCOLS + 4 * (32 + tw), a.sbs + (size_t)b * H * pitch + (3 * (xw - CX) - PHASE) + 4 * (32 + tw), y);
+                    stage_word(Vw + g * VCOLS + 4 * k, a.sbs + (size_t)b * H * pitch + (3 * (xw - CX) - PHASE) + 4 * (int)k, y);
                 }
             }
         }
@@ -619,20 +642,29 @@ __global__ void __launch_bounds__(256, 4) k_blur_sep(BlurArgs a, const __grid_co
             const uint32_t code = tasktab[hidx];
             const uint32_t g = code >> 8, xo = code & 0xffu;
             const uint32_t ent = __shfl_sync(0xffffffffu, ent_c, g);
-            if (!on) continue;
-            const uint32_t phase = ((border >> g) & 1u) ? 0u : (uint32_t)PHASE;
-            const uint32_t *Vc = Vw + g * VCOLS + phase + 3u * (xo + CX) + ch;
-            unsigned long long acc = (unsigned long long)Vc[0] * wts.hx[0];
+            uint32_t q = 0u;
+            bool open = false;
+            if (on) {
+                const uint32_t phase = ((border >> g) & 1u) ? 0u : (uint32_t)PHASE;
+                const uint32_t *Vc = Vw + g * VCOLS + phase + 3u * (xo + CX) + ch;
+                unsigned long long acc = (unsigned long long)Vc[0] * wts.hx[0];
 #pragma unroll
-            for (int j = 1; j <= CX; ++j) acc += (unsigned long long)(Vc[-3 * j] + Vc[3 * j]) * wts.hx[j];
-            const uint32_t r32 = (uint32_t)(acc >> (wts.s - 32u));                 // top 32 bits of the fractional part
-            uint32_t q = (uint32_t)(acc >> wts.s) + (r32 >> 31);
-            const uint32_t row = ent >> 8, xw = (ent & 0xffu) * 32u;
-            if (r32 - 0x80000000u + wts.eps32 <= 2u * wts.eps32) {                  // within eps of a half-integer: exact sum decides
-                int b, y, xw_;
-                decode(ent, b, y, xw_);
-                q = blur_exact_global<PARTS>(a.sbs + (size_t)b * H * pitch, pitch, H, W, y, (int)(xw + xo), (int)ch, a.wq, CX, CY, a.wshift);
+                for (int j = 1; j <= CX; ++j) acc += (unsigned long long)(Vc[-3 * j] + Vc[3 * j]) * wts.hx[j];
+                const uint32_t r32 = (uint32_t)(acc >> (wts.s - 32u));             // top 32 bits of the fractional part
+                q = (uint32_t)(acc >> wts.s) + (r32 >> 31);
+                open = r32 - 0x80000000u + wts.eps32 <= 2u * wts.eps32;            // within eps of a half-integer: exact sum decides
             }
+            // undecided values, one at a time, by the whole warp
+            for (unsigned need = __ballot_sync(0xffffffffu, open); need; need &= need - 1u) {
+                const int src = __ffs(need) - 1;
+                const uint32_t e_s = __shfl_sync(0xffffffffu, ent, src), x_s = __shfl_sync(0xffffffffu, xo, src), c_s = __shfl_sync(0xffffffffu, ch, src);
+                int b, y, xw_;
+                decode(e_s, b, y, xw_);
+                const uint32_t qx = blur_exact_warp<PARTS, CX, CY>(a.sbs + (size_t)b * H * pitch, pitch, H, W, y, xw_ + (int)x_s, (int)c_s, a.wq, a.wshift);
+                if (lane == src) q = qx;
+            }
+            if (!on) continue;
+            const uint32_t row = ent >> 8, xw = (ent & 0xffu) * 32u;
             a.plane[((size_t)row * W + xw + xo) * 3 + ch] = (uint8_t)q;
         }
     }

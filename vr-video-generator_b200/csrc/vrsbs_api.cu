@@ -90,7 +90,6 @@ public:
         cv_.notify_all();
         for (auto &t : workers_) t.join();
     }
-    int threads() const { return (int)workers_.size(); }
     // rows x width bytes from src (pitch spitch) to dst (pitch dpitch); returns a ticket for wait()
     int submit(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows) {
         if (rows == 0 || width == 0) return -1;
@@ -777,19 +776,6 @@ int launch_process_fused(vrsbs_ctx *c, Scratch &s, const uint8_t *frames, const 
     c->state_h = H; c->state_w = W;
     if (!c->params.blur) return VRSBS_OK;
     return launch_blur(c, s, frames, B, H, W, sbs, st);
-}
-
-void parallel_memcpy(void *dst, const void *src, size_t bytes, int nthreads) {
-    if (bytes < (8u << 20) || nthreads <= 1) { memcpy(dst, src, bytes); return; }
-    std::vector<std::thread> th;
-    const size_t part = align_up((bytes + nthreads - 1) / nthreads, 4096);
-    for (int i = 0; i < nthreads; ++i) {
-        const size_t off = (size_t)i * part;
-        if (off >= bytes) break;
-        const size_t len = bytes - off < part ? bytes - off : part;
-        th.emplace_back([=] { memcpy((char *)dst + off, (const char *)src + off, len); });
-    }
-    for (auto &t : th) t.join();
 }
 
 bool is_pinned(const void *p) {

@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_ws(WsArgs wa) {
             const uint4 hdrw = lds_u128(sa_blob);
             if (hdrw.w & 1u) {
                 const uint32_t sa_ent = sa_blob + 16u, sa_lut = sa_ent + a.ent_bytes;
-                const uint32_t lut_mul = 1u << (16u - hdrw.y), lut_last = sa_lut + hdrw.z;
+                const uint32_t lut_sh = hdrw.y, lut_last = sa_lut + hdrw.z;        // cell = fp16 bits >> shift; the last cell = every negative value
                 const uint32_t sa_keys_lo = sa_keys - 4u * (uint32_t)a.key_pad;
                 auto batch = [&](auto Uc, auto Wc, int round0) {
                     constexpr int U = decltype(Uc)::value;
@@ -148,18 +148,18 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_ws(WsArgs wa) {
                     uint32_t dd[U], e[U];
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        dd[u] = c[u] | (c[u] << 16);
-                        e[u] = lds_u8(min(__umulhi(dd[u], lut_mul) + sa_lut, lut_last));
+                        asm("mov.b32 %0, {%1, %1};" : "=r"(dd[u]) : "h"((unsigned short)c[u]));
+                        e[u] = lds_u8(min((c[u] >> lut_sh) + sa_lut, lut_last));
                     }
                     uint2 en[U];
 #pragma unroll
                     for (int u = 0; u < U; ++u) en[u] = lds_u64(sa_ent + 8u * e[u]);
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        const uint32_t px = __funnelshift_r(w0[u], w1[u], wsh) & 0x00ffffffu;
-                        const uint32_t key0 = px | (e[u] << 24);
+                        // key = layer byte | RGB: one PRMT on the funnel-shifted pixel word; a0 = kb + low half of the offset pair (one dp2a)
+                        const uint32_t key0 = __byte_perm(__funnelshift_r(w0[u], w1[u], wsh), e[u], 0x4210);
                         const uint32_t kb = sa_keys_lo + x4[u];
-                        uint32_t a0 = kb + (en[u].y & 0xffffu), a1 = kb + (en[u].y >> 16);
+                        uint32_t a0 = __dp2a_lo(en[u].y, 1u, kb), a1 = kb + (en[u].y >> 16);
                         if (WRAP) {                              // see k_warp_fused: first segment left end, last two right end
                             uint32_t q0 = a0 - sa_keys, q1 = a1 - sa_keys;
                             if (u == 0) { q0 = min(q0, q0 + W4); q1 = min(q1, q1 + W4); }
