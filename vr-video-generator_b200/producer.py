@@ -58,3 +58,62 @@ def reference_depth(model, frame, scaler, input_size=518):
         d = model.forward(x)
         d = torch.nn.functional.interpolate(d[:, None], (h, w), mode="bicubic", align_corners=True)[0][0]
         return d * scaler
+
+
+# ---- f2: the reference's producer process, protocol for protocol ------------------------------------------------------
+def inference_worker(in_queue_list, out_queue_list, notify_queue_list, DEVICE, args_god, model=None, load_model=None,
+                     on_device=False, lowres=False, input_size=518):
+    """Mirror of `inference_worker` (PredictAndGenerate.py:23-61): one depth model serving several SBS workers.
+
+    Protocol, unchanged: an SBS worker announces a job with `notify_queue.put((idx,))` and puts `(img,)` on its own job
+    queue (`SbsProcessor.add_frame`, :127-129); this loop pops the notification, pops that worker's job, runs the model
+    under `no_grad` + fp16 autocast, multiplies by the per-encoder scaler (:27-34) and puts the result on that worker's
+    result queue; `None` on the notify queue or on a job queue ends the loop (:46-51, the shutdown `main_func` sends at
+    :316-319).  A two-deep ring per client keeps the tensor a client may still be reading alive (:40,53-56).  The warm-up
+    forward on a black 1080p frame runs outside autocast like :37.
+
+    `model` (or `load_model(encoder, encoder_path, DEVICE)`, the reference's `SupportFunction.load_model`) supplies
+    `infer_image_gpu(img)`; nothing of the ViT lives in this package.
+
+    on_device=False is the reference's hand-off: the full-resolution depth goes `.to('cpu')` and through the queue (the
+    consumer's `left_side_sbs` then takes the host pipeline).  on_device=True is for SBS workers that are THREADS of this
+    process (queue.Queue): the tensor stays on the GPU - what the author tried and gave up on across processes (:54) - and
+    is complete before it is put (an event is waited for on the producer's side, never on the consumer's).  With
+    lowres=True the DPT-resolution map (`image2tensor` + `forward`, dpt.py:180-228) is handed over instead and the bicubic
+    tail and the scaler run inside the warp's depth pass (`left_side_sbs_batch(..., scaler=producer scaler)`); the queue
+    item is then `(tensor, scaler)`.  Returns the number of frames served."""
+    scaler = encoder_scaler(args_god.encoder)
+    dev = DEVICE if isinstance(DEVICE, torch.device) else torch.device(DEVICE)
+    if model is None:
+        if load_model is None:
+            raise ValueError("inference_worker needs a model or a load_model callable")
+        model = load_model(args_god.encoder, args_god.encoder_path, dev)
+    warm = model.infer_image_gpu(np.zeros((1080, 1920, 3), dtype=np.uint8))
+    ring = [[warm.detach().clone(), warm.detach().clone()] for _ in out_queue_list]
+    del warm
+    served = 0
+    while True:
+        queue_idx = notify_queue_list.get()
+        if queue_idx is None:
+            break
+        task = in_queue_list[queue_idx[0]].get()
+        if task is None:
+            break
+        img = task[0]
+        del ring[queue_idx[0]][0]
+        with torch.no_grad(), torch.autocast(device_type=dev.type, dtype=torch.float16):
+            if lowres:
+                x, _hw = model.image2tensor(img, input_size)
+                d = model.forward(x)[0].contiguous()
+            else:
+                d = model.infer_image_gpu(img) * scaler
+            if not on_device:
+                d = d.to(torch.device("cpu"))
+            elif d.is_cuda:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(d.device))
+                ev.synchronize()
+        ring[queue_idx[0]].append(d)
+        out_queue_list[queue_idx[0]].put((d, scaler) if lowres else d)
+        served += 1
+    return served
