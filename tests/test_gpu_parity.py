@@ -868,3 +868,76 @@ def test_producer_handoff_keeps_depth_on_the_device():
     ref = producer.reference_depth(model, rgb[0], prod.scaler).float().cpu().numpy()
     mine = O.bicubic_resize(lo[0].cpu().numpy(), H, W, prod.scaler).astype(np.float32)
     assert np.all(np.abs(mine - ref) <= 1e-3 * np.abs(ref) + 1e-3)
+
+
+@pytest.mark.parametrize("lowres", [False, True])
+def test_inference_worker_threads_keep_depth_on_the_device(lowres, oracle_lib):
+    """f2: one `producer.inference_worker` thread serving two SBS worker threads over the reference's queue protocol
+    (notify / job / result), the depth never leaving the GPU.  Every worker's frames equal the oracle fed with the depth
+    the producer computed for them (full-resolution hand-off), or the frames of the host hand-off of the same
+    DPT-resolution maps (lowres hand-off: bicubic + scaler inside the depth pass)."""
+    import argparse
+    import queue
+    import threading
+
+    import vr_video_generator_b200 as pkg
+    from vr_video_generator_b200 import producer, synth, worker
+    H, W, n = 270, 480, 5
+
+    class _Model(_ToyDepthModel):
+        def infer_image_gpu(self, img):
+            x, (h, w) = self.image2tensor(img)
+            d = self.forward(x)
+            return torch.nn.functional.interpolate(d[:, None], (h, w), mode="bicubic", align_corners=True)[0, 0]
+    args = argparse.Namespace(offset_fg=0.025, offset_bg=-0.015, offset_step_size=1, encoder="vits", encoder_path="")
+    clips = [synth.frames_gradient(n, H, W, seed=5 + c)[:, :, :, ::-1].copy() for c in range(2)]
+    in_q, out_q, notify = [queue.Queue(), queue.Queue()], [queue.Queue(), queue.Queue()], queue.Queue()
+    served = []
+    prod = threading.Thread(target=lambda: served.append(producer.inference_worker(
+        in_q, out_q, notify, torch.device("cuda", 0), args, model=_Model(), on_device=True, lowres=lowres)))
+    prod.start()
+    results, errors = [None, None], []
+
+    def sbs_thread(c):
+        try:
+            proc = pkg.SbsProcessor(notify, c, args, device=0, max_batch=4)
+            out = []
+            # the reference's loop: add_frame(i) before left_side_sbs(i-1) (PredictAndGenerate.py:226-234)
+            proc.add_frame(clips[c][0], in_q[c], out_q[c])
+            for i in range(1, n):
+                proc.add_frame(clips[c][i], in_q[c], out_q[c])
+                out.append(proc.left_side_sbs(clips[c][i - 1], in_q[c], out_q[c]))
+            out.append(proc.left_side_sbs(clips[c][n - 1], in_q[c], out_q[c]))
+            proc.close()
+            results[c] = np.stack(out)
+        except Exception as e:                                   # noqa: BLE001
+            errors.append(e)
+    threads = [threading.Thread(target=sbs_thread, args=(c,)) for c in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+    notify.put(None)
+    prod.join(timeout=30)
+    assert not errors, errors
+    assert served == [2 * n]
+    model = _Model()
+    scaler = worker.encoder_scaler("vits")
+    w = O.gaussian_weights(*O.blur_kernel_shape(H))
+    for c in range(2):
+        assert np.array_equal(results[c][:, :, W:], clips[c])
+        if lowres:
+            dp = producer.DepthProducer(model, "vits", max_forward_batch=1)
+            lo = torch.cat([dp(clips[c][i:i + 1]) for i in range(n)]).cpu().numpy()
+            ref = pkg.SbsProcessor(None, 0, args, device=0, max_batch=4)
+            want = ref.left_side_sbs_batch(clips[c], lo, scaler=scaler)
+            ref.close()
+            assert np.array_equal(results[c], want)
+        else:
+            with torch.no_grad(), torch.autocast(device_type="cuda", dtype=torch.float16):
+                raws = [(model.infer_image_gpu(clips[c][i]) * scaler).cpu().numpy() for i in range(n)]
+            st = O.WarpState(args.offset_fg, args.offset_bg, args.offset_step_size)
+            for i in range(n):
+                d = raws[i]
+                want = oracle_lib.process_frame(st, clips[c][i], d, weights=w)
+                assert np.array_equal(results[c][i], want), (c, i, d.dtype)

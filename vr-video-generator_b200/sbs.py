@@ -126,6 +126,10 @@ class SbsProcessor:
         on the way back).  A CUDA depth tensor is used where it is."""
         H, W, _ = raw_img.shape
         raw = result_queue.get()
+        if isinstance(raw, tuple):
+            # (DPT-resolution map, scaler) from producer.inference_worker(lowres=True): bicubic + scaler on the device
+            lo, sc = raw
+            return self.left_side_sbs_batch(np.ascontiguousarray(raw_img)[None], lo if lo.dim() == 3 else lo[None], scaler=sc)[0]
         if not (isinstance(raw, torch.Tensor) and raw.is_cuda):
             d = _as_numpy(raw)
             _check_depth_dtype(d.dtype)
