@@ -14,3 +14,13 @@ try:
 except Exception as e: print(f, "ERR", e, open(f.replace(".json",".err")).read()[-1500:])
 PY
 done
+for o in $AB_OPTS; do
+  timeout -k 10 600 python bench.py --steps 10 --warmup 3 --workload ${AB_WL:-1080p_b64} --no-cpu-baseline --no-4k --video-frames 0 --e2e-steps 2 --opt $o > gpurun_out/q_ab_$o.json 2> gpurun_out/q_ab_$o.err
+  python - "$o" <<'PY'
+import json,sys
+f="gpurun_out/q_ab_%s.json"%sys.argv[1]
+try:
+    d=json.load(open(f)); print(sys.argv[1], "ms/step", round(d["ms_per_step"],4), {k: round(v,4) for k,v in d["stage_ms_per_step"].items()})
+except Exception as e: print(f, "ERR", e, open(f.replace(".json",".err")).read()[-800:])
+PY
+done
