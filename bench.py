@@ -162,7 +162,7 @@ def dist_setup():
 class DeviceBench:
     """Device-resident inputs of one workload + the timed step (vrsbs_process_batch, or the low-res depth route)."""
 
-    def __init__(self, args, wl, dev, seed=100):
+    def __init__(self, args, wl, dev, seed=100, f32=False):
         import torch
 
         from vr_video_generator_b200 import _native, tables
@@ -173,8 +173,9 @@ class DeviceBench:
         # between seeds and the job time is the max over ranks
         self.frames_h, self.lowres_h = make_inputs(wl, seed=seed)
         ctx = _native.Context(dev, H, W, B, 512)
-        ctx.reset(wl["fg"], wl["bg"], wl["step"], True)
+        ctx.reset(wl["fg"], wl["bg"], wl["step"], True, _native.DEPTH_F32 if f32 else _native.DEPTH_F16)
         ctx.set_blur_weights(tables.gaussian_weights(*tables.blur_kernel_shape(H)))
+        self.f32 = f32
         if args.scatter_mode:                      # 1/2: the general row kernel instead of the fused route (A/B runs)
             ctx.set_option("fused", 0)
             ctx.set_option("scatter_mode", args.scatter_mode)
@@ -197,6 +198,8 @@ class DeviceBench:
         torch.cuda.synchronize()
         prep.close()
         self.raw_h = self.raw_d.cpu().numpy()
+        if f32:                                    # the same depth values as an fp32 clip (what torch >= 2.4 autocast hands over)
+            self.raw_d = self.raw_d.float()
         self.scratch_d = torch.empty_like(self.raw_d)
         self.sbs_d = torch.empty((B, H, 2 * W, 3), dtype=torch.uint8, device="cuda")
         self.lowres = args.depth_input == "lowres"
@@ -626,6 +629,20 @@ def run_ours(args, wl, name):
         torch.cuda.empty_cache()
     else:
         db.close()
+    # the same headline workload with fp32 depth (the dtype the reference's producer hands over under torch >= 2.4; the general
+    # row kernel with fp32 comparison) - reported aside, the metric's config is fp16
+    if args.also_f32 and not args.scatter_mode and args.depth_input == "full":
+        torch.cuda.empty_cache()
+        db32 = DeviceBench(args, wl, dev, f32=True)
+        steps32 = max(3, min(args.steps, 10))
+        _ms_s, ms32, _hi, stage32, _l32, _infos32 = db32.timed(steps32, 3, barrier)
+        ms32 = reduce_max(ms32)
+        extra[name + "_f32_depth"] = {"value": world * B * steps32 / (ms32 * 1e-3), "unit": UNIT, "steps": steps32, "ms_per_step": ms32 / steps32,
+                                     "stage_ms_per_step": {k: v[0] / steps32 for k, v in stage32.items()},
+                                     "route": "k_depth_f32, k_build_tables (fp32 bounds), k_warp_rows<2,TMA,F32>, k_blur_sep, k_blur_commit"}
+        db32.close()
+        del db32
+        torch.cuda.empty_cache()
 
     cpu = ref_cuda = producer = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -851,6 +868,7 @@ def main():
                     help="stream an N-frame synthetic video sharded by clip range over the ranks (BASELINE.json configs[4]; default "
                          "3600 = 2 min of 1080p30 so that the default run stays short, 18000 = the full 10 minutes, 0 = skip)")
     ap.add_argument("--no-4k", dest="also_4k", action="store_false", help="skip the 4k_wide_b16 sub-record (configs[2])")
+    ap.add_argument("--no-f32", dest="also_f32", action="store_false", help="skip the fp32-depth sub-record")
     ap.add_argument("--no-producer", action="store_true", help="skip the depth producer timing")
     ap.add_argument("--host-opt", action="append", default=[], help="library option name=value for the host-API context")
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (vrsbs_set_option)")

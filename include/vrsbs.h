@@ -38,7 +38,11 @@ enum {
     VRSBS_E_CUDA        = -2,  /* a CUDA runtime call failed; message has cudaGetErrorString        */
     VRSBS_E_NOMEM       = -3,
     VRSBS_E_FRAME       = -4,  /* a frame of the batch was rejected on the device: NaN depth (the    */
-                               /* reference raises in math.ceil) or more layers than max_layers    */
+                               /* reference raises in math.ceil) or more layers than max_layers.   */
+                               /* Like the reference's worker, which dies on that exception, the   */
+                               /* clip-range state is not defined afterwards: call vrsbs_reset.    */
+                               /* The device-pointer calls are asynchronous and report it through  */
+                               /* vrsbs_get_frame_info only; the host calls return it themselves.  */
     VRSBS_E_STATE       = -5   /* call order violated (e.g. warp before prepare)                    */
 };
 

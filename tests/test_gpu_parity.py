@@ -384,6 +384,22 @@ def test_rejected_frames():
         _run_device(ctx, np.zeros((1, 1080, 64, 3), np.uint8), np.full((1, 1080, 64), 14.0, np.float16))
     assert e.value.code == -4 and "max_layers" in str(e.value)
     ctx.close()
+    # the drop-in class: the asynchronous device-resident call reports it on request (check=True / frame_status)
+    import argparse
+    import vr_video_generator_b200 as pkg
+    proc = pkg.SbsProcessor(None, 0, argparse.Namespace(offset_fg=0.05, offset_bg=-0.03, offset_step_size=1), device=0, max_batch=2)
+    f, r = torch.from_numpy(frames).cuda(), torch.from_numpy(raw).cuda()
+    with pytest.raises(_native.VrsbsError):
+        proc.warp_batch_device(f, r, check=True)
+    proc.reset_state()
+    proc.warp_batch_device(f, r)
+    with pytest.raises(_native.VrsbsError):
+        proc.frame_status(1)
+    proc.reset_state()
+    good = torch.full((1, H, W), 5.0, dtype=torch.float16, device="cuda")
+    proc.warp_batch_device(f, good, check=True)
+    assert proc.frame_status(1)[0].layers > 0
+    proc.close()
 
 
 # ---- depth tail (stage 1 from low-res) --------------------------------------------------------------

@@ -231,9 +231,12 @@ class SbsProcessor:
             raise ValueError(f"depth {dshape} does not match {B} frames")
         return dshape, dptr, keep
 
-    def warp_batch_device(self, frames, raw_depth, out=None, depth_scratch=None):
+    def warp_batch_device(self, frames, raw_depth, out=None, depth_scratch=None, check=False):
         """Device-resident batch on the current stream, asynchronous: frames [B,H,W,3] uint8 CUDA,
-        raw_depth [B,H,W] fp16 CUDA (raw, full-res) -> sbs [B,H,2W,3] uint8 CUDA."""
+        raw_depth [B,H,W] fp16 / fp32 CUDA (raw, full-res) -> sbs [B,H,2W,3] uint8 CUDA.  A frame the device rejects (NaN
+        depth - the reference raises in `math.ceil` - or more layers than `max_layers`) leaves garbage in its SBS frame:
+        `check=True` waits for the stream and raises like the host calls do; otherwise call `frame_status(B)` once the
+        stream has been synchronised.  After such an error the clip state is undefined (`reset_state`)."""
         B, H, W, _ = frames.shape
         _check_depth_dtype(raw_depth.dtype)
         ctx = self._context(H, W, raw_depth.dtype == torch.float32)
@@ -244,7 +247,14 @@ class SbsProcessor:
         _check_cuda(frames, torch.uint8), _check_cuda(raw_depth, raw_depth.dtype)
         ctx.process_batch(frames.data_ptr(), raw_depth.data_ptr(), B, H, W, depth_scratch.data_ptr(),
                           out.data_ptr(), self._stream())
+        if check:
+            ctx.frame_info(B, self._stream())      # synchronises the stream; raises VrsbsError(E_FRAME) for a rejected frame
         return out
+
+    def frame_status(self, B):
+        """Per-frame records of the last device-resident batch (layers, limit_step, strip, holes, status); waits for the
+        current stream and raises if the device rejected a frame."""
+        return self._ctx.frame_info(B, self._stream())
 
     # ---- helpers ---------------------------------------------------------------------------------
     def _raw_to_device(self, raw):
