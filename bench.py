@@ -857,7 +857,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="1080p_b64", choices=sorted(WORKLOADS))
     ap.add_argument("--scatter-mode", type=int, default=0)
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--depth-input", default="full", choices=["full", "lowres"],
                     help="full: raw full-resolution fp16 depth (the metric's config); lowres: DPT-resolution map, bicubic on the device")
     ap.add_argument("--host-chunk", type=int, default=0)

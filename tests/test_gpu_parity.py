@@ -660,9 +660,9 @@ def test_out_of_budget_frames_fall_back(oracle_lib):
         ctx.close()
 
 
-@pytest.mark.parametrize("split", [3, 4, 5, 6, 7])
+@pytest.mark.parametrize("split", [3, 4, 5])
 def test_warp_specialised_splits(split, oracle_lib):
-    """k_warp_ws with every scatter/destination warp split (3+5, 4+4, 5+3 of 8 warps, 6+3 of 9, 6+4 of 10)."""
+    """k_warp_ws with every scatter/destination warp split that is built (3+5, 4+4, 5+3 of 8 warps)."""
     for name in ("small_a", "medium"):
         meta, frames, raw, ref_left = load_case(name)
         p = meta["params"]

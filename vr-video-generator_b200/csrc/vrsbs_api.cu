@@ -192,7 +192,8 @@ struct vrsbs_ctx {
     int key_pad = 0;                     // fast path: bound on |signed layer offset| in pixels (multiple of 32)
     int fused = 1;                       // option: use the fused route in vrsbs_process_batch when possible
     int fast_tables = 1;                 // option (tests): 0 forces the slow membership path of k_warp_fused
-    int ws_scatter_warps = 4;            // option: scatter warps of k_warp_ws (3, 4 or 5 of 8 warps; 6 = 6 of 9, 7 = 6 of 10); 4 measured best
+    int ws_scatter_warps = 4;            // option: scatter warps of k_warp_ws (3, 4 or 5 of 8 warps); 4 measured best (9- and 10-warp CTAs were slower
+                                         // and are no longer built)
     int commit_mode = 1;                 // experiments: 1 = commit + strip, 0 = strip only, 3 = commit only, 2 = neither
     int warp_ws = 1;                     // option: 1 = warp-specialised warp kernel (k_warp_ws) when it fits, 0 = k_warp_fused
     int lowres_tiled = 1;                // option: 0 = one-pixel-per-thread bicubic kernel (tests)
@@ -571,8 +572,6 @@ int launch_ws(vrsbs_ctx *c, const FusedArgs &a, cudaStream_t st, bool *launched)
     switch (c->ws_scatter_warps) {
         case 3: return launch_ws_inst<256, 3>(c, a, st, launched);
         case 4: return launch_ws_inst<256, 4>(c, a, st, launched);
-        case 6: return launch_ws_inst<288, 6>(c, a, st, launched);      // 9 warps: 6 scatter + 3 destination
-        case 7: return launch_ws_inst<320, 6>(c, a, st, launched);      // 10 warps: 6 + 4
         case 5: return launch_ws_inst<256, 5>(c, a, st, launched);
         default: return launch_ws_inst<256, 4>(c, a, st, launched);
     }
