@@ -629,8 +629,8 @@ def run_ours(args, wl, name):
         torch.cuda.empty_cache()
     else:
         db.close()
-    # the same headline workload with fp32 depth (the dtype the reference's producer hands over under torch >= 2.4; the general
-    # row kernel with fp32 comparison) - reported aside, the metric's config is fp16
+    # the same headline workload with fp32 depth (the dtype the reference's producer hands over under torch >= 2.4: fp32
+    # smoothing, fp32 comparison) - reported aside, the metric's config is fp16
     if args.also_f32 and not args.scatter_mode and args.depth_input == "full":
         torch.cuda.empty_cache()
         db32 = DeviceBench(args, wl, dev, f32=True)
@@ -639,7 +639,7 @@ def run_ours(args, wl, name):
         ms32 = reduce_max(ms32)
         extra[name + "_f32_depth"] = {"value": world * B * steps32 / (ms32 * 1e-3), "unit": UNIT, "steps": steps32, "ms_per_step": ms32 / steps32,
                                      "stage_ms_per_step": {k: v[0] / steps32 for k, v in stage32.items()},
-                                     "route": "k_depth_f32, k_build_tables (fp32 bounds), k_warp_rows<2,TMA,F32>, k_blur_sep, k_blur_commit"}
+                                     "route": "k_depth_pass_f32, k_build_tables (fp32 bounds + fp32 cell LUT), k_warp_ws<256,4,F32>, k_blur_sep, k_blur_commit"}
         db32.close()
         del db32
         torch.cuda.empty_cache()

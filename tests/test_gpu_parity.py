@@ -109,9 +109,10 @@ def test_small_cases_match_reference(name, mode, oracle_lib):
     ctx.close()
 
 
+@pytest.mark.parametrize("fast", [1, 0])
 @pytest.mark.parametrize("splits", [None, [1, 2], [2, 1, 1]])
 @pytest.mark.parametrize("name", F32_CASES)
-def test_fp32_depth_matches_reference(name, splits, oracle_lib):
+def test_fp32_depth_matches_reference(name, splits, fast, oracle_lib):
     """fp32 depth (what torch >= 2.4's CUDA autocast hands the warp): smoothing, max and the bin comparison in fp32 -
     byte-identical to the UNMODIFIED reference fed the same fp32 maps (fixtures generated by the reference), fp32 bit
     patterns of the smoothed depth and of the bounds equal to the oracle's, state carried across batch splits."""
@@ -122,6 +123,7 @@ def test_fp32_depth_matches_reference(name, splits, oracle_lib):
     if splits is not None and sum(splits) != p["n"]:
         splits = [1] * p["n"]
     ctx = _ctx(p["H"], p["W"], p["fg"], p["bg"], p["step"], w, f32=True)
+    ctx.set_option("f32_fast", fast)      # 1: k_depth_pass_f32 + k_warp_ws<.., F32>; 0: the general kernels (k_depth_f32, k_warp_rows)
     sbs, dep, infos, masks = _run_device(ctx, frames, raw, splits)
     want, stages = _oracle_run(oracle_lib, p, frames, raw, w)
     for t in range(p["n"]):
@@ -138,6 +140,34 @@ def test_fp32_depth_matches_reference(name, splits, oracle_lib):
             lo_ref, hi_ref = O.layer_bounds(unhex(meta["frames"][t]["cutoffs"]), unhex(meta["frames"][t]["steps"]), np.float32)
             assert np.array_equal(lo.view(np.uint32), lo_ref.view(np.uint32)) and np.array_equal(hi.view(np.uint32), hi_ref.view(np.uint32))
     ctx.close()
+
+
+@pytest.mark.parametrize("shape,fg,bg,step", [((40, 1920), 0.4, -0.3, 1), ((36, 2560), 0.6, -0.5, 1), ((48, 512), 0.9, -0.9, 2),
+                                              ((33, 3840), 0.8, 0.2, 1), ((24, 960), 0.05, -0.03, 1)])
+def test_fp32_fast_route_equals_general_route(shape, fg, bg, step):
+    """The warp-specialised kernel's fp32 instantiation (fp32 cell LUT, two fp32 compares) and the vectorised fp32 depth pass
+    against the general kernels the reference-generated fp32 fixtures pin: same bytes, same hole masks, same smoothed depth
+    bits, on rows up to 4K wide, wrapping offsets, negative and tiny depths, and values that sit exactly on bounds."""
+    H, W = shape
+    n = 4
+    rng = np.random.default_rng(H * 131 + W)
+    frames = rng.integers(0, 256, (n, H, W, 3), dtype=np.uint8)
+    raw = (rng.random((n, H, W), dtype=np.float32) * 15.5 - 0.6).astype(np.float32)
+    raw[:, :, : W // 8] = rng.choice(np.float32([0.0, -0.0, 1e-9, 0.0155, 0.0157, 3.0, 7.25]), size=(n, H, W // 8))
+    raw[1, :, W // 2:] = np.float32(5.0)                      # a flat area: many pixels on one value
+    w = O.gaussian_weights(*O.blur_kernel_shape(1080))
+    outs = []
+    for fast in (0, 1):
+        ctx = _ctx(H, W, fg, bg, step, w, max_layers=1024, f32=True)
+        ctx.set_option("f32_fast", fast)
+        sbs, dep, infos, masks = _run_device(ctx, frames, raw, [3, 1])
+        outs.append((sbs, dep, masks, [(i.layers, i.holes, i.strip) for i in infos]))
+        ctx.close()
+    assert outs[0][3] == outs[1][3]
+    assert np.array_equal(outs[0][1].view(np.uint32), outs[1][1].view(np.uint32))
+    assert np.array_equal(outs[0][2], outs[1][2])
+    assert np.array_equal(outs[0][0], outs[1][0]), int((outs[0][0] != outs[1][0]).sum())
+    assert np.array_equal(outs[1][0][:, :, W:], frames)
 
 
 def test_fp32_depth_through_the_dropin_and_the_host_pipeline(oracle_lib):

@@ -46,10 +46,19 @@ struct LayerEnt {
     uint32_t hi_lo;         // half2: .x (low 16) = hi of layer e-1 (-inf for e = 0), .y = lo of layer e (+inf for e = L)
     uint32_t off4;          // low 16: 4*(signed offset of layer e-1 + key_pad); high 16: same for layer e
 };
-__host__ __device__ inline uint32_t blob_ent_bytes(int ent_cap) { return (uint32_t)(((ent_cap + 1) * 8 + 15) / 16 * 16); }
-__host__ __device__ inline uint32_t blob_bytes(int ent_cap, int lut_cap) {
-    return 16u + blob_ent_bytes(ent_cap) + (uint32_t)((lut_cap + 15) / 16 * 16);
+__host__ __device__ inline uint32_t blob_ent_bytes(int ent_cap, bool f32 = false) {
+    return (uint32_t)(((ent_cap + 1) * (f32 ? 16 : 8) + 15) / 16 * 16);
 }
+__host__ __device__ inline uint32_t blob_bytes(int ent_cap, int lut_cap, bool f32 = false) {
+    return 16u + blob_ent_bytes(ent_cap, f32) + (uint32_t)((lut_cap + 15) / 16 * 16);
+}
+// fp32 depth: 16-byte entries - the two bounds as floats (hi of layer e-1: -inf for e = 0; lo of layer e: +inf for e = L) and
+// the same offset pair; BlobHdr.shift = shift | base << 8 with cell = max(fp32 bits >> shift, base) - base
+struct LayerEnt32 {
+    float hi_prev, lo_cur;
+    uint32_t off4, pad;
+};
+constexpr uint32_t kF32LutFloorBits = 0x3C800000u;   // 2^-6: every smaller non-negative depth shares cell 0
 
 // Range-EMA state that survives between batches (SbsProcessor.last_offset_range).
 struct RangeState {

@@ -406,6 +406,67 @@ __global__ void __launch_bounds__(256) k_depth_f32(DepthArgs32 a) {
     }
 }
 
+// ---- fp32 depth pass, vectorised: the fp32 counterpart of k_depth_pass<true> -------------------------------------
+// Full-resolution fp32 raw depth in, smoothed fp32 depth + per-frame max out; 4 pixels (one 16-byte access) per thread and
+// frame, four frames of loads in flight, history in registers.  Same arithmetic as k_depth_f32 (one fp32 rounding per op).
+__global__ void __launch_bounds__(256) k_depth_pass_f32(DepthArgs32 a) {
+    extern __shared__ uint32_t s_red[];
+    uint32_t *s_max = s_red, *s_nan = s_red + a.B;
+    pdl_launch_dependents();
+    for (int i = threadIdx.x; i < 2 * a.B; i += blockDim.x) s_red[i] = 0;
+    __syncthreads();
+    const size_t n = (size_t)a.H * a.W;
+    const size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = v * 4 < n;
+    const size_t base = active ? v * 4 : 0;
+    const float w0 = a.sw.w_now, w1 = a.sw.w_prev1, w2 = a.sw.w_prev2;
+    float4 p1 = make_float4(0.f, 0.f, 0.f, 0.f), p2 = p1;
+    if (active && !a.first) {
+        p1 = __ldg(reinterpret_cast<const float4 *>(a.hist1 + base));
+        p2 = __ldg(reinterpret_cast<const float4 *>(a.hist2 + base));
+    }
+    auto load = [&](int t) -> float4 {
+        return (active && t < a.B) ? __ldg(reinterpret_cast<const float4 *>(a.raw + (size_t)t * n + base)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    constexpr int U = 4;
+    for (int tb = 0; tb < a.B; tb += U) {
+        float4 q[U];
+#pragma unroll
+        for (int i = 0; i < U; ++i) q[i] = load(tb + i);
+#pragma unroll
+        for (int i = 0; i < U; ++i) {
+            const int t = tb + i;
+            if (t >= a.B) break;
+            uint32_t enc = 0;
+            bool nan = false;
+            if (active) {
+                const float4 cur = q[i];
+                if (a.first && t == 0) p1 = p2 = cur;
+                float4 r;
+                r.x = smooth3_f32(cur.x, p1.x, p2.x, w0, w1, w2);
+                r.y = smooth3_f32(cur.y, p1.y, p2.y, w0, w1, w2);
+                r.z = smooth3_f32(cur.z, p1.z, p2.z, w0, w1, w2);
+                r.w = smooth3_f32(cur.w, p1.w, p2.w, w0, w1, w2);
+                *reinterpret_cast<float4 *>(a.out + (size_t)t * n + base) = r;
+                nan = (r.x != r.x) || (r.y != r.y) || (r.z != r.z) || (r.w != r.w);
+                if (!nan) enc = f2ord(fmaxf(fmaxf(r.x, r.y), fmaxf(r.z, r.w)));
+                p2 = p1;
+                p1 = cur;
+            }
+            frame_max_commit(enc, nan, t, s_max, s_nan);
+        }
+    }
+    if (active) {
+        *reinterpret_cast<float4 *>(a.hist1 + base) = p1;
+        *reinterpret_cast<float4 *>(a.hist2 + base) = p2;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < a.B; t += blockDim.x) {
+        if (s_max[t]) atomicMax(&a.frame_max[t], s_max[t]);
+        if (s_nan[t]) atomicOr(&a.frame_nan[t], 1u);
+    }
+}
+
 // ---- low-res DPT output in, tiled: horizontal interpolations shared by the output rows that use them --------
 // Same arithmetic as k_depth_lowres (ATen's: four row interpolations, then one column interpolation, every
 // mul/add in the same order), but a CTA owns a 64 x 16 output tile and first computes the row interpolation

@@ -200,15 +200,17 @@ __global__ void __launch_bounds__(256) k_build_tables(TableArgs a) {
 
     // ---- fast-path blob: entry table + cell LUT (validated exactly, cell by cell) ----------------------
     if (!a.blobs) { if (threadIdx.x == 0) { tab->fast = 0; tab->lut_shift = 0; tab->lut_cells = 0; } return; }
-    const uint32_t ent_bytes = blob_ent_bytes(a.ent_cap);
-    uint8_t *blob = a.blobs + (size_t)b * blob_bytes(a.ent_cap, a.lut_cap);
+    const bool f32 = a.f32 != 0;
+    const uint32_t ent_bytes = blob_ent_bytes(a.ent_cap, f32);
+    uint8_t *blob = a.blobs + (size_t)b * blob_bytes(a.ent_cap, a.lut_cap, f32);
     BlobHdr *hdr = reinterpret_cast<BlobHdr *>(blob);
     LayerEnt *ent = reinterpret_cast<LayerEnt *>(blob + 16);
+    LayerEnt32 *ent32 = reinterpret_cast<LayerEnt32 *>(blob + 16);
     uint8_t *lut = blob + 16 + ent_bytes;
     const float fmax = s_max;
-    bool ok = !a.f32 && mono && !s_bad && !a.frame_nan[b] && L <= a.ent_cap && L <= 255 && a.W * 4 <= 65535 && fmax < 60000.f;
+    bool ok = mono && !s_bad && !a.frame_nan[b] && L <= a.ent_cap && L <= 255 && a.W * 4 <= 65535 && fmax < 60000.f;
     // (the LUT search binary-searches the bounds thousands of times: they are in shared memory already)
-    const uint32_t maxbits = (fmax > 0.f) ? (uint32_t)__half_as_ushort(__float2half_rn(fmax)) : 0u;
+    const uint32_t maxbits = (fmax > 0.f) ? (f32 ? __float_as_uint(fmax) : (uint32_t)__half_as_ushort(__float2half_rn(fmax))) : 0u;
     {
         int fits = 1;
         for (int k = threadIdx.x; k < L; k += blockDim.x) {
@@ -218,8 +220,8 @@ __global__ void __launch_bounds__(256) k_build_tables(TableArgs a) {
         ok = __syncthreads_and(fits) && ok;
     }
     int shift = -1;
-    uint32_t ncells = 0;
-    if (ok) {
+    uint32_t ncells = 0, lbase = 0;
+    if (ok && !f32) {
         for (int sh = 9; sh >= 0; --sh) {
             const uint32_t nc = (maxbits >> sh) + 1;
             if (nc + 1 > (uint32_t)a.lut_cap) break;
@@ -238,22 +240,54 @@ __global__ void __launch_bounds__(256) k_build_tables(TableArgs a) {
             }
             if (__syncthreads_and(valid)) { shift = sh; ncells = nc; break; }
         }
+    } else if (ok) {
+        // fp32 depth: cell = max(bits >> sh, base) - base, base = the cell of 2^-6; cell 0 holds every value in [0, end of that
+        // cell], the last cell every negative value.  From 8 cells per binade (sh = 20) down to 1024 (sh = 13).
+        for (int sh = 20; sh >= 13; --sh) {
+            const uint32_t cb = kF32LutFloorBits >> sh;
+            const uint32_t top = max(maxbits >> sh, cb);
+            const uint32_t nc = top - cb + 1;
+            if (nc + 1 > (uint32_t)a.lut_cap) break;
+            int valid = 1;
+            for (uint32_t q = threadIdx.x; q <= nc; q += blockDim.x) {
+                float vmin, vmax;
+                if (q < nc) {
+                    const uint32_t b0 = q ? (cb + q) << sh : 0u, b1 = max(min((((cb + q) + 1) << sh) - 1, maxbits), b0);
+                    vmin = __uint_as_float(b0);
+                    vmax = __uint_as_float(b1);
+                } else {
+                    vmin = -INFINITY; vmax = 0.f;
+                }
+                int e = cell_entry(s_bounds, L, vmin, vmax);
+                if (e < 0) valid = 0; else lut[q] = (uint8_t)e;
+            }
+            if (__syncthreads_and(valid)) { shift = sh; ncells = nc; lbase = cb; break; }
+        }
     }
     ok = ok && shift >= 0;
     for (int e = threadIdx.x; e <= L && e <= a.ent_cap; e += blockDim.x) {
-        LayerEnt le;
-        const uint32_t hi = e >= 1 ? (uint32_t)__half_as_ushort(__float2half_rn(s_bounds[e - 1].y)) : 0xFC00u;   // -inf
-        const uint32_t lo = e <= L - 1 ? (uint32_t)__half_as_ushort(__float2half_rn(s_bounds[e].x)) : 0x7C00u;    // +inf
         auto biased4 = [&](int o) { return (uint32_t)(((o * 2 < a.W ? o : o - a.W) + a.key_pad) * 4) & 0xffffu; };
         const uint32_t o0 = e >= 1 ? biased4(wrap_mod(s_off[e - 1], a.W)) : 0u;
         const uint32_t o1 = e <= L - 1 ? biased4(wrap_mod(s_off[e], a.W)) : 0u;
-        le.hi_lo = hi | (lo << 16);
-        le.off4 = (o0 & 0xffffu) | (o1 << 16);
-        ent[e] = le;
+        if (f32) {
+            LayerEnt32 le;
+            le.hi_prev = e >= 1 ? s_bounds[e - 1].y : -INFINITY;
+            le.lo_cur = e <= L - 1 ? s_bounds[e].x : INFINITY;
+            le.off4 = (o0 & 0xffffu) | (o1 << 16);
+            le.pad = 0u;
+            ent32[e] = le;
+        } else {
+            LayerEnt le;
+            const uint32_t hi = e >= 1 ? (uint32_t)__half_as_ushort(__float2half_rn(s_bounds[e - 1].y)) : 0xFC00u;   // -inf
+            const uint32_t lo = e <= L - 1 ? (uint32_t)__half_as_ushort(__float2half_rn(s_bounds[e].x)) : 0x7C00u;    // +inf
+            le.hi_lo = hi | (lo << 16);
+            le.off4 = (o0 & 0xffffu) | (o1 << 16);
+            ent[e] = le;
+        }
     }
     if (threadIdx.x == 0) {
         hdr->fill_off = fill_off;
-        hdr->shift = ok ? (uint32_t)shift : 0u;
+        hdr->shift = ok ? ((uint32_t)shift | (lbase << 8)) : 0u;
         hdr->ncells = ok ? ncells : 0u;
         hdr->flags = (ok ? 1u : 0u) | ((uint32_t)L << 8);
         tab->fast = ok ? 1u : 0u;

@@ -195,6 +195,7 @@ struct vrsbs_ctx {
     int ws_scatter_warps = 4;            // option: scatter warps of k_warp_ws (3, 4 or 5 of 8 warps); 4 measured best (9- and 10-warp CTAs were slower
                                          // and are no longer built)
     int commit_mode = 1;                 // experiments: 1 = commit + strip, 0 = strip only, 3 = commit only, 2 = neither
+    int f32_fast = 1;                    // option: 1 = vectorised fp32 depth pass and the warp-specialised warp kernel for fp32 depth when they fit
     int warp_ws = 1;                     // option: 1 = warp-specialised warp kernel (k_warp_ws) when it fits, 0 = k_warp_fused
     int lowres_tiled = 1;                // option: 0 = one-pixel-per-thread bicubic kernel (tests)
     int smooth_in_warp = 0;              // option: 1 = smoothing recomputed inside the warp kernel (no smoothed depth in HBM);
@@ -282,7 +283,7 @@ int alloc_scratch(vrsbs_ctx *c, Scratch &s, int cap_batch) {
     CU_TRY(c, dmalloc(&s.hi16, B * L));
     CU_TRY(c, dmalloc(&s.hole_mask, mask_words));
     CU_TRY(c, dmalloc(&s.hole_list, mask_words));
-    CU_TRY(c, dmalloc(&s.blobs, B * (size_t)blob_bytes(kEntCapMax, kLutCapMax)));
+    CU_TRY(c, dmalloc(&s.blobs, B * (size_t)blob_bytes(kEntCapMax, kLutCapMax, true)));
     return VRSBS_OK;
 }
 
@@ -369,7 +370,10 @@ int launch_depth(vrsbs_ctx *c, Scratch &s, const void *raw_v, const __half *lowr
         const size_t smem32 = sizeof(uint32_t) * 2 * B;
         dim3 grid((W + 31) / 32, (H + 7) / 8);
         StageTimer timer(c, st, 0);
-        if (raw_v) k_depth_f32<false, true><<<grid, 256, smem32, st>>>(a);
+        const size_t n32 = (size_t)H * W;
+        if (raw_v && n32 % 4 == 0 && ((uintptr_t)raw_v % 16 == 0) && ((uintptr_t)out_v % 16 == 0) && c->f32_fast)
+            k_depth_pass_f32<<<(unsigned)((n32 / 4 + 255) / 256), 256, smem32, st>>>(a);
+        else if (raw_v) k_depth_f32<false, true><<<grid, 256, smem32, st>>>(a);
         else if (c->bicubic_contract) k_depth_f32<true, true><<<grid, 256, smem32, st>>>(a);
         else k_depth_f32<true, false><<<grid, 256, smem32, st>>>(a);
         CU_TRY(c, cudaGetLastError());
@@ -537,20 +541,20 @@ int launch_fused_inst(vrsbs_ctx *c, const FusedArgs &a, cudaStream_t st) {
 
 // warp-specialised variant: 5 scatter + 3 destination warps; used when it reaches the same residency as k_warp_fused
 // (4 CTAs per SM), the mask row fits the destination warps and the key-row bound fits the scatter warps
-template <int NT, int NS>
+template <int NT, int NS, bool F32 = false>
 int launch_ws_inst(vrsbs_ctx *c, const FusedArgs &a, cudaStream_t st, bool *launched) {
     *launched = false;
     const int wwords32 = ((a.W + 31) / 32 + 31) / 32 * 32;
     if (a.W % 32 != 0 || a.key_pad > 32 * NS || wwords32 > (NT / 32 - NS) * 32) return VRSBS_OK;
     WsArgs w{};
     w.f = a;
-    w.lay = ws_smem_layout(a.W, a.blob_bytes);
-    auto kern = k_warp_ws<NT, NS>;
+    w.lay = ws_smem_layout(a.W, a.blob_bytes, F32 ? 4 : 2);
+    auto kern = k_warp_ws<NT, NS, F32>;
     if (w.lay.total > 200 * 1024) return VRSBS_OK;
     CU_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.lay.total));
     int occ = 0;
     CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, w.lay.total));
-    if (occ * NT < 1024) return VRSBS_OK;             // fewer than 32 resident warps per SM: k_warp_fused does better
+    if (occ * NT < (F32 ? 512 : 1024)) return VRSBS_OK;   // too few resident warps per SM: k_warp_fused / k_warp_rows do better
     if (c->blocks_per_sm > 0 && c->blocks_per_sm < occ) occ = c->blocks_per_sm;
     long long iters = (long long)a.B * a.H, grid = (long long)c->sm_count * occ;
     if (grid > iters) grid = iters;
@@ -562,6 +566,7 @@ int launch_ws_inst(vrsbs_ctx *c, const FusedArgs &a, cudaStream_t st, bool *laun
     return VRSBS_OK;
 }
 int launch_ws(vrsbs_ctx *c, const FusedArgs &a, cudaStream_t st, bool *launched) {
+    if (c->f32) return a.W > 2048 ? launch_ws_inst<512, 8, true>(c, a, st, launched) : launch_ws_inst<256, 4, true>(c, a, st, launched);
     if (a.W > 2048) {                                  // 4K rows: 2 CTAs of 16 warps per SM (shared memory bound)
         switch (c->ws_scatter_warps) {
             case 3: return launch_ws_inst<512, 6>(c, a, st, launched);
@@ -710,7 +715,7 @@ FusedArgs make_fused_args(vrsbs_ctx *c, Scratch &s, const uint8_t *frames, const
     a.B = B; a.H = H; a.W = W; a.Lcap = c->max_layers; a.Wwords = (W + 31) / 32;
     a.first = 0;
     a.skip_right = c->skip_right;
-    a.blob_bytes = blob_bytes(c->ent_cap, c->lut_cap); a.ent_bytes = blob_ent_bytes(c->ent_cap); a.key_pad = c->key_pad;
+    a.blob_bytes = blob_bytes(c->ent_cap, c->lut_cap, c->f32 != 0); a.ent_bytes = blob_ent_bytes(c->ent_cap, c->f32 != 0); a.key_pad = c->key_pad;
     a.w0 = c->sw.w_now; a.w1 = c->sw.w_prev1; a.w2 = c->sw.w_prev2;
     const FusedSmem L = fused_smem_layout(W, a.blob_bytes);
     a.lay.img = (uint32_t)L.img; a.lay.img_stride = (uint32_t)L.img_stride; a.lay.dep = (uint32_t)L.dep; a.lay.dep_stride = (uint32_t)L.dep_stride;
@@ -726,8 +731,18 @@ int launch_warp(vrsbs_ctx *c, Scratch &s, const uint8_t *frames, const void *dep
     if (rc) return rc;
     if ((rc = fresh_hole_list(c, s, st))) return rc;
     const __half *depth = static_cast<const __half *>(depth_v);
-    if (c->f32) {                                           // fp32 depth: the general row kernel, comparison in fp32
-        WarpArgs a{};
+    if (c->f32) {                                           // fp32 depth, comparison in fp32
+        const bool al = (W % 32 == 0) && ((uintptr_t)frames % 16 == 0) && ((uintptr_t)depth_v % 16 == 0) && ((uintptr_t)sbs % 16 == 0);
+        if (c->f32_fast && c->fused && c->warp_ws && al && c->ent_cap > 0) {      // the warp-specialised kernel's fp32 instantiation
+            FusedArgs fa = make_fused_args(c, s, frames, depth, B, H, W, sbs);
+            bool done = false;
+            if ((rc = launch_ws(c, fa, st, &done))) return rc;
+            if (done) {
+                if (!c->params.blur) return VRSBS_OK;
+                return launch_blur(c, s, frames, B, H, W, sbs, st);
+            }
+        }
+        WarpArgs a{};                                       // the general row kernel
         a.frames = frames; a.depth = depth_v; a.sbs = sbs; a.tabs = s.tabs; a.bounds = s.bounds; a.offm = s.offm;
         a.hole_mask = s.hole_mask; a.B = B; a.H = H; a.W = W; a.Lcap = c->max_layers; a.Wwords = (W + 31) / 32;
         a.hole_list = s.hole_list; a.hole_count = s.hole_count;
@@ -1542,6 +1557,7 @@ int vrsbs_set_option(vrsbs_ctx *c, const char *name, int value) {
     else if (!strcmp(name, "lowres_tiled")) c->lowres_tiled = value != 0;
     else if (!strcmp(name, "warp_ws")) c->warp_ws = value != 0;
     else if (!strcmp(name, "commit_mode")) c->commit_mode = value;
+    else if (!strcmp(name, "f32_fast")) c->f32_fast = value ? 1 : 0;
     else if (!strcmp(name, "blur_screen")) c->blur_screen = value ? 1 : 0;
     else if (!strcmp(name, "blur_sep")) c->blur_sep = value;
     else if (!strcmp(name, "pdl")) c->pdl = value & 15;

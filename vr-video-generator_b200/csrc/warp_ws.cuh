@@ -31,11 +31,11 @@ struct WsLay {               // shared-memory layout of k_warp_ws as kernel para
 constexpr int kWsImgSlots = 3, kWsDepSlots = 3;
 constexpr int kBarFull = 2, kBarEmpty = 4;      // named barriers 2,3: key row complete; 4,5: key row free again (1: destination group)
 
-__host__ inline WsLay ws_smem_layout(int W, uint32_t blob_b) {
+__host__ inline WsLay ws_smem_layout(int W, uint32_t blob_b, int depth_bytes = 2) {
     WsLay s{};
     size_t o = 0;
     s.img = (uint32_t)o;  s.img_stride = (uint32_t)align_up((size_t)W * 3 + 16, 128);  o += kWsImgSlots * s.img_stride;
-    s.dep = (uint32_t)o;  s.dep_stride = (uint32_t)align_up((size_t)W * 2, 128);       o += kWsDepSlots * s.dep_stride;
+    s.dep = (uint32_t)o;  s.dep_stride = (uint32_t)align_up((size_t)W * depth_bytes, 128);   o += kWsDepSlots * s.dep_stride;
     s.out = (uint32_t)o;  o += align_up((size_t)W * 3 + 16, 128);
     s.keys = (uint32_t)o; s.keys_stride = (uint32_t)align_up((size_t)W * 4, 128);      o += 2 * s.keys_stride;
     s.blob = (uint32_t)o; s.blob_stride = (uint32_t)align_up((size_t)blob_b, 128);     o += 2 * s.blob_stride;
@@ -74,8 +74,12 @@ __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int NT, int NS>
-__global__ void __launch_bounds__(NT, 1024 / NT) k_warp_ws(WsArgs wa) {
+// F32: the smoothed depth is fp32 (what torch >= 2.4's autocast hands the reference's warp), compared in fp32 against the
+// double -> float narrowed bounds.  Same kernel; the differences are the depth row (4 bytes per pixel: three CTAs per SM
+// instead of four), the cell of the LUT (fp32 bits >> shift, counted from the cell of `base`; everything below is one cell,
+// every negative value the last one), 16-byte layer entries with the two bounds as floats, and two fp32 compares.
+template <int NT, int NS, bool F32 = false>
+__global__ void __launch_bounds__(NT, F32 ? 768 / NT : 1024 / NT) k_warp_ws(WsArgs wa) {
     const FusedArgs &a = wa.f;
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int NW = NT / 32, ND = NW - NS, NDT = ND * 32;
@@ -85,7 +89,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_ws(WsArgs wa) {
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = a.W, H = a.H, B = a.B;
-    const uint32_t img_bytes = (uint32_t)W * 3, dep_bytes = (uint32_t)W * 2, W4 = (uint32_t)W * 4;
+    const uint32_t img_bytes = (uint32_t)W * 3, dep_bytes = (uint32_t)W * (F32 ? 4u : 2u), W4 = (uint32_t)W * 4;
     const int nseg = W >> 5, nquad = W >> 2, Wwords = a.Wwords;
 
     const long long F = (long long)B * H;
@@ -129,7 +133,9 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_ws(WsArgs wa) {
             const uint4 hdrw = lds_u128(sa_blob);
             if (hdrw.w & 1u) {
                 const uint32_t sa_ent = sa_blob + 16u, sa_lut = sa_ent + a.ent_bytes;
-                const uint32_t lut_sh = hdrw.y, lut_last = sa_lut + hdrw.z;        // cell = fp16 bits >> shift; the last cell = every negative value
+                const uint32_t lut_sh = hdrw.y & 0xffu, lut_last = sa_lut + hdrw.z;   // cell = depth bits >> shift; the last cell = every negative value
+                const uint32_t lut_base = hdrw.y >> 8;                            // F32: cells are counted from this one (everything below is cell 0)
+                const uint32_t sa_lut0 = sa_lut - lut_base;
                 const uint32_t sa_keys_lo = sa_keys - 4u * (uint32_t)a.key_pad;
                 auto batch = [&](auto Uc, auto Wc, int round0) {
                     constexpr int U = decltype(Uc)::value;
@@ -140,7 +146,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_ws(WsArgs wa) {
                         const int seg = (round0 + u) * NS + warp;
                         const int x = (seg << 5) + lane;
                         x4[u] = (uint32_t)x * 4u;
-                        c[u] = lds_u16(sa_cur + 2u * x);
+                        c[u] = F32 ? lds_u32(sa_cur + 4u * x) : lds_u16(sa_cur + 2u * x);
                         const uint32_t ia = sa_img + 96u * (uint32_t)seg;
                         w0[u] = lds_u32(ia);
                         w1[u] = lds_u32(ia + 4u);
@@ -148,18 +154,26 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_ws(WsArgs wa) {
                     uint32_t dd[U], e[U];
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        asm("mov.b32 %0, {%1, %1};" : "=r"(dd[u]) : "h"((unsigned short)c[u]));
-                        e[u] = lds_u8(min((c[u] >> lut_sh) + sa_lut, lut_last));
+                        if (F32) {
+                            dd[u] = c[u];
+                            e[u] = lds_u8(min(max(c[u] >> lut_sh, lut_base) + sa_lut0, lut_last));
+                        } else {
+                            asm("mov.b32 %0, {%1, %1};" : "=r"(dd[u]) : "h"((unsigned short)c[u]));
+                            e[u] = lds_u8(min((c[u] >> lut_sh) + sa_lut, lut_last));
+                        }
                     }
-                    uint2 en[U];
+                    uint4 en[U];
 #pragma unroll
-                    for (int u = 0; u < U; ++u) en[u] = lds_u64(sa_ent + 8u * e[u]);
+                    for (int u = 0; u < U; ++u) {
+                        if (F32) en[u] = lds_u128(sa_ent + 16u * e[u]);
+                        else { const uint2 t = lds_u64(sa_ent + 8u * e[u]); en[u] = make_uint4(t.x, 0u, t.y, 0u); }
+                    }
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
                         // key = layer byte | RGB: one PRMT on the funnel-shifted pixel word; a0 = kb + low half of the offset pair (one dp2a)
                         const uint32_t key0 = __byte_perm(__funnelshift_r(w0[u], w1[u], wsh), e[u], 0x4210);
                         const uint32_t kb = sa_keys_lo + x4[u];
-                        uint32_t a0 = __dp2a_lo(en[u].y, 1u, kb), a1 = kb + (en[u].y >> 16);
+                        uint32_t a0 = __dp2a_lo(en[u].z, 1u, kb), a1 = kb + (en[u].z >> 16);
                         if (WRAP) {                              // see k_warp_fused: first segment left end, last two right end
                             uint32_t q0 = a0 - sa_keys, q1 = a1 - sa_keys;
                             if (u == 0) { q0 = min(q0, q0 + W4); q1 = min(q1, q1 + W4); }
@@ -168,11 +182,17 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_ws(WsArgs wa) {
                             a1 = sa_keys + q1;
                         }
                         uint32_t k0, k1;
-                        asm("{\n\t.reg .pred p, q;\n\t"
-                            "setp.lt.f16x2 p|q, %2, %3;\n\t"
-                            "selp.u32 %0, %4, 0, p;\n\t"
-                            "selp.u32 %1, 0, %5, q;\n\t}"
-                            : "=r"(k0), "=r"(k1) : "r"(dd[u]), "r"(en[u].x), "r"(key0), "r"(key0 + 0x01000000u));
+                        if (F32) {
+                            const float d = __uint_as_float(dd[u]);
+                            k0 = (d < __uint_as_float(en[u].x)) ? key0 : 0u;                 // member of layer e-1 iff d < hi(e-1)
+                            k1 = (d < __uint_as_float(en[u].y)) ? 0u : key0 + 0x01000000u;   // member of layer e iff !(d < lo(e))
+                        } else {
+                            asm("{\n\t.reg .pred p, q;\n\t"
+                                "setp.lt.f16x2 p|q, %2, %3;\n\t"
+                                "selp.u32 %0, %4, 0, p;\n\t"
+                                "selp.u32 %1, 0, %5, q;\n\t}"
+                                : "=r"(k0), "=r"(k1) : "r"(dd[u]), "r"(en[u].x), "r"(key0), "r"(key0 + 0x01000000u));
+                        }
                         asm volatile("red.shared.max.u32 [%0], %1;" :: "r"(a0), "r"(k0) : "memory");
                         asm volatile("red.shared.max.u32 [%0], %1;" :: "r"(a1), "r"(k1) : "memory");
                     }
@@ -198,7 +218,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_ws(WsArgs wa) {
                 const int *go = a.offm + (size_t)t0 * (a.Lcap + 1);
                 for (int seg = warp; seg < nseg; seg += NS) {
                     const int x = (seg << 5) + lane;
-                    const float d = __half2float(__ushort_as_half((unsigned short)lds_u16(sa_cur + 2u * x)));
+                    const float d = F32 ? __uint_as_float(lds_u32(sa_cur + 4u * x)) : __half2float(__ushort_as_half((unsigned short)lds_u16(sa_cur + 2u * x)));
                     for (int k = 0; k < L; ++k) {
                         const float2 bd = __ldg(gb + k);
                         if (bd.x <= d && d < bd.y) {
@@ -225,7 +245,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_warp_ws(WsArgs wa) {
             const uint32_t s3 = (uint32_t)(k % 3), bar = bar_in + 8u * s3;
             mbar_expect_tx_a(bar, img_bytes + dep_bytes + a.blob_bytes);
             bulk_g2s_a(sb + wa.lay.img + s3 * wa.lay.img_stride, a.frames + ((size_t)t * H + y) * img_bytes, img_bytes, bar);
-            bulk_g2s_a(sb + wa.lay.dep + s3 * wa.lay.dep_stride, a.depth + ((size_t)t * H + y) * W, dep_bytes, bar);
+            bulk_g2s_a(sb + wa.lay.dep + s3 * wa.lay.dep_stride, reinterpret_cast<const uint8_t *>(a.depth) + ((size_t)t * H + y) * dep_bytes, dep_bytes, bar);
             bulk_g2s_a(sb + wa.lay.blob + (uint32_t)(k & 1) * wa.lay.blob_stride, a.blobs + (size_t)t * a.blob_bytes, a.blob_bytes, bar);
         };
         if (loader) {
