@@ -479,10 +479,6 @@ __global__ void __launch_bounds__(256, 4) k_blur_sep(BlurArgs a, const __grid_co
     constexpr int NWORDS = (PHASE + 3 * NPX + 3) / 4;                 // aligned 32-bit words that cover the footprint
     constexpr int VCOLS = NWORDS * 4;
     constexpr int G = kBlurSepGroup;
-    // pixels per evaluation lane: with the small footprints a lane evaluates the pixel pair (2s, 2s+1) of a channel - the two
-    // share all but two of their V columns, and the task decode, rounding and store overhead (two thirds of a single-pixel
-    // pass) is paid once; a pair is listed when either pixel is a hole
-    constexpr int NP = CX <= 6 ? 2 : 1;
     static_assert(NWORDS <= 64 && VCOLS == blur_sep_vcols<CX>(), "footprint layout");
     extern __shared__ __align__(16) uint8_t blur_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -578,9 +574,8 @@ __global__ void __launch_bounds__(256, 4) k_blur_sep(BlurArgs a, const __grid_co
         for (int g = 0; g < G; ++g) {
             const uint32_t ent = __shfl_sync(0xffffffffu, ent_c, g), m = __shfl_sync(0xffffffffu, m_c, g);
             if (m == 0u) continue;
-            const uint32_t pm = NP == 2 ? ((m | (m >> 1)) & 0x55555555u) : m;
-            if ((pm >> lane) & 1u) tasktab[nholes + __popc(pm & ((1u << lane) - 1u))] = (uint16_t)((g << 8) | lane);
-            nholes += (uint32_t)__popc(pm);
+            if ((m >> lane) & 1u) tasktab[nholes + __popc(m & ((1u << lane) - 1u))] = (uint16_t)((g << 8) | lane);
+            nholes += (uint32_t)__popc(m);
             const int xw = (int)(ent & 0xffu) * 32;
             if (xw - CX >= 0 && xw + 31 + CX < W) continue;
             // border words: byte by byte with reflect padding (phase 0)
@@ -647,54 +642,30 @@ __global__ void __launch_bounds__(256, 4) k_blur_sep(BlurArgs a, const __grid_co
             const uint32_t code = tasktab[hidx];
             const uint32_t g = code >> 8, xo = code & 0xffu;
             const uint32_t ent = __shfl_sync(0xffffffffu, ent_c, g);
-            const uint32_t mk = NP == 2 ? (__shfl_sync(0xffffffffu, m_c, g) >> xo) & 3u : 1u;   // bit o: pixel xo + o is a hole
-            uint32_t q[NP];
-            bool open[NP];
-#pragma unroll
-            for (int o = 0; o < NP; ++o) { q[o] = 0u; open[o] = false; }
+            uint32_t q = 0u;
+            bool open = false;
             if (on) {
                 const uint32_t phase = ((border >> g) & 1u) ? 0u : (uint32_t)PHASE;
                 const uint32_t *Vc = Vw + g * VCOLS + phase + 3u * (xo + CX) + ch;
-                unsigned long long acc[NP];
-                if (NP == 1) {
-                    acc[0] = (unsigned long long)Vc[0] * wts.hx[0];
+                unsigned long long acc = (unsigned long long)Vc[0] * wts.hx[0];
 #pragma unroll
-                    for (int j = 1; j <= CX; ++j) acc[0] += (unsigned long long)(Vc[-3 * j] + Vc[3 * j]) * wts.hx[j];
-                } else {
-                    uint32_t u[2 * CX + NP];                                      // columns xo-CX .. xo+NP-1+CX, read once
-#pragma unroll
-                    for (int k = 0; k < 2 * CX + NP; ++k) u[k] = Vc[3 * (k - CX)];
-#pragma unroll
-                    for (int o = 0; o < NP; ++o) {
-                        acc[o] = (unsigned long long)u[CX + o] * wts.hx[0];
-#pragma unroll
-                        for (int j = 1; j <= CX; ++j) acc[o] += (unsigned long long)(u[CX + o - j] + u[CX + o + j]) * wts.hx[j];
-                    }
-                }
-#pragma unroll
-                for (int o = 0; o < NP; ++o) {
-                    const uint32_t r32 = (uint32_t)(acc[o] >> (wts.s - 32u));      // top 32 bits of the fractional part
-                    q[o] = (uint32_t)(acc[o] >> wts.s) + (r32 >> 31);
-                    open[o] = ((mk >> o) & 1u) && (r32 - 0x80000000u + wts.eps32 <= 2u * wts.eps32);   // within eps of a half-integer
-                }
+                for (int j = 1; j <= CX; ++j) acc += (unsigned long long)(Vc[-3 * j] + Vc[3 * j]) * wts.hx[j];
+                const uint32_t r32 = (uint32_t)(acc >> (wts.s - 32u));             // top 32 bits of the fractional part
+                q = (uint32_t)(acc >> wts.s) + (r32 >> 31);
+                open = r32 - 0x80000000u + wts.eps32 <= 2u * wts.eps32;            // within eps of a half-integer: exact sum decides
             }
             // undecided values, one at a time, by the whole warp
-#pragma unroll
-            for (int o = 0; o < NP; ++o) {
-                for (unsigned need = __ballot_sync(0xffffffffu, open[o]); need; need &= need - 1u) {
-                    const int src = __ffs(need) - 1;
-                    const uint32_t e_s = __shfl_sync(0xffffffffu, ent, src), x_s = __shfl_sync(0xffffffffu, xo, src), c_s = __shfl_sync(0xffffffffu, ch, src);
-                    int b, y, xw_;
-                    decode(e_s, b, y, xw_);
-                    const uint32_t qx = blur_exact_warp<PARTS, CX, CY>(a.sbs + (size_t)b * H * pitch, pitch, H, W, y, xw_ + (int)x_s + o, (int)c_s, a.wq, a.wshift);
-                    if (lane == src) q[o] = qx;
-                }
+            for (unsigned need = __ballot_sync(0xffffffffu, open); need; need &= need - 1u) {
+                const int src = __ffs(need) - 1;
+                const uint32_t e_s = __shfl_sync(0xffffffffu, ent, src), x_s = __shfl_sync(0xffffffffu, xo, src), c_s = __shfl_sync(0xffffffffu, ch, src);
+                int b, y, xw_;
+                decode(e_s, b, y, xw_);
+                const uint32_t qx = blur_exact_warp<PARTS, CX, CY>(a.sbs + (size_t)b * H * pitch, pitch, H, W, y, xw_ + (int)x_s, (int)c_s, a.wq, a.wshift);
+                if (lane == src) q = qx;
             }
             if (!on) continue;
             const uint32_t row = ent >> 8, xw = (ent & 0xffu) * 32u;
-            uint8_t *dst = a.plane + ((size_t)row * W + xw + xo) * 3 + ch;
-            if (mk & 1u) dst[0] = (uint8_t)q[0];
-            if (NP == 2 && (mk & 2u)) dst[3] = (uint8_t)q[NP - 1];
+            a.plane[((size_t)row * W + xw + xo) * 3 + ch] = (uint8_t)q;
         }
     }
 }
