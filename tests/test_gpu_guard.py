@@ -57,6 +57,7 @@ ROUTES = {
     "smooth_in_warp": {"smooth_in_warp": 1},
     "row_kernel_atomic": {"fused": 0, "scatter_mode": 2},
     "row_kernel_store": {"fused": 0, "scatter_mode": 1},
+    "blur_sep_per_word": {"blur_band": 0},
     "blur_fixed": {"blur_sep": 0},
     "blur_exact_only": {"blur_screen": 0},
 }

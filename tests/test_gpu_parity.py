@@ -704,11 +704,12 @@ def test_warp_specialised_splits(split, oracle_lib):
         ctx.close()
 
 
-@pytest.mark.parametrize("screen", ["sep", "sep_all_exact", "fixed", "fixed_exact"])
+@pytest.mark.parametrize("screen", ["band", "band_all_exact", "sep", "sep_all_exact", "fixed", "fixed_exact"])
 def test_blur_screening_is_exact(screen, oracle_lib):
-    """Every pixel a hole (zero depth), so the blur evaluates ~390k values per frame.  All four evaluation routes equal the
-    oracle bit for bit: the separable screening kernel with its exact fallback for the undecided values (default), the same
-    kernel with EVERY value sent to the fallback, the 2-D one-multiply screening kernel (blur_sep=0), and the exact 2-D sum
+    """Every pixel a hole (zero depth), so the blur evaluates ~390k values per frame.  All evaluation routes equal the
+    oracle bit for bit: the band-driven separable kernel (default at 1080p / 720p) and the per-word separable screening kernel,
+    each with its exact fallback for the undecided values and with EVERY value sent to the fallback, the 2-D one-multiply
+    screening kernel (blur_sep=0), and the exact 2-D sum
     for every value (blur_screen=0) - for the 1080p (11x9, 2 parts), 4K (19x17, 3 parts), 720p and 1440p gaussians, on
     random bytes, on a two-level image (sums cluster, more near-ties; 0/255 maximises the separable kernel's error) and on
     a constant image (every sum lands on the same near-integer)."""
@@ -721,7 +722,9 @@ def test_blur_screening_is_exact(screen, oracle_lib):
     raw = np.zeros((3, H, W), dtype=np.float16)
     for w in (O.gaussian_weights(11, 9), O.gaussian_weights(19, 17), O.gaussian_weights(9, 7), O.gaussian_weights(13, 11)):
         ctx = _ctx(H, W, 0.025, -0.01, 1, w)
-        ctx.set_option("blur_sep", {"sep": 1, "sep_all_exact": 2}.get(screen, 0))
+        # band: the band-driven kernel (default where it is built: 11x9 and 9x7; the other sizes take k_blur_sep)
+        ctx.set_option("blur_sep", {"band": 1, "band_all_exact": 2, "sep": 1, "sep_all_exact": 2}.get(screen, 0))
+        ctx.set_option("blur_band", 1 if screen.startswith("band") else 0)
         ctx.set_option("blur_screen", 0 if screen == "fixed_exact" else 1)
         sbs, _, infos, masks = _run_device(ctx, frames, raw)
         want, _ = _oracle_run(oracle_lib, dict(fg=0.025, bg=-0.01, step=1), frames, raw, w)

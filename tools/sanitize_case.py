@@ -1,7 +1,8 @@
 """Small end-to-end cases for compute-sanitizer (memcheck / racecheck / synccheck / initcheck): every route of the
 default and fallback kernels once, tiny frames.  modes: 0 default (k_warp_ws, LUT membership), 3 slow membership,
 4 smoothing inside k_warp_fused, 5 k_warp_fused without warp specialisation, 2 general row kernel (atomicMax),
-1 general row kernel (store + verify), 6 screening blur off (exact sums only), 7 k_blur_holes_fixed instead of k_blur_sep;
+1 general row kernel (store + verify), 6 screening blur off (exact sums only), 7 k_blur_holes_fixed instead of the separable
+kernels, 8 k_blur_sep (per mask word) instead of k_blur_band;
 plus a 2560-pixel-wide case for the 16-warp instantiation k_warp_ws<512,8> and the host pipeline (submit / collect)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -22,6 +23,7 @@ def run(frames, raw, p, weights, mode, max_layers=512):
     ctx.set_option("warp_ws", 0 if mode == 5 else 1)
     ctx.set_option("blur_screen", 0 if mode == 6 else 1)
     ctx.set_option("blur_sep", 0 if mode == 7 else 1)
+    ctx.set_option("blur_band", 0 if mode == 8 else 1)
     f = torch.from_numpy(np.ascontiguousarray(frames)).cuda(); r = torch.from_numpy(np.ascontiguousarray(raw)).cuda()
     out = torch.empty((n, H, 2 * W, 3), dtype=torch.uint8, device="cuda"); dep = torch.empty((n, H, W), dtype=torch.float16, device="cuda")
     ctx.process_batch(f.data_ptr(), r.data_ptr(), n, H, W, dep.data_ptr(), out.data_ptr(), torch.cuda.current_stream().cuda_stream)
@@ -31,7 +33,7 @@ def run(frames, raw, p, weights, mode, max_layers=512):
     return res
 
 
-modes = [int(m) for m in os.environ.get("SAN_MODES", "0,3,4,5,2,1,6,7").split(",")]
+modes = [int(m) for m in os.environ.get("SAN_MODES", "0,3,4,5,2,1,6,7,8").split(",")]
 for name in os.environ.get("SAN_CASES", "small_a,medium").split(","):
     meta, frames, raw, ref_left = load_case(name)
     p = meta["params"]; W = p["W"]

@@ -33,7 +33,16 @@ struct BlurArgs {
     const uint32_t *hole_mask;   // [B][H][Wwords]
     const uint32_t *hole_list;   // (global row << 8 | word index) of the mask words that contain holes
     const uint32_t *hole_count;
-    uint32_t *ticket;            // pre-zeroed work counter of k_blur_sep (next group of list entries)
+    uint32_t *ticket;            // pre-zeroed work counter of k_blur_sep / k_blur_band (next unit of work)
+    uint32_t *band_map;          // [B*Hb][band_groups] bit per band column (kBandRows rows x one mask word) that holds a hole: set by
+                                 // k_warp_ws (or k_band_map), turned into band_list - and zeroed again - by k_band_list
+    uint32_t *band_list;         // (frame * Hb + row band) << 8 | mask word column of every marked band column: the work list of
+                                 // k_blur_band and k_blur_commit
+    uint32_t *band_count;        // pre-zeroed
+    int band_groups;             // 32-word groups per row of band_map
+    int band_prepass;            // 1: the warp kernel did not mark the band columns, k_band_map does
+    int Hb;                      // row bands per frame, kBandRows rows each
+    unsigned long long magic_hb; // ceil(2^40 / Hb): frame = (band * magic_hb) >> 40
     uint8_t *plane;              // [B,H,W,3] scratch: blurred values of hole pixels
     const uint32_t *wq;          // integer path: [PARTS][(cy+1)][(cx+1)] parts of w * 2^S, low part first (i = |dy|, j = |dx|)
     const float *weights;        // generic: [ky][kx]
@@ -670,13 +679,243 @@ __global__ void __launch_bounds__(256, 4) k_blur_sep(BlurArgs a, const __grid_co
     }
 }
 
+// ---- band-driven hole blur for the small footprints (the footprint of a mask word fits 32 aligned words) ------------
+// k_blur_sep stages every listed mask word (32 pixels of ONE row) on its own: nine row loads, nine byte expansions and the
+// weighted sum per aligned word, although the word of the row below needs eight of the same nine rows.  Here the unit of
+// work is a BAND COLUMN - one mask word column over kBandRows = 8 consecutive rows of one frame: the warp walks the 8 + 2 CY
+// input rows once (lane = aligned word of the footprint), keeps them expanded in a register window, and emits the V columns
+// of every row of the band that has holes.  Per staged row that is CY + 1 packed additions and 4 (CY + 1) multiply-adds
+// instead of nine loads, eighteen expansions and the same arithmetic.  The evaluation (one horizontal pass per hole and
+// channel, undecided values exactly, by the whole warp) is k_blur_sep's.  The band columns that hold a hole are marked in a
+// bitmap - by k_warp_ws itself, one fire-and-forget OR per row (it then needs no slot from a global counter for a per-word
+// list: 0.260 instead of 0.278 ms), or by k_band_map from the hole mask behind the other warp kernels; k_band_list compacts the
+// bitmap into the work list of k_blur_band and k_blur_commit.  Results are bit-identical to k_blur_sep (same integer sums).
+constexpr int kBandRows = 8;
+static_assert(kBandRows == kBlurSepGroup, "a band's rows use the V buffers of a k_blur_sep group");
+
+__global__ void __launch_bounds__(256) k_band_map(BlurArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const long long total = (long long)a.B * a.Hb * a.Wwords;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int w = (int)(idx % a.Wwords);
+    const long long q = idx / a.Wwords;                           // frame * Hb + band
+    const int t = (int)(q / a.Hb), yb = (int)(q - (long long)t * a.Hb);
+    const uint32_t *mp = a.hole_mask + ((size_t)t * a.H + (size_t)yb * kBandRows) * a.Wwords + w;
+    uint32_t any = 0u;
+#pragma unroll
+    for (int r = 0; r < kBandRows; ++r)
+        if (yb * kBandRows + r < a.H) any |= mp[(size_t)r * a.Wwords];
+    if (any) atomicOr(a.band_map + (size_t)q * a.band_groups + (w >> 5), 1u << (w & 31));
+}
+
+// band map -> band list (and the map is zero again): one thread per map word, list slots by one atomic per warp
+__global__ void __launch_bounds__(256) k_band_list(BlurArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const uint32_t nwords = (uint32_t)a.B * (uint32_t)a.Hb * (uint32_t)a.band_groups;
+    const uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    uint32_t bits = wi < nwords ? a.band_map[wi] : 0u;
+    if (bits) a.band_map[wi] = 0u;
+    const uint32_t cnt = (uint32_t)__popc(bits);
+    uint32_t incl = cnt;                                          // inclusive prefix sum over the warp
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0u) return;
+    uint32_t base = 0;
+    if (lane == 31) base = atomicAdd(a.band_count, total);
+    base = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
+    const uint32_t q = wi / (uint32_t)a.band_groups, g = wi - q * (uint32_t)a.band_groups;
+    for (; bits; bits &= bits - 1u) a.band_list[base++] = (q << 8) | (32u * g + (uint32_t)__ffs((int)bits) - 1u);
+}
+
+template <int PARTS, int CX, int CY>
+__global__ void __launch_bounds__(256, 4) k_blur_band(BlurArgs a, const __grid_constant__ BlurSepWeights<CX, CY> wts) {
+    constexpr int KX = 2 * CX + 1, NPX = 32 + KX - 1;
+    constexpr int PHASE = ((-3 * CX) % 4 + 4) % 4;
+    constexpr int NWORDS = (PHASE + 3 * NPX + 3) / 4;
+    constexpr int VCOLS = NWORDS * 4;
+    constexpr int RB = kBandRows, NR = RB + 2 * CY;                   // rows of a band, input rows it reads
+    static_assert(NWORDS <= 32 && VCOLS == blur_sep_vcols<CX>(), "one aligned word of the footprint per lane");
+    extern __shared__ __align__(16) uint8_t blur_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int W = a.W, H = a.H;
+    uint32_t *Vw = reinterpret_cast<uint32_t *>(blur_smem) + (size_t)warp * (RB * (VCOLS + 16));
+    uint16_t *tasktab = reinterpret_cast<uint16_t *>(Vw + RB * VCOLS);   // [RB * 32]: (row of the band << 8 | pixel) of every hole
+    pdl_launch_dependents();
+    pdl_wait();                                  // the band list
+    const uint32_t count = *a.band_count;
+    const size_t pitch = (size_t)W * 6;
+
+    // unit metadata, one unit ahead: lane r (< RB) holds the mask word of row r of the band column (strip columns removed)
+    auto fetch_meta = [&](uint32_t u, uint32_t &code, uint32_t &m) {
+        code = 0u; m = 0u;
+        if (u >= count) return;
+        code = a.band_list[u];
+        const uint32_t q = code >> 8, w = code & 0xffu;
+        const int t = (int)(((unsigned long long)q * a.magic_hb) >> 40), y = ((int)q - t * a.Hb) * RB + lane;
+        if (lane < RB && y < H) {
+            const int strip = a.tabs[t].strip, xw = (int)w * 32;
+            m = a.hole_mask[((size_t)t * H + y) * a.Wwords + w];
+            if (strip > xw) m = (strip - xw >= 32) ? 0u : (m & ~((1u << (strip - xw)) - 1u));
+        }
+    };
+    auto grab = [&]() -> uint32_t { return lane == 0 ? atomicAdd(a.ticket, 1u) : 0u; };
+    uint32_t t_a = __shfl_sync(0xffffffffu, grab(), 0);
+    uint32_t t_b_raw = grab();
+    uint32_t code_n, m_n;
+    fetch_meta(t_a, code_n, m_n);
+    for (;;) {
+        if (t_a >= count) break;
+        const uint32_t code = code_n, m_c = m_n;
+        t_a = __shfl_sync(0xffffffffu, t_b_raw, 0);
+        fetch_meta(t_a, code_n, m_n);
+        t_b_raw = grab();
+        const uint32_t q = code >> 8;
+        const int t = (int)(((unsigned long long)q * a.magic_hb) >> 40), y0 = ((int)q - t * a.Hb) * RB, xw = (int)(code & 0xffu) * 32;
+        const uint8_t *left = a.sbs + (size_t)t * H * pitch;
+        const uint32_t rmask = __ballot_sync(0xffffffffu, m_c != 0u) & ((1u << RB) - 1u);   // rows of the band that have holes
+        __syncwarp();
+        // ---- hole table of the band column ----
+        uint32_t nholes = 0;
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+            const uint32_t m = __shfl_sync(0xffffffffu, m_c, r);
+            if (m == 0u) continue;
+            if ((m >> lane) & 1u) tasktab[nholes + __popc(m & ((1u << lane) - 1u))] = (uint16_t)((r << 8) | lane);
+            nholes += (uint32_t)__popc(m);
+        }
+        const bool border = !(xw - CX >= 0 && xw + 31 + CX < W);
+        if (!border) {
+            // ---- vertical pass over the band: input rows y0 - CY .. y0 + RB - 1 + CY, expanded once, window in registers ----
+            uint32_t need = 0u;                                       // input rows some hole row reads
+#pragma unroll
+            for (int i = 0; i <= 2 * CY; ++i) need |= rmask << i;
+            const uint8_t *colp = left + (3 * (xw - CX) - PHASE) + 4 * lane;
+            const bool wl = NWORDS >= 32 || lane < NWORDS;
+            uint32_t raw[NR];
+#pragma unroll
+            for (int j = 0; j < NR; ++j)
+                raw[j] = (wl && ((need >> j) & 1u)) ? __ldg(reinterpret_cast<const uint32_t *>(colp + (size_t)reflect_idx(y0 - CY + j, H) * pitch)) : 0u;
+            uint32_t lo[NR], hi[NR];
+#pragma unroll
+            for (int j = 0; j < NR; ++j) {
+                lo[j] = __byte_perm(raw[j], 0u, 0x4140);
+                hi[j] = __byte_perm(raw[j], 0u, 0x4342);
+                if (j >= 2 * CY) {
+                    const int r = j - 2 * CY, c = j - CY;
+                    if ((rmask >> r) & 1u) {
+                        uint32_t V0 = (lo[c] & 0xffffu) * wts.hy[0], V1 = (lo[c] >> 16) * wts.hy[0];
+                        uint32_t V2 = (hi[c] & 0xffffu) * wts.hy[0], V3 = (hi[c] >> 16) * wts.hy[0];
+#pragma unroll
+                        for (int i = 1; i <= CY; ++i) {
+                            const uint32_t l = lo[c - i] + lo[c + i], h = hi[c - i] + hi[c + i];
+                            V0 += (l & 0xffffu) * wts.hy[i]; V1 += (l >> 16) * wts.hy[i];
+                            V2 += (h & 0xffffu) * wts.hy[i]; V3 += (h >> 16) * wts.hy[i];
+                        }
+                        if (wl) *reinterpret_cast<uint4 *>(Vw + r * VCOLS + 4 * lane) = make_uint4(V0, V1, V2, V3);
+                    }
+                }
+            }
+        } else {
+            // border band columns: byte by byte with reflect padding (phase 0), row by row
+#pragma unroll 1
+            for (int r = 0; r < RB; ++r) {
+                if (!((rmask >> r) & 1u)) continue;
+                const int y = y0 + r;
+                uint32_t *V = Vw + r * VCOLS;
+                for (int c = lane; c < 3 * NPX; c += 32) {
+                    const int px = c / 3, ch = c - px * 3;
+                    const int X = min(max(reflect_idx(xw - CX + px, W), 0), W - 1);
+                    const uint8_t *cp = left + (size_t)X * 3 + ch;
+                    uint32_t acc = (uint32_t)cp[(size_t)y * pitch] * wts.hy[0];
+#pragma unroll
+                    for (int i = 1; i <= CY; ++i)
+                        acc += ((uint32_t)cp[(size_t)reflect_idx(y - i, H) * pitch] + (uint32_t)cp[(size_t)reflect_idx(y + i, H) * pitch]) * wts.hy[i];
+                    V[c] = acc;
+                }
+            }
+        }
+        __syncwarp();
+        // ---- evaluate: task = (hole of the band column, channel), 32 tasks per pass ----
+        const uint32_t tasks = 3u * nholes, phase = border ? 0u : (uint32_t)PHASE;
+        for (uint32_t t0 = 0; t0 < tasks; t0 += 32) {
+            const uint32_t task = t0 + lane;
+            const bool on = task < tasks;
+            const uint32_t hidx = on ? task / 3u : 0u, ch = task - hidx * 3u;
+            const uint32_t tc = tasktab[hidx];
+            const uint32_t g = tc >> 8, xo = tc & 0xffu;
+            uint32_t qv = 0u;
+            bool open = false;
+            if (on) {
+                const uint32_t *Vc = Vw + g * VCOLS + phase + 3u * (xo + CX) + ch;
+                unsigned long long acc = (unsigned long long)Vc[0] * wts.hx[0];
+#pragma unroll
+                for (int j = 1; j <= CX; ++j) acc += (unsigned long long)(Vc[-3 * j] + Vc[3 * j]) * wts.hx[j];
+                const uint32_t r32 = (uint32_t)(acc >> (wts.s - 32u));             // top 32 bits of the fractional part
+                qv = (uint32_t)(acc >> wts.s) + (r32 >> 31);
+                open = r32 - 0x80000000u + wts.eps32 <= 2u * wts.eps32;            // within eps of a half-integer: exact sum decides
+            }
+            for (unsigned todo = __ballot_sync(0xffffffffu, open); todo; todo &= todo - 1u) {
+                const int src = __ffs(todo) - 1;
+                const uint32_t g_s = __shfl_sync(0xffffffffu, g, src), x_s = __shfl_sync(0xffffffffu, xo, src), c_s = __shfl_sync(0xffffffffu, ch, src);
+                const uint32_t qx = blur_exact_warp<PARTS, CX, CY>(left, pitch, H, W, y0 + (int)g_s, xw + (int)x_s, (int)c_s, a.wq, a.wshift);
+                if (lane == src) qv = qx;
+            }
+            if (!on) continue;
+            a.plane[(((size_t)t * H + y0 + g) * W + xw + xo) * 3 + ch] = (uint8_t)qv;
+        }
+        __syncwarp();                                 // the next unit rewrites the hole table and the V rows
+    }
+}
+
 // plane -> SBS frame for the listed holes right of the strip, then result_img[:, 0:strip] = img[:, 0:strip]
 // (PredictAndGenerate.py:196).  A warp takes 32 list entries at a time: lane l fetches entry l's word index, mask
 // and strip (one round of dependent loads for 32 entries), then the warp walks the entries, lane = pixel.
-__global__ void __launch_bounds__(256) k_blur_commit(BlurArgs a, int do_commit) {
+__global__ void __launch_bounds__(256, 6) k_blur_commit(BlurArgs a, int do_commit) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     pdl_wait();                                  // every blurred value is in the plane
-    const uint32_t count = (do_commit & 1) ? *a.hole_count : 0u;      // do_commit: bit 0 = hole values, bit 1 = skip the strip (experiments)
+    if ((do_commit & 1) && (do_commit & 4)) {
+        // band-driven (do_commit bit 2: k_blur_band ran, band_list is valid): a warp per band column - the eight mask words in
+        // one round of loads, then lane = pixel for each row; eight independent load chains per lane instead of four
+        const uint32_t count = *a.band_count;
+        for (uint32_t u = blockIdx.x * nwarps + warp; u < count; u += gridDim.x * nwarps) {
+            const uint32_t code = a.band_list[u];
+            const uint32_t q = code >> 8, w = code & 0xffu;
+            const int t = (int)(((unsigned long long)q * a.magic_hb) >> 40), y0 = ((int)q - t * a.Hb) * kBandRows;
+            uint32_t m = 0u;
+            if (lane < kBandRows && y0 + lane < a.H) {
+                const int strip = a.tabs[t].strip, xw = (int)w * 32;
+                m = a.hole_mask[((size_t)t * a.H + y0 + lane) * a.Wwords + w];
+                if (strip > xw) m = (strip - xw >= 32) ? 0u : (m & ~((1u << (strip - xw)) - 1u));
+            }
+            const size_t px0 = ((size_t)t * a.H + y0) * a.W + w * 32u + lane;
+            uint32_t val[kBandRows];
+            bool on[kBandRows];
+#pragma unroll
+            for (int r = 0; r < kBandRows; ++r) {
+                on[r] = (__shfl_sync(0xffffffffu, m, r) >> lane) & 1u;
+                val[r] = 0u;
+                if (on[r]) {
+                    const uint8_t *src = a.plane + (px0 + (size_t)r * a.W) * 3;
+                    val[r] = (uint32_t)src[0] | ((uint32_t)src[1] << 8) | ((uint32_t)src[2] << 16);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < kBandRows; ++r)
+                if (on[r]) {
+                    uint8_t *dst = a.sbs + (((size_t)t * a.H + y0 + r) * 2 * a.W + w * 32u + lane) * 3;
+                    dst[0] = (uint8_t)val[r]; dst[1] = (uint8_t)(val[r] >> 8); dst[2] = (uint8_t)(val[r] >> 16);
+                }
+        }
+    }
+    const uint32_t count = ((do_commit & 1) && !(do_commit & 4)) ? *a.hole_count : 0u;   // do_commit: bit 0 = hole values, bit 1 = skip the strip (experiments)
     constexpr int E = 4;                                   // entries per warp step: four independent load chains in flight
     for (uint32_t e0 = (blockIdx.x * nwarps + warp) * E; e0 < count; e0 += gridDim.x * nwarps * E) {
         uint32_t gw = 0, m = 0, strip = 0;

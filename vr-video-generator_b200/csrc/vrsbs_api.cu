@@ -30,7 +30,7 @@ namespace {
 thread_local char g_create_error[256] = "";
 
 struct Scratch {                 // per-batch device scratch; one per pipeline slot
-    uint32_t *frame_max = nullptr, *frame_nan = nullptr;   // one allocation: [B] max | [B] nan | [1] hole_count | [1] blur ticket
+    uint32_t *frame_max = nullptr, *frame_nan = nullptr;   // one allocation: [B] max | [B] nan | [1] hole_count | [1] blur ticket | [1] band count
     FrameTab *tabs = nullptr;
     float2 *bounds = nullptr;
     int *offm = nullptr;
@@ -39,6 +39,10 @@ struct Scratch {                 // per-batch device scratch; one per pipeline s
     uint16_t *lo16 = nullptr, *hi16 = nullptr;
     uint32_t *hole_mask = nullptr;
     uint32_t *hole_list = nullptr;   // mask words that contain holes (blur work list)
+    uint32_t *band_map = nullptr;    // bit per band column (8 rows x one mask word) with a hole; all zero between batches (set by k_warp_ws or
+                                     // k_band_map, compacted into band_list and cleared by k_band_list)
+    uint32_t *band_list = nullptr;   // the marked band columns: work list of k_blur_band and k_blur_commit
+    bool band_marked = false;        // the last warp launch marked the band columns itself (otherwise k_band_map does)
     uint32_t *hole_count = nullptr;  // points into frame_max's allocation: one memset clears all three
     uint8_t *blobs = nullptr;        // [B][kBlobMax] fast-path tables
     uint8_t *plane = nullptr;        // [B,H,W,3] blurred hole values (allocated on first blur)
@@ -184,6 +188,7 @@ struct vrsbs_ctx {
     std::vector<uint32_t> sep_hy, sep_hx;     // separable screening kernel of k_blur_sep (scale 2^sep_s), empty if the weights are not near rank 1
     uint32_t sep_s = 0, sep_eps32 = 0;
     int blur_sep = 1;
+    int blur_band = 1;                        // option: 1 = band-driven k_blur_band for the footprints it is built for (1080p, 720p)
     int pdl = 0;                              // option (bit mask): programmatic dependent launch of 1 tables, 2 warp, 4 blur, 8 commit.
                                               // Measured slower than plain stream order with all four edges on (0.532 vs 0.512 ms per
                                               // 1080p step), so off by default                         // option: 1 = k_blur_sep when the weights allow it, 0 = k_blur_holes_fixed
@@ -263,7 +268,7 @@ cudaError_t dmalloc(T **p, size_t count) { return cudaMalloc(reinterpret_cast<vo
 void free_scratch(Scratch &s) {
     cudaFree(s.frame_max); cudaFree(s.tabs); cudaFree(s.bounds); cudaFree(s.offm);
     cudaFree(s.cutoffs); cudaFree(s.offsets); cudaFree(s.lo16); cudaFree(s.hi16); cudaFree(s.hole_mask);
-    cudaFree(s.hole_list); cudaFree(s.blobs); cudaFree(s.plane);
+    cudaFree(s.hole_list); cudaFree(s.band_map); cudaFree(s.band_list); cudaFree(s.blobs); cudaFree(s.plane);
     s = Scratch{};
 }
 
@@ -271,7 +276,7 @@ int alloc_scratch(vrsbs_ctx *c, Scratch &s, int cap_batch) {
     const size_t B = cap_batch, L = c->max_layers;
     s.cap_batch = cap_batch;
     const size_t mask_words = B * c->max_h * ((c->max_w + 31) / 32);
-    CU_TRY(c, dmalloc(&s.frame_max, 2 * B + 2));
+    CU_TRY(c, dmalloc(&s.frame_max, 2 * B + 4));
     s.frame_nan = s.frame_max + B;
     s.hole_count = s.frame_max + 2 * B;
     CU_TRY(c, dmalloc(&s.tabs, B));
@@ -283,6 +288,12 @@ int alloc_scratch(vrsbs_ctx *c, Scratch &s, int cap_batch) {
     CU_TRY(c, dmalloc(&s.hi16, B * L));
     CU_TRY(c, dmalloc(&s.hole_mask, mask_words));
     CU_TRY(c, dmalloc(&s.hole_list, mask_words));
+    {
+        const size_t words = B * (size_t)((c->max_h + kBandRows - 1) / kBandRows) * (((c->max_w + 31) / 32 + 31) / 32);
+        CU_TRY(c, dmalloc(&s.band_map, words));
+        CU_TRY(c, dmalloc(&s.band_list, words * 32));
+        CU_TRY(c, cudaMemset(s.band_map, 0, words * sizeof(uint32_t)));
+    }
     CU_TRY(c, dmalloc(&s.blobs, B * (size_t)blob_bytes(kEntCapMax, kLutCapMax, true)));
     return VRSBS_OK;
 }
@@ -334,14 +345,14 @@ cudaError_t launch_pdl(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, 
 // ---- stage launchers (stream-ordered, no host sync) ---------------------------------------------------
 int clear_counters(vrsbs_ctx *c, Scratch &s, int B, cudaStream_t st) {
     (void)B;
-    CU_TRY(c, cudaMemsetAsync(s.frame_max, 0, sizeof(uint32_t) * (2 * s.cap_batch + 2), st));
+    CU_TRY(c, cudaMemsetAsync(s.frame_max, 0, sizeof(uint32_t) * (2 * s.cap_batch + 4), st));
     s.holes_dirty = false;
     return VRSBS_OK;
 }
 
 // the hole work list must start empty for every warp launch (a second vrsbs_warp_batch without a depth call in between)
 int fresh_hole_list(vrsbs_ctx *c, Scratch &s, cudaStream_t st) {
-    if (s.holes_dirty) CU_TRY(c, cudaMemsetAsync(s.hole_count, 0, 2 * sizeof(uint32_t), st));   // hole count + blur ticket
+    if (s.holes_dirty) CU_TRY(c, cudaMemsetAsync(s.hole_count, 0, 4 * sizeof(uint32_t), st));   // hole count, blur ticket, band count
     s.holes_dirty = true;
     return VRSBS_OK;
 }
@@ -637,19 +648,76 @@ int launch_blur_sep(vrsbs_ctx *c, const BlurArgs &b, cudaStream_t st) {
     return VRSBS_OK;
 }
 
+// true when launch_blur will run the band-driven kernel for this frame size (the warp kernel then lists the band columns itself)
+bool band_route(const vrsbs_ctx *c, int B, int H, int W, const uint8_t *sbs) {
+    const int cx = c->kx / 2, cy = c->ky / 2;
+    const bool sep = c->blur_sep && c->blur_screen && !c->sep_hy.empty();
+    const bool aligned = (W % 2 == 0) && ((uintptr_t)sbs % 4 == 0);
+    const bool built = (cx == 5 && cy == 4) || (cx == 4 && cy == 3);
+    return c->params.blur && c->blur_band && sep && aligned && built && (c->wparts == 2 || c->wparts == 3) &&
+           (long long)B * ((H + kBandRows - 1) / kBandRows) < (1 << 24) && (W + 31) / 32 <= 256;
+}
+
+// band-driven blur: the list of band columns that hold a hole (unless the warp kernel made it), then one warp per band column
+template <int PARTS, int CX, int CY>
+int launch_blur_band(vrsbs_ctx *c, const BlurArgs &b, cudaStream_t st) {
+    BlurSepWeights<CX, CY> wts;
+    memcpy(wts.hy, c->sep_hy.data(), sizeof(wts.hy));
+    memcpy(wts.hx, c->sep_hx.data(), sizeof(wts.hx));
+    wts.s = c->sep_s; wts.eps32 = c->blur_sep == 2 ? 0x7fffffffu : c->sep_eps32;
+    if (b.band_prepass) {
+        const long long cells = (long long)b.B * b.Hb * b.Wwords;
+        CU_TRY(c, launch_pdl((c->pdl & 4) != 0, k_band_map, dim3((unsigned)((cells + 255) / 256)), dim3(256), 0, st, b));
+        c->launches++;
+    }
+    {
+        const long long words = (long long)b.B * b.Hb * b.band_groups;
+        CU_TRY(c, launch_pdl((c->pdl & 4) != 0, k_band_list, dim3((unsigned)((words + 255) / 256)), dim3(256), 0, st, b));
+        c->launches++;
+    }
+    auto kern = k_blur_band<PARTS, CX, CY>;
+    const int warps = 8;
+    const size_t bsmem = blur_sep_warp_smem<CX>() * warps;
+    CU_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+    int occ = 0;
+    CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, bsmem));
+    if (occ < 1) occ = 1;
+    CU_TRY(c, launch_pdl((c->pdl & 4) != 0, kern, dim3((unsigned)(c->sm_count * occ)), dim3(warps * 32), bsmem, st, b, wts));
+    return VRSBS_OK;
+}
+
 int launch_blur(vrsbs_ctx *c, Scratch &s, const uint8_t *frames, int B, int H, int W, uint8_t *sbs, cudaStream_t st) {
     if (!s.plane) CU_TRY(c, dmalloc(&s.plane, (size_t)s.cap_batch * c->max_h * c->max_w * 3));
     BlurArgs b{};
     b.frames = frames; b.sbs = sbs; b.tabs = s.tabs; b.hole_mask = s.hole_mask; b.hole_list = s.hole_list;
     b.hole_count = s.hole_count; b.ticket = s.hole_count + 1; b.plane = s.plane; b.wq = c->wq; b.weights = c->weights;
+    b.band_list = s.band_list; b.band_count = s.hole_count + 2; b.Hb = (H + kBandRows - 1) / kBandRows;
+    b.magic_hb = ((1ull << 40) + (unsigned long long)b.Hb - 1) / (unsigned long long)b.Hb;
+    b.band_groups = ((W + 31) / 32 + 31) / 32;
+    const bool band = band_route(c, B, H, W, sbs);
+    b.band_map = band ? s.band_map : nullptr;
+    b.band_prepass = (band && !s.band_marked) ? 1 : 0;
+    s.band_marked = false;
     b.B = B; b.H = H; b.W = W; b.Wwords = (W + 31) / 32; b.kx = c->kx; b.ky = c->ky; b.wshift = c->wshift;
     b.magic_h = ((1ull << 40) + (unsigned long long)H - 1) / (unsigned long long)H;
     const int cx = c->kx / 2, cy = c->ky / 2;
     const bool aligned = (W % 2 == 0) && ((uintptr_t)sbs % 4 == 0);
+    bool band_done = false;
     {
         StageTimer timer(c, st, 3);
         bool done = false;
         const bool sep = c->blur_sep && c->blur_screen && !c->sep_hy.empty();
+#define VRSBS_BLUR_BAND(P, CXv, CYv)                                                    \
+        if (!done && band && c->wparts == P && cx == CXv && cy == CYv) {                \
+            int rc = launch_blur_band<P, CXv, CYv>(c, b, st);                           \
+            if (rc) return rc;                                                          \
+            done = true; band_done = true;                                              \
+        }
+        VRSBS_BLUR_BAND(2, 5, 4)       // 1080p: 11 x 9
+        VRSBS_BLUR_BAND(3, 5, 4)
+        VRSBS_BLUR_BAND(2, 4, 3)       // 720p: 9 x 7
+        VRSBS_BLUR_BAND(3, 4, 3)
+#undef VRSBS_BLUR_BAND
 #define VRSBS_BLUR_SEP(P, CXv, CYv)                                                     \
         if (!done && sep && aligned && c->wparts == P && cx == CXv && cy == CYv) {      \
             int rc = launch_blur_sep<P, CXv, CYv>(c, b, st);                            \
@@ -696,7 +764,7 @@ int launch_blur(vrsbs_ctx *c, Scratch &s, const uint8_t *frames, int B, int H, i
         CU_TRY(c, cudaGetLastError());
         c->launches++;
     }
-    return launch_commit(c, b, c->commit_mode, st);
+    return launch_commit(c, b, band_done ? (1 | 4) : c->commit_mode, st);   // (the band route has no per-word list to commit from)
 }
 
 int check_blur_ready(vrsbs_ctx *c, int H, int W) {
@@ -713,6 +781,8 @@ FusedArgs make_fused_args(vrsbs_ctx *c, Scratch &s, const uint8_t *frames, const
     a.sbs = sbs; a.blobs = s.blobs; a.tabs = s.tabs; a.bounds = s.bounds; a.offm = s.offm;
     a.hole_mask = s.hole_mask; a.hole_list = s.hole_list; a.hole_count = s.hole_count;
     a.B = B; a.H = H; a.W = W; a.Lcap = c->max_layers; a.Wwords = (W + 31) / 32;
+    a.band_map = nullptr;
+    a.Hb = (H + kBandRows - 1) / kBandRows; a.band_groups = (a.Wwords + 31) / 32;
     a.first = 0;
     a.skip_right = c->skip_right;
     a.blob_bytes = blob_bytes(c->ent_cap, c->lut_cap, c->f32 != 0); a.ent_bytes = blob_ent_bytes(c->ent_cap, c->f32 != 0); a.key_pad = c->key_pad;
@@ -735,8 +805,10 @@ int launch_warp(vrsbs_ctx *c, Scratch &s, const uint8_t *frames, const void *dep
         const bool al = (W % 32 == 0) && ((uintptr_t)frames % 16 == 0) && ((uintptr_t)depth_v % 16 == 0) && ((uintptr_t)sbs % 16 == 0);
         if (c->f32_fast && c->fused && c->warp_ws && al && c->ent_cap > 0) {      // the warp-specialised kernel's fp32 instantiation
             FusedArgs fa = make_fused_args(c, s, frames, depth, B, H, W, sbs);
+            if (band_route(c, B, H, W, sbs)) fa.band_map = s.band_map;
             bool done = false;
             if ((rc = launch_ws(c, fa, st, &done))) return rc;
+            s.band_marked = done && fa.band_map;
             if (done) {
                 if (!c->params.blur) return VRSBS_OK;
                 return launch_blur(c, s, frames, B, H, W, sbs, st);
@@ -754,8 +826,11 @@ int launch_warp(vrsbs_ctx *c, Scratch &s, const uint8_t *frames, const void *dep
     }
     if (c->fused && fused_capable(c, frames, depth, sbs, W)) {
         FusedArgs a = make_fused_args(c, s, frames, depth, B, H, W, sbs);
+        if (c->warp_ws && band_route(c, B, H, W, sbs)) a.band_map = s.band_map;
         bool done = false;
         if (c->warp_ws) rc = launch_ws(c, a, st, &done);
+        s.band_marked = !rc && done && a.band_map;
+        if (!done) a.band_map = nullptr;                      // the kernels below keep the per-word list
         if (!rc && !done) rc = W <= 2048 ? launch_fused_inst<false, 256>(c, a, st) : launch_fused_inst<false, 512>(c, a, st);
     } else {
         WarpArgs a{};
@@ -1560,6 +1635,7 @@ int vrsbs_set_option(vrsbs_ctx *c, const char *name, int value) {
     else if (!strcmp(name, "f32_fast")) c->f32_fast = value ? 1 : 0;
     else if (!strcmp(name, "blur_screen")) c->blur_screen = value ? 1 : 0;
     else if (!strcmp(name, "blur_sep")) c->blur_sep = value;
+    else if (!strcmp(name, "blur_band")) c->blur_band = value ? 1 : 0;
     else if (!strcmp(name, "pdl")) c->pdl = value & 15;
     else if (!strcmp(name, "host_async")) c->host_async = value ? 1 : 0;
     else if (!strcmp(name, "ws_scatter_warps")) c->ws_scatter_warps = value;

@@ -47,6 +47,9 @@ struct FusedArgs {
     uint32_t *hole_mask;       // [B][H][Wwords]
     uint32_t *hole_list;       // (global row << 8 | word) of every mask word that has a hole (any order)
     uint32_t *hole_count;      // pre-zeroed
+    uint32_t *band_map;        // k_warp_ws, optional: [B*Hb][band_groups] bit per band column (8 rows x one mask word), set when a row of it has
+                               //   a hole; replaces hole_list / hole_count as the work index of k_blur_band and k_blur_commit
+    int Hb, band_groups;       //   row bands per frame (8 rows each), 32-word groups per row
     int B, H, W, Lcap, Wwords;
     int first;                 // frame 0 of the batch is the first frame of the clip range
     int skip_right;            // 1: do not store the right half of the SBS row (the host pipeline's caller already holds it)

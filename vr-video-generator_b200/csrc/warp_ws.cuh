@@ -333,13 +333,17 @@ __global__ void __launch_bounds__(NT, F32 ? 768 / NT : 1024 / NT) k_warp_ws(WsAr
                 const unsigned nz = __ballot_sync(0xffffffffu, v != 0u);
                 if (nz) {
                     const unsigned holes = __reduce_add_sync(0xffffffffu, (unsigned)__popc(v));
-                    uint32_t base = 0;
-                    if (lane == 0) {
-                        base = atomicAdd(a.hole_count, (uint32_t)__popc(nz));
-                        atomicAdd(&a.tabs[t0].holes, (unsigned long long)holes);
+                    if (lane == 0) atomicAdd(&a.tabs[t0].holes, (unsigned long long)holes);
+                    if (a.band_map) {
+                        // k_blur_band / k_blur_commit walk a bitmap of band columns (8 rows x one mask word) that hold a hole: one
+                        // fire-and-forget OR per row and 32-word group, no list slot to wait for
+                        if (lane == 0) atomicOr(a.band_map + ((size_t)t0 * a.Hb + ((uint32_t)y0 >> 3)) * a.band_groups + (dt >> 5), nz);
+                    } else {
+                        uint32_t base = 0;
+                        if (lane == 0) base = atomicAdd(a.hole_count, (uint32_t)__popc(nz));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        if (v) a.hole_list[base + __popc(nz & ((1u << lane) - 1u))] = (row << 8) | (uint32_t)w;
                     }
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (v) a.hole_list[base + __popc(nz & ((1u << lane) - 1u))] = (row << 8) | (uint32_t)w;
                 }
             }
             if (++i3 == 3) { i3 = 0; par3 ^= 1u; }
