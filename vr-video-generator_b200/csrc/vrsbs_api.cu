@@ -43,6 +43,7 @@ struct Scratch {                 // per-batch device scratch; one per pipeline s
                                      // k_band_map, compacted into band_list and cleared by k_band_list)
     uint32_t *band_list = nullptr;   // the marked band columns: work list of k_blur_band and k_blur_commit
     bool band_marked = false;        // the last warp launch marked the band columns itself (otherwise k_band_map does)
+    bool list_missing = false;       // the last warp launch left the per-word hole list to k_word_list
     uint32_t *hole_count = nullptr;  // points into frame_max's allocation: one memset clears all three
     uint8_t *blobs = nullptr;        // [B][kBlobMax] fast-path tables
     uint8_t *plane = nullptr;        // [B,H,W,3] blurred hole values (allocated on first blur)
@@ -188,6 +189,7 @@ struct vrsbs_ctx {
     std::vector<uint32_t> sep_hy, sep_hx;     // separable screening kernel of k_blur_sep (scale 2^sep_s), empty if the weights are not near rank 1
     uint32_t sep_s = 0, sep_eps32 = 0;
     int blur_sep = 1;
+    int ws_no_list = 1;                       // option: 1 = k_warp_ws leaves the per-word hole list to k_word_list (list-driven blur kernels)
     int blur_band = 1;                        // option: 1 = band-driven k_blur_band for the footprints it is built for (1080p, 720p)
     int pdl = 0;                              // option (bit mask): programmatic dependent launch of 1 tables, 2 warp, 4 blur, 8 commit.
                                               // Measured slower than plain stream order with all four edges on (0.532 vs 0.512 ms per
@@ -718,6 +720,13 @@ int launch_blur(vrsbs_ctx *c, Scratch &s, const uint8_t *frames, int B, int H, i
         VRSBS_BLUR_BAND(2, 4, 3)       // 720p: 9 x 7
         VRSBS_BLUR_BAND(3, 4, 3)
 #undef VRSBS_BLUR_BAND
+        if (!done && s.list_missing) {                   // the list-driven kernels below need the per-word list
+            const long long nw = (long long)B * H * b.Wwords;
+            CU_TRY(c, launch_pdl((c->pdl & 4) != 0, k_word_list, dim3((unsigned)((nw + 1023) / 1024)), dim3(1024), 0, st,
+                                 (const uint32_t *)s.hole_mask, s.hole_list, s.hole_count, nw, b.Wwords));
+            c->launches++;
+        }
+        s.list_missing = false;
 #define VRSBS_BLUR_SEP(P, CXv, CYv)                                                     \
         if (!done && sep && aligned && c->wparts == P && cx == CXv && cy == CYv) {      \
             int rc = launch_blur_sep<P, CXv, CYv>(c, b, st);                            \
@@ -806,9 +815,11 @@ int launch_warp(vrsbs_ctx *c, Scratch &s, const uint8_t *frames, const void *dep
         if (c->f32_fast && c->fused && c->warp_ws && al && c->ent_cap > 0) {      // the warp-specialised kernel's fp32 instantiation
             FusedArgs fa = make_fused_args(c, s, frames, depth, B, H, W, sbs);
             if (band_route(c, B, H, W, sbs)) fa.band_map = s.band_map;
+            if (c->params.blur && c->ws_no_list) fa.hole_list = nullptr;
             bool done = false;
             if ((rc = launch_ws(c, fa, st, &done))) return rc;
             s.band_marked = done && fa.band_map;
+            s.list_missing = done && !fa.band_map && !fa.hole_list;
             if (done) {
                 if (!c->params.blur) return VRSBS_OK;
                 return launch_blur(c, s, frames, B, H, W, sbs, st);
@@ -827,10 +838,12 @@ int launch_warp(vrsbs_ctx *c, Scratch &s, const uint8_t *frames, const void *dep
     if (c->fused && fused_capable(c, frames, depth, sbs, W)) {
         FusedArgs a = make_fused_args(c, s, frames, depth, B, H, W, sbs);
         if (c->warp_ws && band_route(c, B, H, W, sbs)) a.band_map = s.band_map;
+        if (c->warp_ws && c->params.blur && c->ws_no_list) a.hole_list = nullptr;
         bool done = false;
         if (c->warp_ws) rc = launch_ws(c, a, st, &done);
         s.band_marked = !rc && done && a.band_map;
-        if (!done) a.band_map = nullptr;                      // the kernels below keep the per-word list
+        s.list_missing = !rc && done && !a.band_map && !a.hole_list;
+        if (!done) { a.band_map = nullptr; a.hole_list = s.hole_list; }    // the kernels below keep the per-word list
         if (!rc && !done) rc = W <= 2048 ? launch_fused_inst<false, 256>(c, a, st) : launch_fused_inst<false, 512>(c, a, st);
     } else {
         WarpArgs a{};
@@ -1636,6 +1649,7 @@ int vrsbs_set_option(vrsbs_ctx *c, const char *name, int value) {
     else if (!strcmp(name, "blur_screen")) c->blur_screen = value ? 1 : 0;
     else if (!strcmp(name, "blur_sep")) c->blur_sep = value;
     else if (!strcmp(name, "blur_band")) c->blur_band = value ? 1 : 0;
+    else if (!strcmp(name, "ws_no_list")) c->ws_no_list = value ? 1 : 0;
     else if (!strcmp(name, "pdl")) c->pdl = value & 15;
     else if (!strcmp(name, "host_async")) c->host_async = value ? 1 : 0;
     else if (!strcmp(name, "ws_scatter_warps")) c->ws_scatter_warps = value;

@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(NT, F32 ? 768 / NT : 1024 / NT) k_warp_ws(WsAr
                         // k_blur_band / k_blur_commit walk a bitmap of band columns (8 rows x one mask word) that hold a hole: one
                         // fire-and-forget OR per row and 32-word group, no list slot to wait for
                         if (lane == 0) atomicOr(a.band_map + ((size_t)t0 * a.Hb + ((uint32_t)y0 >> 3)) * a.band_groups + (dt >> 5), nz);
-                    } else {
+                    } else if (a.hole_list) {                 // (nullptr: k_word_list makes the per-word list from the hole mask)
                         uint32_t base = 0;
                         if (lane == 0) base = atomicAdd(a.hole_count, (uint32_t)__popc(nz));
                         base = __shfl_sync(0xffffffffu, base, 0);
