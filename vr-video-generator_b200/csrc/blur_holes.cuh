@@ -686,29 +686,43 @@ __global__ void __launch_bounds__(1024) k_word_list(const uint32_t *hole_mask, u
     __shared__ uint32_t s_cnt[32], s_base;
     pdl_launch_dependents();
     pdl_wait();
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int V = 4;                              // mask words per thread: a quarter of the CTAs, each one atomic round trip
+    const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * V;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t v = i < nwords ? hole_mask[i] : 0u;
-    const unsigned nz = __ballot_sync(0xffffffffu, v != 0u);
-    if (lane == 0) s_cnt[warp] = (uint32_t)__popc(nz);
+    uint32_t v[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) v[k] = i0 + k < nwords ? hole_mask[i0 + k] : 0u;
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int k = 0; k < V; ++k) cnt += v[k] != 0u;
+    uint32_t incl = cnt;                              // inclusive prefix sum over the warp
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_cnt[warp] = incl;
     __syncthreads();
     if (warp == 0) {                                  // one list-slot request per CTA
         const uint32_t c = lane < (int)(blockDim.x >> 5) ? s_cnt[lane] : 0u;
-        uint32_t incl = c;
+        uint32_t ws = c;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
+            const uint32_t t = __shfl_up_sync(0xffffffffu, ws, d);
+            if (lane >= d) ws += t;
         }
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t total = __shfl_sync(0xffffffffu, ws, 31);
         if (lane == 0) s_base = total ? atomicAdd(hole_count, total) : 0u;
-        s_cnt[lane] = incl - c;                       // exclusive offsets of the warps
+        s_cnt[lane] = ws - c;                         // exclusive offsets of the warps
     }
     __syncthreads();
-    if (v) {
-        const long long row = i / Wwords;
-        hole_list[s_base + s_cnt[warp] + __popc(nz & ((1u << lane) - 1u))] = ((uint32_t)row << 8) | (uint32_t)(i - row * Wwords);
-    }
+    uint32_t at = s_base + s_cnt[warp] + incl - cnt;
+#pragma unroll
+    for (int k = 0; k < V; ++k)
+        if (v[k]) {
+            const long long i = i0 + k, row = i / Wwords;
+            hole_list[at++] = ((uint32_t)row << 8) | (uint32_t)(i - row * Wwords);
+        }
 }
 
 // ---- band-driven hole blur for the small footprints (the footprint of a mask word fits 32 aligned words) ------------

@@ -567,7 +567,8 @@ int launch_ws_inst(vrsbs_ctx *c, const FusedArgs &a, cudaStream_t st, bool *laun
     CU_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.lay.total));
     int occ = 0;
     CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, w.lay.total));
-    if (occ * NT < (F32 ? 512 : 1024)) return VRSBS_OK;   // too few resident warps per SM: k_warp_fused / k_warp_rows do better
+    if (occ * NT < (F32 ? 512 : 768)) return VRSBS_OK;    // too few resident warps per SM: k_warp_fused / k_warp_rows do better (three
+                                                          // 8-warp CTAs still beat k_warp_fused: 0.315 vs 0.338 ms per 64 frames of 1080p)
     if (c->blocks_per_sm > 0 && c->blocks_per_sm < occ) occ = c->blocks_per_sm;
     long long iters = (long long)a.B * a.H, grid = (long long)c->sm_count * occ;
     if (grid > iters) grid = iters;
@@ -722,7 +723,7 @@ int launch_blur(vrsbs_ctx *c, Scratch &s, const uint8_t *frames, int B, int H, i
 #undef VRSBS_BLUR_BAND
         if (!done && s.list_missing) {                   // the list-driven kernels below need the per-word list
             const long long nw = (long long)B * H * b.Wwords;
-            CU_TRY(c, launch_pdl((c->pdl & 4) != 0, k_word_list, dim3((unsigned)((nw + 1023) / 1024)), dim3(1024), 0, st,
+            CU_TRY(c, launch_pdl((c->pdl & 4) != 0, k_word_list, dim3((unsigned)((nw + 4095) / 4096)), dim3(1024), 0, st,
                                  (const uint32_t *)s.hole_mask, s.hole_list, s.hole_count, nw, b.Wwords));
             c->launches++;
         }

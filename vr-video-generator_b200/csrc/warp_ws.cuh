@@ -34,9 +34,11 @@ constexpr int kBarFull = 2, kBarEmpty = 4;      // named barriers 2,3: key row c
 __host__ inline WsLay ws_smem_layout(int W, uint32_t blob_b, int depth_bytes = 2) {
     WsLay s{};
     size_t o = 0;
-    s.img = (uint32_t)o;  s.img_stride = (uint32_t)align_up((size_t)W * 3 + 16, 128);  o += kWsImgSlots * s.img_stride;
+    // (rows only need the 16-byte alignment of the bulk copies: 128-byte strides cost 448 B at 1080p, the difference between three
+    // and four CTAs per SM for offsets like fg .025 / bg -.015 whose LUT is twice the default's)
+    s.img = (uint32_t)o;  s.img_stride = (uint32_t)align_up((size_t)W * 3 + 16, 16);   o += kWsImgSlots * s.img_stride;
     s.dep = (uint32_t)o;  s.dep_stride = (uint32_t)align_up((size_t)W * depth_bytes, 128);   o += kWsDepSlots * s.dep_stride;
-    s.out = (uint32_t)o;  o += align_up((size_t)W * 3 + 16, 128);
+    s.out = (uint32_t)o;  o += align_up((size_t)W * 3 + 16, 16);
     s.keys = (uint32_t)o; s.keys_stride = (uint32_t)align_up((size_t)W * 4, 128);      o += 2 * s.keys_stride;
     s.blob = (uint32_t)o; s.blob_stride = (uint32_t)align_up((size_t)blob_b, 128);     o += 2 * s.blob_stride;
     s.mask = (uint32_t)o; o += align_up((size_t)((W + 31) / 32) * 4, 16);
