@@ -7,7 +7,7 @@ echo "# SASS excerpt of libvrsbs.so (cuobjdump -sass, sm_100a), default route"
 echo
 echo "| kernel | instructions | UBLKCP (bulk copy, TMA engine) | SYNCS (mbarrier) | ATOMS | BAR | REDUX | IDP | UTMALDG / UTMASTG | UTC*MMA |"
 echo "|---|---|---|---|---|---|---|---|---|---|"
-for k in k_depth_passILb1E k_build_tables k_warp_wsILi256ELi4E k_warp_wsILi512ELi8E k_blur_sepILi2ELi5ELi4E k_blur_sepILi3ELi9ELi8E k_blur_commit k_depth_lowres_tiledILb1E; do
+for k in k_depth_passILb1E k_depth_pass_f32 k_build_tables k_warp_wsILi256ELi4ELb0E k_warp_wsILi512ELi8ELb0E k_warp_wsILi256ELi4ELb1E k_band_list k_word_list k_blur_bandILi2ELi5ELi4E k_blur_sepILi3ELi9ELi8E k_blur_commit k_depth_lowres_tiledILb1E; do
   cuobjdump -sass $SO | awk -v k="$k" '/Function :/{f=index($0,k)>0} f{print}' > /tmp/_k.sass
   n=$(grep -cE '^\s+/\*[0-9a-f]{4,5}\*/' /tmp/_k.sass)
   c() { grep -cE "$1" /tmp/_k.sass; }
@@ -20,7 +20,7 @@ echo
 echo "## k_warp_ws<256,4>: one scatter batch of 4 segments without wrap (81 instructions, 8 ATOMS.MAX)"
 echo
 echo '```'
-cuobjdump -sass $SO | awk '/Function : _ZN5vrsbs9k_warp_wsILi256ELi4E/{f=1} f{print} /Function : _ZN5vrsbs9k_warp_wsILi256ELi3E/{if(f) exit}' > /tmp/_ws.sass
+cuobjdump -sass $SO | awk '/Function : /{f=index($0,"k_warp_wsILi256ELi4ELb0E")>0} f{print}' > /tmp/_ws.sass
 python3 - <<'PY'
 import re
 ins=[]
