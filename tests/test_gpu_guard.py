@@ -58,6 +58,7 @@ ROUTES = {
     "row_kernel_atomic": {"fused": 0, "scatter_mode": 2},
     "row_kernel_store": {"fused": 0, "scatter_mode": 1},
     "blur_sep_per_word": {"blur_band": 0},
+    "blur_sep_list_from_warp_kernel": {"blur_band": 0, "ws_no_list": 0},
     "blur_fixed": {"blur_sep": 0},
     "blur_exact_only": {"blur_screen": 0},
 }
