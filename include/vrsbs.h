@@ -173,7 +173,10 @@ int  vrsbs_process_host(vrsbs_ctx *ctx, const uint8_t *frames_host, const void *
  * frames_host may be pitched: row y of frame t starts at frames_host + t * frame_pitch + y * frame_row_pitch
  * (0 = packed).  With VRSBS_HOST_RIGHT_IN_PLACE the caller has decoded its frames straight into the right halves of
  * sbs_host (frames_host = sbs_host + 3W, frame_row_pitch = 6W, frame_pitch = 6WH): the input then never gets copied
- * on the host and only the synthesised left halves come back across PCIe.  depth_host as in vrsbs_process_host. */
+ * on the host and only the synthesised left halves come back across PCIe.  depth_host as in vrsbs_process_host.
+ * Mixing the two entry styles on one context: the device-pointer calls run on the caller's stream, the host calls on the
+ * library's; a host call orders itself behind the device-pointer calls made before it (event), a device-pointer call is
+ * refused (VRSBS_E_STATE) while submitted batches have not been collected. */
 #define VRSBS_HOST_RIGHT_IN_PLACE 1u
 int  vrsbs_submit_host(vrsbs_ctx *ctx, const uint8_t *frames_host, size_t frame_row_pitch, size_t frame_pitch,
                        const void *depth_host, int B, int H, int W, int lowres_h, int lowres_w, float scaler,

@@ -169,3 +169,45 @@ def test_pipelined_worker_with_real_decode_and_encode(tmp_path, oracle_lib):
     ok, img = cap.read()
     assert ok and img.shape == (H, 2 * W, 3)
     assert np.mean(np.abs(img[:, :, ::-1].astype(int) - kept[names[1]][0].astype(int))) < 12
+
+
+def test_mixed_entry_styles_share_the_clip_state(oracle_lib):
+    """Device-pointer calls (caller's stream) and host calls (the library's streams) alternate on one context: the host call
+    orders itself behind the device work (depth history, range EMA), and a device-pointer call is refused while a submitted
+    batch has not been collected.  The frames equal the oracle's walk over the clip."""
+    import argparse
+    import vr_video_generator_b200 as pkg
+    from vr_video_generator_b200 import _native
+    from vr_video_generator_b200.sbs import pinned_sbs_buffer
+    meta, frames, raw, _ = load_case("medium")
+    p = meta["params"]
+    H, W, n = p["H"], p["W"], p["n"]
+    w = golden_weights(meta)
+    proc = pkg.SbsProcessor(None, 0, argparse.Namespace(offset_fg=p["fg"], offset_bg=p["bg"], offset_step_size=p["step"]), device=0, max_batch=4)
+    proc._context(H, W, False).set_blur_weights(w)
+    st = O.WarpState(p["fg"], p["bg"], p["step"])
+    want = [oracle_lib.process_frame(st, frames[t], raw[t], weights=w) for t in range(n)]
+    side = torch.cuda.Stream()
+    outs = []
+    for t in range(n):
+        if t % 2 == 0:                                        # device-pointer call on a side stream, not synchronised by the caller
+            with torch.cuda.stream(side):
+                f = torch.from_numpy(frames[t:t + 1]).cuda()
+                r = torch.from_numpy(raw[t:t + 1]).cuda()
+                o = proc.warp_batch_device(f, r)
+            outs.append(o)
+        else:                                                 # host call right behind it
+            outs.append(proc.left_side_sbs_batch(frames[t:t + 1], raw[t:t + 1]))
+    torch.cuda.synchronize()
+    for t in range(n):
+        got = outs[t].cpu().numpy()[0] if isinstance(outs[t], torch.Tensor) else outs[t][0]
+        assert np.array_equal(got, want[t]), t
+    # a submitted batch blocks the device-pointer entry until it is collected
+    proc.reset_state()
+    out, view, _keep = pinned_sbs_buffer(1, H, W)
+    np.copyto(view, frames[:1])
+    ticket = proc.submit_batch(view, torch.from_numpy(raw[:1]).pin_memory(), out)
+    with pytest.raises(_native.VrsbsError):
+        proc.warp_batch_device(torch.from_numpy(frames[:1]).cuda(), torch.from_numpy(raw[:1]).cuda())
+    proc.collect(ticket)
+    proc.close()

@@ -224,6 +224,8 @@ struct vrsbs_ctx {
     int slot_n[kSlots] = {0, 0, 0}, slot_first[kSlots] = {0, 0, 0};
     long long chunk_seq = 0;             // chunks enqueued so far: slot = chunk_seq % kSlots
     cudaEvent_t dep_event = nullptr;     // vrsbs_host_depends_on
+    cudaStream_t last_dev_stream = nullptr;   // stream of the last device-pointer call that touched the clip state ...
+    bool dev_state_dirty = false;        // ... since the host pipeline last ordered itself behind it (mixed_entry_sync)
     // options / accounting
     int scatter_mode = 2;
     int bicubic_contract = 1;
@@ -952,6 +954,17 @@ int frame_status_error(vrsbs_ctx *c, const FrameTab *tabs, int B, int first_inde
     return VRSBS_OK;
 }
 
+// The device-pointer calls run on the caller's stream, the host pipeline on the context's own streams; both share the depth
+// history and the range state.  A host call that follows device-pointer calls orders its kernel stream behind them.
+int mixed_entry_sync(vrsbs_ctx *c) {
+    if (!c->dev_state_dirty || !c->st_k) { c->dev_state_dirty = c->dev_state_dirty && !c->st_k; return VRSBS_OK; }
+    if (!c->dep_event) CU_TRY(c, cudaEventCreateWithFlags(&c->dep_event, cudaEventDisableTiming));
+    CU_TRY(c, cudaEventRecord(c->dep_event, c->last_dev_stream));
+    CU_TRY(c, cudaStreamWaitEvent(c->st_k, c->dep_event, 0));
+    c->dev_state_dirty = false;
+    return VRSBS_OK;
+}
+
 }  // namespace
 
 // =========================================================================================================
@@ -1192,6 +1205,8 @@ int vrsbs_depth_from_lowres(vrsbs_ctx *c, const void *lo, int B, int h, int w, f
     if (rc) return rc;
     if (!lo || !out || h < 1 || w < 1) return fail(c, VRSBS_E_INVALID, "bad low-res depth arguments");
     DeviceGuard g(c->device);
+    if (!c->inflight.empty()) return fail(c, VRSBS_E_STATE, "device-pointer call with submitted host batches not yet collected");
+    c->last_dev_stream = (cudaStream_t)stream; c->dev_state_dirty = true;
     return launch_depth(c, c->scratch[0], nullptr, (const __half *)lo, B, H, W, h, w, scaler, out, (cudaStream_t)stream);
 }
 
@@ -1200,6 +1215,8 @@ int vrsbs_depth_from_full(vrsbs_ctx *c, const void *raw, int B, int H, int W, vo
     if (rc) return rc;
     if (!raw || !out) return fail(c, VRSBS_E_INVALID, "NULL depth pointer");
     DeviceGuard g(c->device);
+    if (!c->inflight.empty()) return fail(c, VRSBS_E_STATE, "device-pointer call with submitted host batches not yet collected");
+    c->last_dev_stream = (cudaStream_t)stream; c->dev_state_dirty = true;
     return launch_depth(c, c->scratch[0], raw, nullptr, B, H, W, 0, 0, 1.f, out, (cudaStream_t)stream);
 }
 
@@ -1207,6 +1224,8 @@ int vrsbs_build_tables(vrsbs_ctx *c, int B, int H, int W, void *stream) {
     int rc = check_dims(c, B, H, W);
     if (rc) return rc;
     DeviceGuard g(c->device);
+    if (!c->inflight.empty()) return fail(c, VRSBS_E_STATE, "device-pointer call with submitted host batches not yet collected");
+    c->last_dev_stream = (cudaStream_t)stream; c->dev_state_dirty = true;
     return launch_tables(c, c->scratch[0], B, H, W, (cudaStream_t)stream);
 }
 
@@ -1215,6 +1234,8 @@ int vrsbs_warp_batch(vrsbs_ctx *c, const uint8_t *frames, const void *depth, int
     if (rc) return rc;
     if (!frames || !depth || !sbs) return fail(c, VRSBS_E_INVALID, "NULL buffer");
     DeviceGuard g(c->device);
+    if (!c->inflight.empty()) return fail(c, VRSBS_E_STATE, "device-pointer call with submitted host batches not yet collected");
+    c->last_dev_stream = (cudaStream_t)stream; c->dev_state_dirty = true;
     return launch_warp(c, c->scratch[0], frames, depth, B, H, W, sbs, (cudaStream_t)stream);
 }
 
@@ -1224,6 +1245,8 @@ int vrsbs_process_batch(vrsbs_ctx *c, const uint8_t *frames, const void *raw, in
     if (rc) return rc;
     if (!frames || !raw || !sbs) return fail(c, VRSBS_E_INVALID, "NULL buffer");
     DeviceGuard g(c->device);
+    if (!c->inflight.empty()) return fail(c, VRSBS_E_STATE, "device-pointer call with submitted host batches not yet collected");
+    c->last_dev_stream = (cudaStream_t)stream; c->dev_state_dirty = true;
     cudaStream_t st = (cudaStream_t)stream;
     Scratch &s = c->scratch[0];
     fast_caps(c, H, W, &c->ent_cap, &c->lut_cap);
@@ -1283,6 +1306,7 @@ int vrsbs_process_host(vrsbs_ctx *c, const uint8_t *frames, const void *depth, i
     CopyPool *pool = c->pool;
     fast_caps(c, H, W, &c->ent_cap, &c->lut_cap);
     if ((rc = check_blur_ready(c, H, W))) return rc;
+    if ((rc = mixed_entry_sync(c))) return rc;
     const bool use_fused = !c->f32 && !dev_d && !lowres && c->fused && c->smooth_in_warp && ((size_t)H * W) % 8 == 0 &&
                            fused_capable(c, c->slot[0].dev_frames, c->slot[0].dev_depth_in, c->slot[0].dev_sbs, W);
 
@@ -1481,6 +1505,7 @@ int vrsbs_submit_host(vrsbs_ctx *c, const uint8_t *frames, size_t frame_row_pitc
     }
     fast_caps(c, H, W, &c->ent_cap, &c->lut_cap);
     if ((rc = check_blur_ready(c, H, W))) return rc;
+    if ((rc = mixed_entry_sync(c))) return rc;
     const bool plain = frame_row_pitch == row3 && frame_pitch == fb;
     // without the in-place layout the right halves are the caller's own frames: copied host to host by the pool
     const bool host_right = !in_place && c->host_right_half != 0;
