@@ -846,9 +846,18 @@ __global__ void __launch_bounds__(256, 4) k_blur_band(BlurArgs a, const __grid_c
             const uint8_t *colp = left + (3 * (xw - CX) - PHASE) + 4 * lane;
             const bool wl = NWORDS >= 32 || lane < NWORDS;
             uint32_t raw[NR];
+            if (y0 - CY >= 0 && y0 + RB - 1 + CY < H) {                // no reflected row: walk down the column
+                const uint8_t *rp = colp + (size_t)(y0 - CY) * pitch;
 #pragma unroll
-            for (int j = 0; j < NR; ++j)
-                raw[j] = (wl && ((need >> j) & 1u)) ? __ldg(reinterpret_cast<const uint32_t *>(colp + (size_t)reflect_idx(y0 - CY + j, H) * pitch)) : 0u;
+                for (int j = 0; j < NR; ++j) {
+                    raw[j] = (wl && ((need >> j) & 1u)) ? __ldg(reinterpret_cast<const uint32_t *>(rp)) : 0u;
+                    rp += pitch;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < NR; ++j)
+                    raw[j] = (wl && ((need >> j) & 1u)) ? __ldg(reinterpret_cast<const uint32_t *>(colp + (size_t)reflect_idx(y0 - CY + j, H) * pitch)) : 0u;
+            }
             uint32_t lo[NR], hi[NR];
 #pragma unroll
             for (int j = 0; j < NR; ++j) {
