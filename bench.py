@@ -38,7 +38,7 @@ WORKLOADS = {
     "1080p_stress_b64": dict(H=1080, W=1920, B=64, fg=0.025, bg=-0.015, step=1, depth="stress"),
 }
 ranks = None
-ROUTE = "default (k_depth_pass, k_build_tables, k_warp_ws, k_blur_holes_fixed, k_blur_commit)"
+ROUTE = "default (k_depth_pass, k_build_tables, k_warp_ws, k_band_list + k_blur_band [1080p] / k_word_list + k_blur_sep [4K], k_blur_commit)"
 METRIC = "sbs_frames_per_sec_warp_stage"
 UNIT = "frames/s"
 
