@@ -27,7 +27,7 @@ def _sha(a):
 # (store+verify / atomicMax); 3 default route with the slow membership path; 4 smoothing inside the warp kernel
 # (k_warp_fused<true>, no smoothed depth in HBM); 5 = 4 with the slow membership path; 6 = default route with the
 # barrier-synchronised k_warp_fused<false> instead of the warp-specialised k_warp_ws
-MODES = [0, 1, 2, 3, 4, 5, 6]
+MODES = [0, 1, 2, 3, 4, 5, 6, 7]       # 7: default kernels with the per-word blur (k_word_list + k_blur_sep) instead of the band-driven one
 
 
 def _ctx(H, W, fg, bg, step, weights=None, blur=True, max_batch=8, max_layers=512, mode=0, f32=False):
@@ -41,6 +41,7 @@ def _ctx(H, W, fg, bg, step, weights=None, blur=True, max_batch=8, max_layers=51
     ctx.set_option("fast_tables", 0 if mode in (3, 5) else 1)
     ctx.set_option("smooth_in_warp", 1 if mode in (4, 5) else 0)
     ctx.set_option("warp_ws", 0 if mode == 6 else 1)
+    ctx.set_option("blur_band", 0 if mode == 7 else 1)
     if mode in (1, 2):
         ctx.set_option("scatter_mode", mode)
     return ctx
@@ -92,7 +93,7 @@ def test_small_cases_match_reference(name, mode, oracle_lib):
     for t in range(p["n"]):
         fm = meta["frames"][t]
         # T7 (smoothing half): fp16 bit-exact (modes 4/5 never materialise the smoothed depth)
-        if mode in (0, 1, 2, 3, 6):
+        if mode in (0, 1, 2, 3, 6, 7):
             assert np.array_equal(dep[t].view(np.uint16), stages[t]["depth"].view(np.uint16))
         # T1 (summary; the full lists are checked in test_device_tables_equal_reference_lists)
         assert infos[t].layers == fm["layers"] and infos[t].limit_step == fm["limit"]
