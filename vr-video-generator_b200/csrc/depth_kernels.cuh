@@ -475,7 +475,8 @@ __global__ void __launch_bounds__(256) k_depth_pass_f32(DepthArgs32 a) {
 // output pixels (two adjacent columns, rows ty and ty + 8) for all frames of the batch, history in registers.
 constexpr int kLrTileW = 64, kLrTileH = 16;
 
-template <bool CONTRACT, bool INTERIOR>
+// FULL: the whole 64 x 16 tile lies inside the frame (all but the last row of tiles at 1080p): no per-pixel bounds predicates
+template <bool CONTRACT, bool INTERIOR, bool FULL = false>
 __device__ __forceinline__ void depth_lowres_tile(const DepthArgs &a, int rmax, int cmax, uint8_t *lr_smem) {
     float *R = reinterpret_cast<float *>(lr_smem);                          // [rmax][64] row interpolations
     float *Tin = R + rmax * kLrTileW;                                       // [2][rmax][cmax] staged input tile (as fp32)
@@ -532,7 +533,7 @@ __device__ __forceinline__ void depth_lowres_tile(const DepthArgs &a, int rmax, 
         e_src[q] = (rbase + r) * a.w + cbase + col;
         e_dst[q] = r * cmax + col;
     }
-    const bool pair_ok = xin[0] && xin[1];
+    const bool pair_ok = FULL || (xin[0] && xin[1]);
     auto pix = [&](int j) { return (size_t)(ty0 + warp + 8 * j) * a.W + x0; };
     auto ld2 = [&](const __half *p, size_t i) -> float2 {
         if (pair_ok) return __half22float2(*reinterpret_cast<const __half2 *>(p + i));
@@ -545,7 +546,7 @@ __device__ __forceinline__ void depth_lowres_tile(const DepthArgs &a, int rmax, 
     // raw depth of t-1 / t-2 at my 2 x 2 pixels, as floats (exact fp16 values)
     float2 p1[2], p2[2];
     p1[0] = p1[1] = p2[0] = p2[1] = make_float2(0.f, 0.f);
-    const bool on[2] = {yin[0] && xin[0], yin[1] && xin[0]};
+    const bool on[2] = {FULL || (yin[0] && xin[0]), FULL || (yin[1] && xin[0])};
     if (!a.first) {
 #pragma unroll
         for (int j = 0; j < 2; ++j)
@@ -649,7 +650,9 @@ __global__ void __launch_bounds__(256, 3) k_depth_lowres_tiled(DepthArgs a, int 
     const int xlast = min(tx0 + kLrTileW - 1, a.W - 1), ylast = min(ty0 + kLrTileH - 1, a.H - 1);
     const bool interior = (int)floorf(__fmul_rn(a.scale_x, (float)tx0)) >= 1 && (int)floorf(__fmul_rn(a.scale_x, (float)xlast)) + 2 <= a.w - 1 &&
                           (int)floorf(__fmul_rn(a.scale_y, (float)ty0)) >= 1 && (int)floorf(__fmul_rn(a.scale_y, (float)ylast)) + 2 <= a.h - 1;
-    if (interior) depth_lowres_tile<CONTRACT, true>(a, rmax, cmax, lr_smem);
+    const bool full = tx0 + kLrTileW <= a.W && ty0 + kLrTileH <= a.H;
+    if (interior && full) depth_lowres_tile<CONTRACT, true, true>(a, rmax, cmax, lr_smem);
+    else if (interior) depth_lowres_tile<CONTRACT, true>(a, rmax, cmax, lr_smem);
     else depth_lowres_tile<CONTRACT, false>(a, rmax, cmax, lr_smem);
     __syncthreads();
     for (int t = threadIdx.x; t < a.B; t += blockDim.x) {
