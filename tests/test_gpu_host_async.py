@@ -224,3 +224,51 @@ def test_mixed_entry_styles_share_the_clip_state(oracle_lib):
         proc.warp_batch_device(torch.from_numpy(frames[:1]).cuda(), torch.from_numpy(raw[:1]).cuda())
     proc.collect(ticket)
     proc.close()
+
+
+def test_many_batches_through_the_pipeline_stay_exact(oracle_lib):
+    """Soak: 90 batches of varying length through submit / collect (three scratch sets in rotation, two batches in flight,
+    clip state reset in between) and through the device-pointer call on one context, with the 1080p blur footprint (11 x 9:
+    the band-driven blur); every batch equals the oracle's frames.  Guards the per-batch bookkeeping that must return to its
+    initial state (work counters, the blur's band map)."""
+    import argparse
+    import vr_video_generator_b200 as pkg
+    from vr_video_generator_b200.sbs import pinned_sbs_buffer
+    meta, frames, raw, ref_left = load_case("medium")
+    p = meta["params"]
+    H, W, n = p["H"], p["W"], p["n"]
+    proc = pkg.SbsProcessor(None, 0, argparse.Namespace(offset_fg=p["fg"], offset_bg=p["bg"], offset_step_size=p["step"]), device=0, max_batch=8)
+    w = O.gaussian_weights(11, 9)
+    proc._context(H, W, False).set_blur_weights(w)
+    st = O.WarpState(p["fg"], p["bg"], p["step"])
+    ref_left = np.stack([oracle_lib.process_frame(st, frames[t], raw[t], weights=w) for t in range(n)])[:, :, :W]
+    ring = [pinned_sbs_buffer(n, H, W) for _ in range(2)]
+    d_pin = torch.from_numpy(np.ascontiguousarray(raw)).pin_memory()
+    f_dev, r_dev = torch.from_numpy(frames).cuda(), torch.from_numpy(raw).cuda()
+    pending = None
+    for it in range(90):
+        k = 1 + it % n                                         # batch of the clip's first k frames
+        if it % 5 == 4:                                        # every fifth batch through the device-pointer entry
+            if pending is not None:
+                t, buf, kk = pending
+                proc.collect(t)
+                assert np.array_equal(buf[0][:kk, :, :W], ref_left[:kk]), it
+                pending = None
+            proc.reset_state()
+            out = proc.warp_batch_device(f_dev[:k], r_dev[:k], check=True)
+            assert np.array_equal(out.cpu().numpy()[:, :, :W], ref_left[:k]), it
+            continue
+        buf = ring[it & 1]
+        if pending is not None:                                # the clip state is per batch here: collect before the reset
+            t, pbuf, kk = pending
+            proc.collect(t)
+            assert np.array_equal(pbuf[0][:kk, :, :W], ref_left[:kk]), it
+            assert np.array_equal(pbuf[0][:kk, :, W:], frames[:kk]), it
+        proc.reset_state()
+        np.copyto(buf[1][:k], frames[:k])
+        pending = (proc.submit_batch(buf[1][:k], d_pin[:k], buf[0][:k]), buf, k)
+    if pending is not None:
+        t, buf, kk = pending
+        proc.collect(t)
+        assert np.array_equal(buf[0][:kk, :, :W], ref_left[:kk])
+    proc.close()
