@@ -215,6 +215,9 @@ int  vrsbs_get_stage_times(vrsbs_ctx *ctx, double ms[VRSBS_NUM_STAGES], uint64_t
  *   "scatter_mode" of the general row kernel (2 = atomicMax for every key, 1 = plain store + verify),
  *   "blur_sep" (1 = separable screening kernel k_blur_sep when the weights are near rank 1, 0 = k_blur_holes_fixed,
  *   2 = k_blur_sep with every value sent to its exact fallback),
+ *   "blur_band" (1 = band-driven k_blur_band where it is built - the 1080p and 720p footprints -, 0 = per-word k_blur_sep),
+ *   "ws_no_list" (1 = k_warp_ws leaves the per-word hole list to k_word_list), "f32_fast" (1 = the vectorised fp32 depth pass
+ *   and the warp-specialised kernel's fp32 instantiation, 0 = the general fp32 kernels),
  *   "blur_screen" (1 = screening sum before the exact integer blur, 0 = exact sum for every hole),
  *   "commit_mode", "lowres_tiled", "bicubic_contract", "blocks_per_sm", "host_chunk", "copy_threads",
  *   "pageable_direct", "host_right_half", "host_async" (0 = page-locked callers of vrsbs_process_host use the blocking
