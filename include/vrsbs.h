@@ -152,7 +152,7 @@ int  vrsbs_process_batch(vrsbs_ctx *ctx, const uint8_t *frames_dev, const void *
  * (`.cpu().numpy()`, PredictAndGenerate.py:197) for B frames with HOST buffers.  depth_host is
  * either full-res raw depth [B,H,W] fp16 (lowres_h = lowres_w = 0) or DPT low-res [B,h,w] fp16.
  * Internally pipelined: three streams (H2D / kernels / D2H) and three pinned slots; frames are
- * processed in chunks ("host_chunk", default 4) so copy-in, kernels and copy-out of neighbouring
+ * processed in chunks ("host_chunk", default 8) so copy-in, kernels and copy-out of neighbouring
  * chunks overlap.  Only the synthesised (left) half of every SBS row crosses PCIe on the way back;
  * the right half is the caller's own frame and is copied host-to-host by the library's copy threads
  * (option "host_right_half", default 1).  Returns after sbs_host is complete (like the reference's
