@@ -28,7 +28,9 @@ struct TableArgs {
     int step, B, H, W, Lcap;
     int ent_cap, lut_cap;        // capacity of the blob's entry table (layers) and cell LUT (bytes)
     int key_pad;                 // fast path: every signed offset (shortest way round the row) must satisfy |off| <= key_pad
-    int f32;                     // 1: the depth is fp32 - bounds narrowed double -> float only, no fast-path tables
+    int f32;                     // 1: the depth is fp32 - bounds narrowed double -> float, fp32 cell LUT
+    float cell_width;            // host estimate of the widest valid LUT cell in depth units (0.85 * 0.9 * layer width): where the
+                                 // search for the cell shift starts (any shift that validates is correct)
 };
 
 // LUT value for the cell of depth values [vmin, vmax] (monotone bounds required): e such that every
@@ -221,8 +223,17 @@ __global__ void __launch_bounds__(256) k_build_tables(TableArgs a) {
     }
     int shift = -1;
     uint32_t ncells = 0, lbase = 0;
+    // first shift to try: one coarser than the estimate for the binade of the frame maximum (the search walks towards finer
+    // cells until one validates; starting at the coarsest shift cost four or five failed passes per frame)
+    int sh_est = 0;
+    if (fmax > 0.f && a.cell_width > 0.f) {
+        int e2;
+        frexpf(fmax, &e2);                                     // fmax = m * 2^e2, m in [0.5, 1): binade exponent e2 - 1
+        const float ulp = ldexpf(1.f, e2 - 1 - (f32 ? 23 : 10));
+        while (sh_est < 30 && ulp * (float)(2u << sh_est) <= a.cell_width) ++sh_est;
+    }
     if (ok && !f32) {
-        for (int sh = 9; sh >= 0; --sh) {
+        for (int sh = min(9, sh_est + 1); sh >= 0; --sh) {
             const uint32_t nc = (maxbits >> sh) + 1;
             if (nc + 1 > (uint32_t)a.lut_cap) break;
             int valid = 1;
@@ -243,7 +254,7 @@ __global__ void __launch_bounds__(256) k_build_tables(TableArgs a) {
     } else if (ok) {
         // fp32 depth: cell = max(bits >> sh, base) - base, base = the cell of 2^-6; cell 0 holds every value in [0, end of that
         // cell], the last cell every negative value.  From 8 cells per binade (sh = 20) down to 1024 (sh = 13).
-        for (int sh = 20; sh >= 13; --sh) {
+        for (int sh = max(13, min(20, sh_est + 1)); sh >= 13; --sh) {
             const uint32_t cb = kF32LutFloorBits >> sh;
             const uint32_t top = max(maxbits >> sh, cb);
             const uint32_t nc = top - cb + 1;

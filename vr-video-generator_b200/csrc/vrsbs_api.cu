@@ -499,6 +499,10 @@ int launch_tables(vrsbs_ctx *c, Scratch &s, int B, int H, int W, cudaStream_t st
     a.offset_fg = c->params.offset_fg; a.offset_bg = c->params.offset_bg; a.step = c->params.offset_step_size;
     a.B = B; a.H = H; a.W = W; a.Lcap = c->max_layers; a.f32 = c->f32;
     fast_caps(c, H, W, &c->ent_cap, &c->lut_cap);
+    {
+        const double span_per_limit = fabs(c->params.offset_fg - c->params.offset_bg) * H / 14.0;
+        a.cell_width = span_per_limit > 0 ? (float)(0.85 * 0.9 * c->params.offset_step_size / span_per_limit) : 0.f;
+    }
     a.blobs = s.blobs; a.ent_cap = c->ent_cap; a.lut_cap = c->lut_cap; a.key_pad = c->key_pad;
     const size_t smem = sizeof(double) * 2 * (size_t)(c->max_layers + 2 > B ? c->max_layers + 2 : B) +
                         sizeof(int) * (size_t)(c->max_layers + 2);
