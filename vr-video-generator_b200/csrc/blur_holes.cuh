@@ -3,7 +3,9 @@
 // The reference blurs the whole filled frame with a (2k+1)x(2k+3) fp32 gaussian (torchvision
 // gaussian_blur: reflect padding, one depthwise conv, round_) and keeps the result only at hole
 // pixels.  Here only hole pixels are evaluated.  The warp kernel leaves (a) the FILLED pre-blur view in
-// the SBS frame, (b) a hole bitmask and (c) a list of the mask words that contain holes.
+// the SBS frame, (b) a hole bitmask and (c) a work index: a bitmap of the band columns (8 rows x one mask word) that hold a hole
+// (k_warp_ws -> k_band_list -> k_blur_band, the default at 1080p / 720p) or a list of the mask words that contain holes
+// (from the warp kernel or from k_word_list; k_blur_sep, k_blur_holes_fixed, k_blur_holes).
 //
 //   k_blur_holes  : one warp per listed mask word (32 pixels of one row).  The warp stages the word's
 //                   footprint (ky rows x (32 + kx - 1) pixels, reflect padded) once, as per-byte-column

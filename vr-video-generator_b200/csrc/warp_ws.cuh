@@ -7,7 +7,8 @@
 //   scatter warps, row n:  wait in_full[n%3] (TMA data, mbarrier) and k_empty[n&1]  ->  atomicMax keys into keys[n&1]
 //                          ->  arrive k_full[n&1]                     (and go straight on to row n+1)
 //   destination warps:     wait in_full[n%3] and k_full[n&1]  ->  read + re-zero keys[n&1], fill holes, pack the
-//                          row  ->  bulk stores  ->  arrive k_empty[n&1]  ->  mask flush, TMA loads of row n+2
+//                          row  ->  bulk stores  ->  arrive k_empty[n&1]  ->  mask flush (hole mask row, band-column bitmap or
+//                          per-word list for the blur), TMA loads of row n+2
 //
 // k_full / k_empty are hardware named barriers (bar.arrive by the producer group, bar.sync by the consumer group):
 // a parked consumer issues nothing, whereas mbarrier try_wait loops spent 23 % of the kernel's issue slots on
