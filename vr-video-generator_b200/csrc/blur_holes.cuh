@@ -935,7 +935,7 @@ __global__ void __launch_bounds__(256, 4) k_blur_band(BlurArgs a, const __grid_c
 // plane -> SBS frame for the listed holes right of the strip, then result_img[:, 0:strip] = img[:, 0:strip]
 // (PredictAndGenerate.py:196).  A warp takes 32 list entries at a time: lane l fetches entry l's word index, mask
 // and strip (one round of dependent loads for 32 entries), then the warp walks the entries, lane = pixel.
-__global__ void __launch_bounds__(256, 6) k_blur_commit(BlurArgs a, int do_commit) {
+__global__ void __launch_bounds__(256, 8) k_blur_commit(BlurArgs a, int do_commit) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     pdl_wait();                                  // every blurred value is in the plane
     if ((do_commit & 1) && (do_commit & 4)) {
@@ -953,23 +953,26 @@ __global__ void __launch_bounds__(256, 6) k_blur_commit(BlurArgs a, int do_commi
                 if (strip > xw) m = (strip - xw >= 32) ? 0u : (m & ~((1u << (strip - xw)) - 1u));
             }
             const size_t px0 = ((size_t)t * a.H + y0) * a.W + w * 32u + lane;
-            uint32_t val[kBandRows];
-            bool on[kBandRows];
 #pragma unroll
-            for (int r = 0; r < kBandRows; ++r) {
-                on[r] = (__shfl_sync(0xffffffffu, m, r) >> lane) & 1u;
-                val[r] = 0u;
-                if (on[r]) {
-                    const uint8_t *src = a.plane + (px0 + (size_t)r * a.W) * 3;
-                    val[r] = (uint32_t)src[0] | ((uint32_t)src[1] << 8) | ((uint32_t)src[2] << 16);
+            for (int r0 = 0; r0 < kBandRows; r0 += 4) {          // four rows at a time: four load chains per lane, no spills
+                uint32_t val[4];
+                bool on[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    on[k] = (__shfl_sync(0xffffffffu, m, r0 + k) >> lane) & 1u;
+                    val[k] = 0u;
+                    if (on[k]) {
+                        const uint8_t *src = a.plane + (px0 + (size_t)(r0 + k) * a.W) * 3;
+                        val[k] = (uint32_t)src[0] | ((uint32_t)src[1] << 8) | ((uint32_t)src[2] << 16);
+                    }
                 }
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (on[k]) {
+                        uint8_t *dst = a.sbs + (((size_t)t * a.H + y0 + r0 + k) * 2 * a.W + w * 32u + lane) * 3;
+                        dst[0] = (uint8_t)val[k]; dst[1] = (uint8_t)(val[k] >> 8); dst[2] = (uint8_t)(val[k] >> 16);
+                    }
             }
-#pragma unroll
-            for (int r = 0; r < kBandRows; ++r)
-                if (on[r]) {
-                    uint8_t *dst = a.sbs + (((size_t)t * a.H + y0 + r) * 2 * a.W + w * 32u + lane) * 3;
-                    dst[0] = (uint8_t)val[r]; dst[1] = (uint8_t)(val[r] >> 8); dst[2] = (uint8_t)(val[r] >> 16);
-                }
         }
     }
     const uint32_t count = ((do_commit & 1) && !(do_commit & 4)) ? *a.hole_count : 0u;   // do_commit: bit 0 = hole values, bit 1 = skip the strip (experiments)
